@@ -1,0 +1,214 @@
+/*
+ * ubm.h — C ABI of libubm.so, the B200-native engine for the coupled-chain hot path of
+ * pierrejacob/unbiasedmcmc.
+ *
+ * This is the drop-in boundary.  In the reference the boundary is R `.Call` into the 28
+ * `RcppExport SEXP _unbiasedmcmc_*` wrappers registered in src/RcppExports.cpp:388-423, one coupled
+ * pair per call, driven by the interpreted loops in R/coupled_chains.R:39-87, R/meetingtime.R:24-48 and
+ * R/unbiasedestimator.R:43-104.  A GPU cannot run R closures, so the replacement boundary is BATCHED:
+ * one call runs `nrep` independent replicates of a registered model to completion on the device.
+ *
+ * Conventions
+ *   - plain C, no C++/torch/SEXP types; every function returns an int status (UBM_OK == 0);
+ *     ubm_last_error(handle) gives the message for the last non-zero status on that handle.
+ *   - the caller owns every buffer it passes; the library keeps no caller pointer after return.
+ *     Unless a name ends in `_dev`, pointers are HOST pointers and the call is synchronous.
+ *   - matrices are column-major (R layout) unless stated; indices are 0-based (the R shim converts).
+ *   - there is NO CPU fallback: without a CUDA device ubm_create fails with UBM_ERR_CUDA.
+ *   - replicate r of a call uses global index rep_offset + r; draws are keyed by (seed, global index),
+ *     so results do not depend on how replicates are split over calls, GPUs or thread blocks.
+ */
+#ifndef UBM_H
+#define UBM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UBM_OK 0
+#define UBM_ERR_INVALID 1      /* bad argument (the R layer's print("error...") / stop() cases) */
+#define UBM_ERR_CUDA 2         /* CUDA runtime error or no device */
+#define UBM_ERR_UNSUPPORTED 3  /* model / option not in the device registry (no CPU fallback) */
+#define UBM_ERR_TAPE 4         /* replay tape exhausted */
+#define UBM_ERR_NOMEM 5
+
+typedef struct ubm_handle ubm_handle;
+
+/* ---------------------------------------------------------------------------------------------
+ * handle
+ * ------------------------------------------------------------------------------------------- */
+int ubm_create(int device, ubm_handle** out);
+int ubm_destroy(ubm_handle* h);
+const char* ubm_last_error(const ubm_handle* h);
+/* device name, SM count, and the library's build arch, for logs */
+int ubm_device_info(const ubm_handle* h, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
+int64_t ubm_launch_count(const ubm_handle* h);
+
+/* ---------------------------------------------------------------------------------------------
+ * draw sources.  Replaces R's global RNG stream (GetRNGstate/PutRNGstate brackets, e.g.
+ * src/mvnorm.cpp:15-17).  PHILOX: typed counter-based streams of include/ubm_numerics.h.
+ * TAPE: replay mode — three typed tapes per replicate (uniforms, standard normals, Exp(1) draws)
+ * consumed in the order of SURVEY.md Appendix A; running off a tape is UBM_ERR_TAPE.
+ * ------------------------------------------------------------------------------------------- */
+#define UBM_DRAWS_PHILOX 0
+#define UBM_DRAWS_TAPE 1
+
+typedef struct {
+  int32_t mode;
+  int32_t reserved;
+  uint64_t seed;          /* PHILOX */
+  const double* tape_u;   /* TAPE: [nrep][len_u] row-major */
+  const double* tape_n;   /*       [nrep][len_n] */
+  const double* tape_e;   /*       [nrep][len_e] */
+  int64_t len_u, len_n, len_e;
+} ubm_draws;
+
+/* ---------------------------------------------------------------------------------------------
+ * model registry (north_star: "targets are chosen from a device-side registry").
+ * A model bundles what the reference passes as the three closures single_kernel / coupled_kernel /
+ * rinit (R/coupled_chains.R:39).
+ * ------------------------------------------------------------------------------------------- */
+#define UBM_COUPLING_REFLECTION_MAX 0  /* R/rnorm_reflectionmax.R:18, src/mvnorm.cpp:185 */
+#define UBM_COUPLING_MAX 1             /* R/get_max_coupling.R:24, R/rnorm_max_coupling.R:17 */
+
+/* C1: univariate Normal-mixture target, random-walk MH.
+ * target: README.Rmd:69-72; kernels: R/get_mh_kernels.R:20-79 (reflection-max) or
+ * inst/reproducebimodal/bimodal.run.R:14-63 (max coupling); rinit: README.Rmd:80-84. */
+typedef struct {
+  int32_t ncomp;          /* <= 8 */
+  int32_t coupling;
+  const double* weights;  /* [ncomp] mixture weights (log taken with ubm_log at registration) */
+  const double* means;    /* [ncomp] */
+  const double* sds;      /* [ncomp] */
+  double proposal_sd;     /* chol(Sigma_proposal)[1,1] */
+  double init_mean, init_sd;
+} ubm_model_normal_mixture;
+
+/* C2: multivariate Normal target N(mean_pi, Sigma_pi), random-walk MH with reflection-max coupled
+ * proposals.  Kernels: R/get_mh_kernels.R:20-79 with src/mvnorm.cpp:30-46 (proposal),
+ * src/mvnorm.cpp:71-86 (target density via Cholesky inverse), src/mvnorm.cpp:185-236 (coupling);
+ * shape: inst/reproducescalingdimension/scaling.rwmh.reflectionmaxcoupling.R:12-103.
+ * All matrices d x d column-major, UPPER triangular as produced by R's chol() / solve(chol()). */
+typedef struct {
+  int32_t d;              /* 2 <= d <= 128 */
+  int32_t reserved;
+  const double* mean_pi;            /* [d] */
+  const double* chol_inv_pi;        /* solve(chol(Sigma_pi)) */
+  const double* chol_prop;          /* chol(Sigma_proposal) */
+  const double* chol_inv_prop;      /* solve(chol(Sigma_proposal)) */
+  const double* init_mean;          /* [d]  rinit: fast_rmvnorm_chol(1, init_mean, init_chol) */
+  const double* init_chol;          /* d x d upper */
+} ubm_model_mvn;
+
+/* ---------------------------------------------------------------------------------------------
+ * test functions h and histogram bins
+ * ------------------------------------------------------------------------------------------- */
+#define UBM_H_IDENTITY 0   /* h(x) = x (the R default, R/unbiasedestimator.R:43); dimh = dim */
+#define UBM_H_SQUARE 1     /* h(x) = x^2 componentwise (inst/check/check_lags.R:60) */
+#define UBM_H_BOTH 2       /* h(x) = (x, x^2); dimh = 2 dim */
+
+/* estimator_bin_ (src/estimator_bin.cpp:10-42) for every bin [breaks[b], breaks[b+1]) of one
+ * component, membership strict on both sides as in the reference. nbreaks == 0 disables bins. */
+typedef struct {
+  int32_t component;      /* 0-based */
+  int32_t nbreaks;        /* <= 257 */
+  const double* breaks;   /* [nbreaks] increasing */
+} ubm_bins;
+
+/* Aggregates over the uncensored replicates of one call, in one flat double buffer so that a
+ * multi-GPU caller can all-reduce it:
+ *   [0] n_done  [1] n_censored  [2] sum tau  [3] sum tau^2  [4] sum cost  [5] sum iteration
+ *   [6 .. 6+dimh)            sum_r uestimator_r
+ *   [6+dimh .. 6+2dimh)      sum_r uestimator_r^2
+ *   [6+2dimh .. +nbins)      sum_r bin_r        (bin_r = estimator_bin value of replicate r)
+ *   [6+2dimh+nbins .. +nbins) sum_r bin_r^2
+ * Sums over replicates run in replicate-index order with a fixed tree, so they are reproducible. */
+#define UBM_SUMMARY_HEAD 6
+int64_t ubm_summary_len(int32_t dimh, int32_t nbins);
+
+typedef struct {
+  /* per replicate; any pointer may be NULL */
+  double* uestimator;     /* [nrep][dimh]  R/unbiasedestimator.R:102 */
+  double* mcmcestimator;  /* [nrep][dimh] */
+  double* correction;     /* [nrep][dimh] */
+  double* meetingtime;    /* [nrep]  +Inf when max_iterations was hit (R/coupled_chains.R:57) */
+  int64_t* iteration;     /* [nrep] */
+  double* cost;           /* [nrep]  lag + 2 (tau - lag) + max(0, time - tau), +Inf if censored */
+  double* bins;           /* [nrep][nbins] */
+  /* aggregate */
+  double* summary;        /* [ubm_summary_len(dimh, nbins)] */
+} ubm_estimator_out;
+
+/* ---------------------------------------------------------------------------------------------
+ * the three drivers, batched.
+ * `model_kind` + `model` select the registry entry: model points at the matching ubm_model_* struct.
+ * ------------------------------------------------------------------------------------------- */
+#define UBM_MODEL_NORMAL_MIXTURE 1
+#define UBM_MODEL_MVN 2
+#define UBM_MODEL_PG_LOGISTIC 3
+#define UBM_MODEL_ISING_PT 4
+#define UBM_MODEL_VARSEL 5
+
+/* dimension of the chain state / of h for a model (so callers can size buffers) */
+int ubm_model_dim(int32_t model_kind, const void* model, int32_t* dim);
+int ubm_h_dim(int32_t model_kind, const void* model, int32_t h_kind, int32_t* dimh);
+
+/* sample_meetingtime (R/meetingtime.R:24-48): lag >= 1; max_iterations <= 0 means Inf.
+ * meetingtime[r] = +Inf if the replicate was stopped by max_iterations. */
+int ubm_sample_meetingtime(ubm_handle* h, int32_t model_kind, const void* model, const ubm_draws* draws,
+                           int64_t lag, int64_t max_iterations, int64_t nrep, int64_t rep_offset,
+                           double* meetingtime);
+
+/* sample_unbiasedestimator (R/unbiasedestimator.R:43-104) + estimator_bin_ for all bins, on the fly.
+ * Requires k <= m and lag <= m (the reference prints an error and returns NULL: UBM_ERR_INVALID). */
+int ubm_sample_unbiasedestimator(ubm_handle* h, int32_t model_kind, const void* model, const ubm_draws* draws,
+                                 int32_t h_kind, const ubm_bins* bins,
+                                 int64_t k, int64_t m, int64_t lag, int64_t max_iterations,
+                                 int64_t nrep, int64_t rep_offset, const ubm_estimator_out* out);
+
+/* sample_coupled_chains (R/coupled_chains.R:39-87): trajectories to HBM and back (parity / debug path).
+ * Each replicate gets `stride` rows of storage: samples1[r] is [stride][dim] row-major holding
+ * X_0..X_iteration, samples2[r] holds Y_0..Y_{iteration-lag}.  Replicates that would need more than
+ * `stride` rows are stopped as if max_iterations = stride - 1. */
+int ubm_sample_coupled_chains(ubm_handle* h, int32_t model_kind, const void* model, const ubm_draws* draws,
+                              int64_t m, int64_t lag, int64_t max_iterations, int64_t stride,
+                              int64_t nrep, int64_t rep_offset,
+                              double* samples1, double* samples2,
+                              double* meetingtime, int64_t* iteration, double* cost);
+
+/* H_bar (R/H_bar.R:19-54) and estimator_bin_ (src/estimator_bin.cpp:10-42) from stored chains, batched
+ * over replicates: the post-processing half of the path, run on the device over the layout produced by
+ * ubm_sample_coupled_chains. */
+int ubm_h_bar(ubm_handle* h, int32_t dim, int32_t h_kind, int64_t k, int64_t m, int64_t lag, int64_t stride,
+              int64_t nrep, const double* samples1, const double* samples2,
+              const double* meetingtime, const int64_t* iteration, double* hbar /* [nrep][dimh] */);
+int ubm_estimator_bins(ubm_handle* h, int32_t dim, const ubm_bins* bins, int64_t k, int64_t m, int64_t lag,
+                       int64_t stride, int64_t nrep, const double* samples1, const double* samples2,
+                       const double* meetingtime, double* binvals /* [nrep][nbins] */);
+
+/* ---------------------------------------------------------------------------------------------
+ * device-resident variant used for kernel-only timing (bench.py `value`): the model is uploaded once,
+ * the run leaves per-replicate results and the summary in device memory owned by the handle.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ubm_plan ubm_plan;
+int ubm_plan_create(ubm_handle* h, int32_t model_kind, const void* model, int32_t h_kind, const ubm_bins* bins,
+                    int64_t k, int64_t m, int64_t lag, int64_t max_iterations, int64_t max_nrep,
+                    ubm_plan** out);
+/* enqueue one batch on the handle's stream; returns without synchronising */
+int ubm_plan_launch(ubm_plan* p, uint64_t seed, int64_t nrep, int64_t rep_offset);
+/* wait for the stream and copy the summary (and optionally per-replicate arrays) to the host */
+int ubm_plan_fetch(ubm_plan* p, const ubm_estimator_out* out);
+/* device pointer of the summary buffer (for NCCL all-reduce through torch) and the raw stream */
+int ubm_plan_summary_dev(ubm_plan* p, void** dev_ptr, int64_t* len);
+int ubm_plan_stream(ubm_plan* p, void** cuda_stream);
+/* time of the last launched batch in ms, measured with CUDA events on the plan's stream */
+int ubm_plan_last_ms(ubm_plan* p, float* ms_main_kernel, float* ms_total);
+int ubm_plan_destroy(ubm_plan* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UBM_H */

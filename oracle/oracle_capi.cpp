@@ -1,0 +1,203 @@
+// oracle_capi.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see oracle_core.hpp header; parity unpinned).
+// extern "C" surface of the CPU oracle, loaded with ctypes by tests/, smoke() and bench.py's CPU legs.
+// Mirrors the product's C ABI (include/ubm.h) argument for argument so that a test can hand the same
+// structs to both sides.  `nthreads` > 1 runs replicates on a std::thread pool (the cpu_baseline leg).
+#include <atomic>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include "oracle_models.hpp"
+#include "oracle_more.hpp"
+
+using namespace orc;
+
+namespace {
+
+template <class F>
+void parallel_for(int64_t n, int nthreads, F f) {
+  if (nthreads <= 1 || n <= 1) { for (int64_t i = 0; i < n; ++i) f(i); return; }
+  std::atomic<int64_t> next(0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; ++t)
+    pool.emplace_back([&]() { for (;;) { int64_t i = next.fetch_add(1); if (i >= n) break; f(i); } });
+  for (auto& th : pool) th.join();
+}
+
+// canonical reduction over replicates: 1024 interleaved partials (ascending r), then xor-butterfly.
+double sum1024(int64_t n, const std::function<double(int64_t)>& term, bool square) {
+  std::vector<double> s(1024, 0.0), t(1024);
+  for (int64_t r = 0; r < n; ++r) {
+    double v = term(r);
+    int q = (int)(r & 1023);
+    s[q] = square ? ubm_fma(v, v, s[q]) : (s[q] + v);
+  }
+  for (int off = 512; off >= 1; off >>= 1) {
+    for (int q = 0; q < 1024; ++q) t[q] = s[q] + s[q ^ off];
+    s.swap(t);
+  }
+  return s[0];
+}
+
+template <class M>
+int run_meeting(const M& model, const ubm_draws* draws, int64_t lag, int64_t max_it, int64_t nrep,
+                int64_t rep_offset, double* meetingtime, int nthreads) {
+  std::atomic<int> bad(0);
+  parallel_for(nrep, nthreads, [&](int64_t r) {
+    Draws D = make_draws(draws, r, rep_offset);
+    RepResult res = sample_meetingtime(model, D, lag, max_it);
+    meetingtime[r] = res.meetingtime;
+    if (res.tape_exhausted) bad = 1;
+  });
+  return bad ? UBM_ERR_TAPE : UBM_OK;
+}
+
+template <class M>
+int run_estimator(const M& model, const ubm_draws* draws, int h_kind, const ubm_bins* bins, int64_t k, int64_t m,
+                  int64_t lag, int64_t max_it, int64_t nrep, int64_t rep_offset, const ubm_estimator_out* out,
+                  int nthreads) {
+  const int dimh = h_dim(h_kind, model.dim());
+  const int nbins = (bins && bins->nbreaks >= 2) ? bins->nbreaks - 1 : 0;
+  std::vector<double> ue((size_t)nrep * dimh), mc((size_t)nrep * dimh), co((size_t)nrep * dimh),
+      bv((size_t)nrep * std::max(nbins, 1));
+  std::vector<int64_t> bn((size_t)nrep * std::max(nbins, 1));
+  std::vector<RepResult> rr(nrep);
+  std::atomic<int> bad(0);
+  parallel_for(nrep, nthreads, [&](int64_t r) {
+    Draws D = make_draws(draws, r, rep_offset);
+    rr[r] = sample_unbiasedestimator(model, D, h_kind, bins, k, m, lag, max_it, &mc[(size_t)r * dimh],
+                                     &co[(size_t)r * dimh], &ue[(size_t)r * dimh],
+                                     nbins ? &bv[(size_t)r * nbins] : nullptr, nbins ? &bn[(size_t)r * nbins] : nullptr);
+    if (rr[r].tape_exhausted) bad = 1;
+  });
+  if (out->uestimator) memcpy(out->uestimator, ue.data(), ue.size() * 8);
+  if (out->mcmcestimator) memcpy(out->mcmcestimator, mc.data(), mc.size() * 8);
+  if (out->correction) memcpy(out->correction, co.data(), co.size() * 8);
+  if (out->bins && nbins) memcpy(out->bins, bv.data(), (size_t)nrep * nbins * 8);
+  for (int64_t r = 0; r < nrep; ++r) {
+    if (out->meetingtime) out->meetingtime[r] = rr[r].meetingtime;
+    if (out->iteration) out->iteration[r] = rr[r].iteration;
+    if (out->cost) out->cost[r] = rr[r].cost;
+  }
+  if (out->summary) {
+    double* S = out->summary;
+    auto ok = [&](int64_t r) { return std::isfinite(rr[r].meetingtime); };
+    double nd = 0, nc = 0;
+    for (int64_t r = 0; r < nrep; ++r) { if (ok(r)) nd += 1; else nc += 1; }
+    S[0] = nd; S[1] = nc;
+    S[2] = sum1024(nrep, [&](int64_t r) { return ok(r) ? rr[r].meetingtime : 0.0; }, false);
+    S[3] = sum1024(nrep, [&](int64_t r) { return ok(r) ? rr[r].meetingtime : 0.0; }, true);
+    S[4] = sum1024(nrep, [&](int64_t r) { return ok(r) ? rr[r].cost : 0.0; }, false);
+    S[5] = sum1024(nrep, [&](int64_t r) { return ok(r) ? (double)rr[r].iteration : 0.0; }, false);
+    for (int i = 0; i < dimh; ++i) {
+      S[6 + i] = sum1024(nrep, [&](int64_t r) { return ok(r) ? ue[(size_t)r * dimh + i] : 0.0; }, false);
+      S[6 + dimh + i] = sum1024(nrep, [&](int64_t r) { return ok(r) ? ue[(size_t)r * dimh + i] : 0.0; }, true);
+    }
+    // bins: exact integer sums of the numerators (and of their squares), one rounding each
+    const double denom = (double)(m - k + 1);
+    for (int b = 0; b < nbins; ++b) {
+      long long c1 = 0, c2 = 0;
+      for (int64_t r = 0; r < nrep; ++r) if (ok(r)) { long long c = bn[(size_t)r * nbins + b]; c1 += c; c2 += c * c; }
+      S[6 + 2 * dimh + b] = (double)c1 / denom;
+      S[6 + 2 * dimh + nbins + b] = (double)c2 / (denom * denom);
+    }
+  }
+  return bad ? UBM_ERR_TAPE : UBM_OK;
+}
+
+template <class M>
+int run_chains(const M& model, const ubm_draws* draws, int64_t m, int64_t lag, int64_t max_it, int64_t stride,
+               int64_t nrep, int64_t rep_offset, double* samples1, double* samples2, double* meetingtime,
+               int64_t* iteration, double* cost, int nthreads) {
+  const int d = model.dim();
+  std::atomic<int> bad(0);
+  int64_t cap = stride - 1;
+  int64_t eff_max = (max_it <= 0 || max_it > cap) ? cap : max_it;
+  parallel_for(nrep, nthreads, [&](int64_t r) {
+    Draws D = make_draws(draws, r, rep_offset);
+    std::vector<double> s1, s2;
+    RepResult res = sample_coupled_chains(model, D, m, lag, eff_max, s1, s2);
+    memcpy(samples1 + (size_t)r * stride * d, s1.data(), s1.size() * 8);
+    memcpy(samples2 + (size_t)r * stride * d, s2.data(), s2.size() * 8);
+    if (meetingtime) meetingtime[r] = res.meetingtime;
+    if (iteration) iteration[r] = res.iteration;
+    if (cost) cost[r] = res.cost;
+    if (res.tape_exhausted) bad = 1;
+  });
+  return bad ? UBM_ERR_TAPE : UBM_OK;
+}
+
+}  // namespace
+
+#define DISPATCH(CALL)                                                                              \
+  switch (model_kind) {                                                                             \
+    case UBM_MODEL_NORMAL_MIXTURE: { MixtureModel M((const ubm_model_normal_mixture*)model); return CALL; } \
+    case UBM_MODEL_MVN: { MvnModel M((const ubm_model_mvn*)model); return CALL; }                   \
+    ORC_MORE_DISPATCH(CALL)                                                                         \
+    default: return UBM_ERR_UNSUPPORTED;                                                            \
+  }
+
+extern "C" {
+
+int orc_sample_meetingtime(int32_t model_kind, const void* model, const ubm_draws* draws, int64_t lag,
+                           int64_t max_iterations, int64_t nrep, int64_t rep_offset, double* meetingtime,
+                           int32_t nthreads) {
+  if (lag < 1) return UBM_ERR_INVALID;
+  DISPATCH(run_meeting(M, draws, lag, max_iterations, nrep, rep_offset, meetingtime, nthreads))
+}
+
+int orc_sample_unbiasedestimator(int32_t model_kind, const void* model, const ubm_draws* draws, int32_t h_kind,
+                                 const ubm_bins* bins, int64_t k, int64_t m, int64_t lag, int64_t max_iterations,
+                                 int64_t nrep, int64_t rep_offset, const ubm_estimator_out* out, int32_t nthreads) {
+  if (lag < 1 || k > m || lag > m || k < 0) return UBM_ERR_INVALID;   // R/unbiasedestimator.R:44-51
+  DISPATCH(run_estimator(M, draws, h_kind, bins, k, m, lag, max_iterations, nrep, rep_offset, out, nthreads))
+}
+
+int orc_sample_coupled_chains(int32_t model_kind, const void* model, const ubm_draws* draws, int64_t m, int64_t lag,
+                              int64_t max_iterations, int64_t stride, int64_t nrep, int64_t rep_offset,
+                              double* samples1, double* samples2, double* meetingtime, int64_t* iteration,
+                              double* cost, int32_t nthreads) {
+  if (lag < 1) return UBM_ERR_INVALID;
+  DISPATCH(run_chains(M, draws, m, lag, max_iterations, stride, nrep, rep_offset, samples1, samples2, meetingtime,
+                      iteration, cost, nthreads))
+}
+
+int orc_h_bar(int32_t dim, int32_t h_kind, int64_t k, int64_t m, int64_t lag, int64_t stride, int64_t nrep,
+              const double* samples1, const double* samples2, const double* meetingtime, const int64_t* iteration,
+              double* hbar) {
+  const int dimh = h_dim(h_kind, dim);
+  for (int64_t r = 0; r < nrep; ++r) {
+    if (k > iteration[r] || m > iteration[r]) return UBM_ERR_INVALID;   // R/H_bar.R:21-28
+    H_bar(samples1 + (size_t)r * stride * dim, samples2 + (size_t)r * stride * dim, dim, h_kind, k, m, lag,
+          meetingtime[r], hbar + (size_t)r * dimh);
+  }
+  return UBM_OK;
+}
+
+int orc_estimator_bins(int32_t dim, const ubm_bins* bins, int64_t k, int64_t m, int64_t lag, int64_t stride,
+                       int64_t nrep, const double* samples1, const double* samples2, const double* meetingtime,
+                       double* binvals) {
+  const int nbins = bins->nbreaks - 1;
+  for (int64_t r = 0; r < nrep; ++r)
+    for (int b = 0; b < nbins; ++b)
+      binvals[(size_t)r * nbins + b] =
+          estimator_bin(samples1 + (size_t)r * stride * dim, samples2 + (size_t)r * stride * dim, dim,
+                        bins->component, bins->breaks[b], bins->breaks[b + 1], k, m, lag, meetingtime[r]);
+  return UBM_OK;
+}
+
+// numerics probes (tests/test_numerics.py)
+void orc_vec_log(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ubm_log(x[i]); }
+void orc_vec_exp(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ubm_exp(x[i]); }
+void orc_vec_log1p(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ubm_log1p(x[i]); }
+void orc_vec_qnorm(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ubm_qnorm(x[i]); }
+void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+  ubm_u32x4 b = ubm_philox4x32_10(c0, c1, c2, c3, k0, k1);
+  for (int i = 0; i < 4; ++i) out[i] = b.w[i];
+}
+// the first n draws of each typed stream of one replicate (to build tapes that replay a Philox run)
+void orc_stream(uint64_t seed, uint64_t rep, int32_t type, int64_t n, double* out) {
+  Draws D; D.seed = seed; D.rep = rep;
+  for (int64_t i = 0; i < n; ++i) out[i] = (type == 0) ? D.u() : (type == 1) ? D.n() : D.e();
+}
+
+}  // extern "C"

@@ -1,0 +1,5 @@
+// oracle_more.hpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see oracle_core.hpp header).
+// Dispatch hook for the remaining registry models (Ising PT, PG logistic, variable selection).
+#pragma once
+#include "oracle_core.hpp"
+#define ORC_MORE_DISPATCH(CALL)

@@ -1,0 +1,155 @@
+"""ctypes loader of the CPU oracle (oracle/_build/libubm_oracle.so).
+
+TEST INFRASTRUCTURE, NOT PRODUCT CODE: only tests/, __graft_entry__.smoke() and bench.py's CPU legs
+(cpu_baseline, --impl reference) may import this module.  Parity status: unpinned (see oracle_core.hpp).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from unbiasedmcmc_b200 import _abi as A
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "libubm_oracle.so")
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", HERE], check=True, stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.orc_sample_meetingtime.argtypes = [C.c_int32, vp, C.POINTER(A.ubm_draws), C.c_int64, C.c_int64, C.c_int64,
+                                             C.c_int64, A.c_double_p, C.c_int32]
+        L.orc_sample_unbiasedestimator.argtypes = [C.c_int32, vp, C.POINTER(A.ubm_draws), C.c_int32,
+                                                   C.POINTER(A.ubm_bins), C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                                   C.c_int64, C.c_int64, C.POINTER(A.ubm_estimator_out), C.c_int32]
+        L.orc_sample_coupled_chains.argtypes = [C.c_int32, vp, C.POINTER(A.ubm_draws), C.c_int64, C.c_int64,
+                                                C.c_int64, C.c_int64, C.c_int64, C.c_int64, A.c_double_p,
+                                                A.c_double_p, A.c_double_p, A.c_int64_p, A.c_double_p, C.c_int32]
+        L.orc_h_bar.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                A.c_double_p, A.c_double_p, A.c_double_p, A.c_int64_p, A.c_double_p]
+        L.orc_estimator_bins.argtypes = [C.c_int32, C.POINTER(A.ubm_bins), C.c_int64, C.c_int64, C.c_int64,
+                                         C.c_int64, C.c_int64, A.c_double_p, A.c_double_p, A.c_double_p,
+                                         A.c_double_p]
+        for f in ("orc_vec_log", "orc_vec_exp", "orc_vec_log1p", "orc_vec_qnorm"):
+            getattr(L, f).argtypes = [A.c_double_p, A.c_double_p, C.c_int64]
+            getattr(L, f).restype = None
+        L.orc_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
+        L.orc_philox.restype = None
+        L.orc_stream.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, A.c_double_p]
+        L.orc_stream.restype = None
+        _lib = L
+    return _lib
+
+
+class OracleError(RuntimeError):
+    def __init__(self, status):
+        super().__init__(f"oracle status {status}")
+        self.status = status
+
+
+def _check(st):
+    if st != 0:
+        raise OracleError(st)
+
+
+def vec(fn, x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    getattr(lib(), "orc_vec_" + fn)(A.dptr(x), A.dptr(y), x.size)
+    return y
+
+
+def philox(ctr, key):
+    out = (C.c_uint32 * 4)()
+    lib().orc_philox(*[int(c) for c in ctr], *[int(k) for k in key], out)
+    return [int(v) for v in out]
+
+
+def stream(seed, rep, type_, n):
+    out = np.empty(n, dtype=np.float64)
+    lib().orc_stream(int(seed), int(rep), int(type_), n, A.dptr(out))
+    return out
+
+
+def sample_meetingtime(model, draws, lag=1, max_iterations=0, nrep=1, rep_offset=0, nthreads=1):
+    mt = np.empty(nrep, dtype=np.float64)
+    ds = draws.struct(nrep)
+    _check(lib().orc_sample_meetingtime(model.kind, model.ref(), C.byref(ds), lag, max_iterations, nrep, rep_offset,
+                                        A.dptr(mt), nthreads))
+    return {"meetingtime": mt}
+
+
+def alloc_estimator_out(nrep, dimh, nbins, per_replicate=True):
+    res = {
+        "uestimator": np.zeros((nrep, dimh)), "mcmcestimator": np.zeros((nrep, dimh)),
+        "correction": np.zeros((nrep, dimh)), "meetingtime": np.zeros(nrep),
+        "iteration": np.zeros(nrep, dtype=np.int64), "cost": np.zeros(nrep),
+        "bins": np.zeros((nrep, nbins)) if nbins else None,
+        "summary": np.zeros(A.summary_len(dimh, nbins)),
+    }
+    if not per_replicate:
+        for k in ("uestimator", "mcmcestimator", "correction", "meetingtime", "iteration", "cost", "bins"):
+            res[k] = None
+    out = A.ubm_estimator_out(A.dptr(res["uestimator"]), A.dptr(res["mcmcestimator"]), A.dptr(res["correction"]),
+                              A.dptr(res["meetingtime"]), A.i64ptr(res["iteration"]), A.dptr(res["cost"]),
+                              A.dptr(res["bins"]), A.dptr(res["summary"]))
+    return res, out
+
+
+def sample_unbiasedestimator(model, draws, h_kind=A.UBM_H_IDENTITY, bins=None, k=0, m=1, lag=1, max_iterations=0,
+                             nrep=1, rep_offset=0, nthreads=1):
+    dimh = model.h_dim(h_kind)
+    nbins = bins.nbins if bins is not None else 0
+    res, out = alloc_estimator_out(nrep, dimh, nbins)
+    ds = draws.struct(nrep)
+    bs = bins.struct() if bins is not None else None
+    _check(lib().orc_sample_unbiasedestimator(model.kind, model.ref(), C.byref(ds), h_kind,
+                                              C.byref(bs) if bs is not None else None, k, m, lag, max_iterations,
+                                              nrep, rep_offset, C.byref(out), nthreads))
+    return res
+
+
+def sample_coupled_chains(model, draws, m=1, lag=1, max_iterations=0, stride=None, nrep=1, rep_offset=0, nthreads=1):
+    d = model.dim
+    if stride is None:
+        raise ValueError("stride (rows of storage per replicate) is required")
+    s1 = np.full((nrep, stride, d), np.nan)
+    s2 = np.full((nrep, stride, d), np.nan)
+    mt = np.zeros(nrep)
+    it = np.zeros(nrep, dtype=np.int64)
+    cost = np.zeros(nrep)
+    ds = draws.struct(nrep)
+    _check(lib().orc_sample_coupled_chains(model.kind, model.ref(), C.byref(ds), m, lag, max_iterations, stride, nrep,
+                                           rep_offset, A.dptr(s1), A.dptr(s2), A.dptr(mt), A.i64ptr(it), A.dptr(cost),
+                                           nthreads))
+    return {"samples1": s1, "samples2": s2, "meetingtime": mt, "iteration": it, "cost": cost, "lag": lag}
+
+
+def h_bar(chains, h_kind=A.UBM_H_IDENTITY, k=0, m=1):
+    s1, s2 = chains["samples1"], chains["samples2"]
+    nrep, stride, d = s1.shape
+    dimh = 2 * d if h_kind == A.UBM_H_BOTH else d
+    out = np.zeros((nrep, dimh))
+    _check(lib().orc_h_bar(d, h_kind, k, m, chains["lag"], stride, nrep, A.dptr(s1), A.dptr(s2),
+                           A.dptr(chains["meetingtime"]), A.i64ptr(chains["iteration"]), A.dptr(out)))
+    return out
+
+
+def estimator_bins(chains, bins, k=0, m=1):
+    s1, s2 = chains["samples1"], chains["samples2"]
+    nrep, stride, d = s1.shape
+    out = np.zeros((nrep, bins.nbins))
+    bs = bins.struct()
+    _check(lib().orc_estimator_bins(d, C.byref(bs), k, m, chains["lag"], stride, nrep, A.dptr(s1), A.dptr(s2),
+                                    A.dptr(chains["meetingtime"]), A.dptr(out)))
+    return out

@@ -1,0 +1,39 @@
+"""Seeded synthetic inputs for the BASELINE configs, shared by tests, smoke() and bench.py."""
+import numpy as np
+
+from unbiasedmcmc_b200 import _abi as A
+from unbiasedmcmc_b200 import registry as R
+
+SEED = 20251019
+
+
+def c1_model(coupling=A.UBM_COUPLING_REFLECTION_MAX):
+    """README.Rmd:69-84: target 0.5 N(-4,1) + 0.5 N(4,1), proposal variance 4, init N(3, 2^2)."""
+    if coupling == A.UBM_COUPLING_MAX:   # inst/reproducebimodal/bimodal.run.R:65 get_pb(3, 10, 10)
+        return R.NormalMixtureRWMH([0.5, 0.5], [-4.0, 4.0], [1.0, 1.0], 3.0, 10.0, 10.0, coupling)
+    return R.NormalMixtureRWMH([0.5, 0.5], [-4.0, 4.0], [1.0, 1.0], 2.0, 3.0, 2.0, coupling)
+
+
+def c1_bins():
+    return R.Bins(0, np.linspace(-8.0, 8.0, 81))
+
+
+def mvn_sigma(d, kind="dense", seed=21):
+    """scaling.rwmh.reflectionmaxcoupling.R:19-27: 'sparse' AR(0.5) or 'dense' inverse of one Wishart(d, I) draw."""
+    if kind == "sparse":
+        i = np.arange(d)
+        return 0.5 ** np.abs(i[:, None] - i[None, :])
+    rng = np.random.default_rng(seed)
+    G = rng.standard_normal((d, d))
+    W = G.T @ G                      # Wishart(d, I)
+    S = np.linalg.inv(W)
+    return (S + S.T) / 2
+
+
+def c2_model(d=100, kind="dense", init="target", mean=None):
+    """scaling.rwmh.reflectionmaxcoupling.R:12-103 with scale_type = 'optimal' (Sigma_proposal = Sigma_pi / d)."""
+    Sigma = mvn_sigma(d, kind)
+    mean_pi = np.zeros(d) if mean is None else np.asarray(mean, dtype=np.float64)
+    if init == "target":
+        return R.MvnRWMH(mean_pi, Sigma, Sigma / d, mean_pi, Sigma)
+    return R.MvnRWMH(mean_pi, Sigma, Sigma / d, np.ones(d), np.eye(d))

@@ -1,0 +1,184 @@
+"""GPU parity, C1 (Normal mixture) and C2 (MVN): the CUDA engine, called through the C ABI, against the CPU
+oracle on the same seeded inputs.  Bar: meeting times, iterations, costs and bin numerators bit-exact;
+FP64 estimators bit-exact too (stated tolerance of north_star: 1e-12 relative; we assert equality and report
+the max deviation if it ever fails)."""
+import numpy as np
+import pytest
+
+from tests import cases
+from unbiasedmcmc_b200 import _abi as A
+from unbiasedmcmc_b200 import registry as R
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_same(res_gpu, res_cpu, keys, tol=0.0):
+    for k in keys:
+        a, b = res_gpu[k], res_cpu[k]
+        if a is None and b is None:
+            continue
+        if tol == 0.0:
+            if not np.array_equal(a, b):
+                bad = np.argwhere(~(np.asarray(a) == np.asarray(b)))
+                dev = np.nanmax(np.abs(np.asarray(a, dtype=float) - np.asarray(b, dtype=float)))
+                raise AssertionError(f"{k}: {len(bad)} mismatches, first at {bad[:3].tolist()}, max abs dev {dev}")
+        else:
+            np.testing.assert_allclose(a, b, rtol=tol, atol=0)
+
+
+EST_KEYS = ["meetingtime", "iteration", "cost", "uestimator", "mcmcestimator", "correction", "bins", "summary"]
+
+
+@pytest.mark.parametrize("coupling", [A.UBM_COUPLING_REFLECTION_MAX, A.UBM_COUPLING_MAX])
+def test_c1_estimator_philox_bit_exact(engine, oracle, coupling):
+    mdl = cases.c1_model(coupling)
+    kw = dict(h_kind=A.UBM_H_BOTH, bins=cases.c1_bins(), k=500, m=2000, lag=500, nrep=1500, rep_offset=7)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=11), **kw)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=11), nthreads=8, **kw)
+    assert_same(g, c, EST_KEYS)
+    assert np.all(np.isfinite(g["meetingtime"]))
+
+
+@pytest.mark.parametrize("lag,k,m", [(1, 0, 1), (1, 0, 50), (10, 10, 50), (3, 7, 7), (50, 0, 50)])
+def test_c1_estimator_small_horizons(engine, oracle, lag, k, m):
+    mdl = cases.c1_model()
+    kw = dict(h_kind=A.UBM_H_IDENTITY, bins=cases.c1_bins(), k=k, m=m, lag=lag, nrep=257)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=5), **kw)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=5), **kw)
+    assert_same(g, c, EST_KEYS)
+
+
+def test_c1_meetingtime_and_censoring(engine, oracle):
+    mdl = cases.c1_model()
+    g = engine.sample_meetingtime(mdl, R.Draws(seed=3), lag=1, nrep=4000)
+    c = oracle.sample_meetingtime(mdl, R.Draws(seed=3), lag=1, nrep=4000, nthreads=8)
+    assert_same(g, c, ["meetingtime"])
+    # max_iterations: censored replicates report +Inf (R/meetingtime.R:35-36)
+    g = engine.sample_meetingtime(mdl, R.Draws(seed=3), lag=1, max_iterations=20, nrep=4000)
+    c = oracle.sample_meetingtime(mdl, R.Draws(seed=3), lag=1, max_iterations=20, nrep=4000, nthreads=8)
+    assert_same(g, c, ["meetingtime"])
+    assert np.isinf(g["meetingtime"]).any() and np.isfinite(g["meetingtime"]).any()
+
+
+def test_c1_estimator_censored_summary(engine, oracle):
+    mdl = cases.c1_model()
+    kw = dict(bins=cases.c1_bins(), k=5, m=20, lag=2, max_iterations=25, nrep=999)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=9), **kw)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=9), **kw)
+    assert_same(g, c, EST_KEYS)
+    assert g["summary"][1] > 0   # some censored
+
+
+def test_c1_replay_tapes_bit_exact(engine, oracle):
+    """Replay mode: both sides consume the same recorded draws (typed tapes), not Philox."""
+    mdl = cases.c1_model()
+    nrep, L = 64, 4000
+    rng = np.random.default_rng(123)
+    draws = R.Draws(tape_u=rng.uniform(size=(nrep, L)), tape_n=rng.standard_normal((nrep, L)))
+    kw = dict(bins=cases.c1_bins(), k=100, m=400, lag=50, nrep=nrep)
+    g = engine.sample_unbiasedestimator(mdl, draws, **kw)
+    c = oracle.sample_unbiasedestimator(mdl, draws, **kw)
+    assert_same(g, c, EST_KEYS)
+    # a tape recorded from the Philox streams replays the Philox run exactly
+    tu = np.stack([oracle.stream(77, r, 0, L) for r in range(nrep)])
+    tn = np.stack([oracle.stream(77, r, 1, L) for r in range(nrep)])
+    g_t = engine.sample_unbiasedestimator(mdl, R.Draws(tape_u=tu, tape_n=tn), **kw)
+    g_p = engine.sample_unbiasedestimator(mdl, R.Draws(seed=77), **kw)
+    assert_same(g_t, g_p, EST_KEYS)
+
+
+def test_c1_tape_exhaustion_is_an_error(engine):
+    from unbiasedmcmc_b200.engine import UbmError
+    mdl = cases.c1_model()
+    rng = np.random.default_rng(1)
+    draws = R.Draws(tape_u=rng.uniform(size=(8, 10)), tape_n=rng.standard_normal((8, 10)))
+    with pytest.raises(UbmError) as e:
+        engine.sample_unbiasedestimator(mdl, draws, k=10, m=100, lag=1, nrep=8)
+    assert e.value.status == A.UBM_ERR_TAPE
+
+
+def test_c1_chains_hbar_bins(engine, oracle):
+    mdl = cases.c1_model()
+    kw = dict(m=300, lag=20, stride=2048, nrep=200)
+    g = engine.sample_coupled_chains(mdl, R.Draws(seed=4), **kw)
+    c = oracle.sample_coupled_chains(mdl, R.Draws(seed=4), **kw)
+    assert_same(g, c, ["meetingtime", "iteration", "cost"])
+    for r in range(200):
+        n = int(c["iteration"][r]) + 1
+        assert np.array_equal(g["samples1"][r, :n], c["samples1"][r, :n])
+        assert np.array_equal(g["samples2"][r, :n - 20], c["samples2"][r, :n - 20])
+    hb_g = engine.h_bar(g, A.UBM_H_BOTH, k=50, m=300)
+    hb_c = oracle.h_bar(c, A.UBM_H_BOTH, k=50, m=300)
+    assert np.array_equal(hb_g, hb_c)
+    bins = cases.c1_bins()
+    assert np.array_equal(engine.estimator_bins(g, bins, k=50, m=300), oracle.estimator_bins(c, bins, k=50, m=300))
+    # on-the-fly estimator == H_bar of the stored chains (same draws), up to summation order
+    e = engine.sample_unbiasedestimator(mdl, R.Draws(seed=4), h_kind=A.UBM_H_BOTH, bins=bins, k=50, m=300, lag=20, nrep=200)
+    np.testing.assert_allclose(e["uestimator"], hb_g, rtol=1e-12, atol=1e-12)
+    assert np.array_equal(e["bins"], engine.estimator_bins(g, bins, k=50, m=300))
+
+
+def test_c1_split_invariance(engine):
+    """Results depend only on (seed, global replicate index), not on how replicates are split over calls."""
+    mdl = cases.c1_model()
+    kw = dict(k=20, m=100, lag=5)
+    a = engine.sample_unbiasedestimator(mdl, R.Draws(seed=8), nrep=300, **kw)
+    b1 = engine.sample_unbiasedestimator(mdl, R.Draws(seed=8), nrep=100, rep_offset=0, **kw)
+    b2 = engine.sample_unbiasedestimator(mdl, R.Draws(seed=8), nrep=200, rep_offset=100, **kw)
+    assert np.array_equal(a["uestimator"], np.concatenate([b1["uestimator"], b2["uestimator"]]))
+    assert np.array_equal(a["meetingtime"], np.concatenate([b1["meetingtime"], b2["meetingtime"]]))
+
+
+@pytest.mark.parametrize("d,kind,init", [(2, "dense", "target"), (5, "sparse", "offset"), (23, "dense", "offset"),
+                                         (100, "dense", "target")])
+def test_c2_meetingtime_bit_exact(engine, oracle, d, kind, init):
+    mdl = cases.c2_model(d, kind, init)
+    nrep = 300 if d < 100 else 120
+    g = engine.sample_meetingtime(mdl, R.Draws(seed=21), lag=1, nrep=nrep, rep_offset=3)
+    c = oracle.sample_meetingtime(mdl, R.Draws(seed=21), lag=1, nrep=nrep, rep_offset=3, nthreads=8)
+    assert_same(g, c, ["meetingtime"])
+
+
+@pytest.mark.parametrize("d,lag,k,m,h", [(5, 1, 0, 30, A.UBM_H_BOTH), (12, 4, 10, 60, A.UBM_H_IDENTITY),
+                                         (100, 1, 50, 250, A.UBM_H_SQUARE)])
+def test_c2_estimator_bit_exact(engine, oracle, d, lag, k, m, h):
+    mean = np.linspace(-1, 1, d) if d == 12 else None     # non-zero target mean exercises the centred path
+    mdl = cases.c2_model(d, "dense", "offset", mean=mean)
+    nrep = 100 if d < 100 else 40
+    kw = dict(h_kind=h, k=k, m=m, lag=lag, nrep=nrep)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=2), **kw)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=2), nthreads=8, **kw)
+    assert_same(g, c, ["meetingtime", "iteration", "cost", "uestimator", "mcmcestimator", "correction", "summary"])
+
+
+def test_c2_chains_and_hbar(engine, oracle):
+    mdl = cases.c2_model(7, "dense", "offset")
+    kw = dict(m=40, lag=3, stride=1024, nrep=50)
+    g = engine.sample_coupled_chains(mdl, R.Draws(seed=6), **kw)
+    c = oracle.sample_coupled_chains(mdl, R.Draws(seed=6), **kw)
+    assert_same(g, c, ["meetingtime", "iteration", "cost"])
+    for r in range(50):
+        n = int(c["iteration"][r]) + 1
+        assert np.array_equal(g["samples1"][r, :n], c["samples1"][r, :n])
+        assert np.array_equal(g["samples2"][r, :n - 3], c["samples2"][r, :n - 3])
+    assert np.array_equal(engine.h_bar(g, A.UBM_H_IDENTITY, k=5, m=40), oracle.h_bar(c, A.UBM_H_IDENTITY, k=5, m=40))
+
+
+def test_c2_replay_tapes(engine, oracle):
+    d = 6
+    mdl = cases.c2_model(d, "sparse", "offset")
+    nrep, steps = 16, 400
+    rng = np.random.default_rng(5)
+    draws = R.Draws(tape_u=rng.uniform(size=(nrep, 2 * steps)), tape_n=rng.standard_normal((nrep, d * (steps + 2))))
+    g = engine.sample_meetingtime(mdl, draws, lag=2, max_iterations=steps - 5, nrep=nrep)
+    c = oracle.sample_meetingtime(mdl, draws, lag=2, max_iterations=steps - 5, nrep=nrep)
+    assert_same(g, c, ["meetingtime"])
+
+
+def test_invalid_arguments(engine):
+    from unbiasedmcmc_b200.engine import UbmError
+    mdl = cases.c1_model()
+    for kw in (dict(k=5, m=3, lag=1), dict(k=0, m=3, lag=4), dict(k=0, m=3, lag=0)):   # R/unbiasedestimator.R:44-51
+        with pytest.raises(UbmError) as e:
+            engine.sample_unbiasedestimator(mdl, R.Draws(seed=1), nrep=4, **kw)
+        assert e.value.status == A.UBM_ERR_INVALID

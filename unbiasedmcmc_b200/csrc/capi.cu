@@ -1,0 +1,506 @@
+// capi.cu — the extern "C" boundary of libubm.so (include/ubm.h) and the host-side plumbing behind it:
+// handle (device, stream, error text), plan (uploaded model + device result buffers), launches.
+// Replaces the R `.Call` boundary of the reference (src/RcppExports.cpp:388-423) for the coupled-chain
+// hot path.  No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ubm_common.cuh"
+#include "ubm_mix.cuh"
+#include "ubm_mvn.cuh"
+#include "ubm_summary.cuh"
+#include "ubm_post.cuh"
+
+using namespace ubm;
+
+struct ubm_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  cudaDeviceProp prop{};
+};
+
+static int fail(ubm_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(h, UBM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) {
+    if (p) { cudaFree(p); p = nullptr; }
+    bytes = n;
+    if (n == 0) return cudaSuccess;
+    return cudaMalloc(&p, n);
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct ubm_plan {
+  ubm_handle* h = nullptr;
+  int model_kind = 0, mode = MODE_ESTIMATOR, h_kind = 0;
+  int dim = 0, dimh = 0, nbins = 0, nbreaks = 0, component = 0;
+  int64_t k = 0, m = 1, lag = 1, max_it = 0, max_nrep = 0, stride = 0;
+  // models
+  MixParams mix{};
+  MvnDevice mvn{};
+  DevBuf model_blob;
+  // results
+  DevBuf uest, mcmc, corr, tau, cost, iter, bins_out, bin_acc, breaks, summary, counter, status, scratch;
+  DevBuf tape_u, tape_n, tape_e, samples1, samples2;
+  int64_t len_u = 0, len_n = 0, len_e = 0;
+  bool want_bins_out = false, want_parts = false;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+  int64_t last_nrep = 0;
+  ~ubm_plan() {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (e2) cudaEventDestroy(e2);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// model registration (host side of the device registry)
+// ---------------------------------------------------------------------------------------------------
+static int model_dims(int32_t kind, const void* model, int* dim) {
+  if (!model) return UBM_ERR_INVALID;
+  switch (kind) {
+    case UBM_MODEL_NORMAL_MIXTURE: *dim = 1; return UBM_OK;
+    case UBM_MODEL_MVN: *dim = ((const ubm_model_mvn*)model)->d; return UBM_OK;
+    default: return UBM_ERR_UNSUPPORTED;
+  }
+}
+
+static int register_model(ubm_plan* p, int32_t kind, const void* model) {
+  ubm_handle* h = p->h;
+  p->model_kind = kind;
+  if (kind == UBM_MODEL_NORMAL_MIXTURE) {
+    const ubm_model_normal_mixture* s = (const ubm_model_normal_mixture*)model;
+    if (s->ncomp < 1 || s->ncomp > 8) return fail(h, UBM_ERR_INVALID, "normal mixture: 1..8 components");
+    if (s->coupling != UBM_COUPLING_REFLECTION_MAX && s->coupling != UBM_COUPLING_MAX)
+      return fail(h, UBM_ERR_UNSUPPORTED, "normal mixture: unknown coupling");
+    if (!(s->proposal_sd > 0)) return fail(h, UBM_ERR_INVALID, "normal mixture: proposal_sd must be > 0");
+    MixParams& M = p->mix;
+    M.ncomp = s->ncomp; M.coupling = s->coupling;
+    for (int i = 0; i < s->ncomp; ++i) {
+      M.logw[i] = ubm_log(s->weights[i]); M.mean[i] = s->means[i]; M.sd[i] = s->sds[i]; M.logsd[i] = ubm_log(s->sds[i]);
+    }
+    M.prop_sd = s->proposal_sd; M.log_prop_sd = ubm_log(s->proposal_sd);
+    M.init_mean = s->init_mean; M.init_sd = s->init_sd;
+    p->dim = 1;
+    return UBM_OK;
+  }
+  if (kind == UBM_MODEL_MVN) {
+    const ubm_model_mvn* s = (const ubm_model_mvn*)model;
+    if (s->d < 2 || s->d > 128) return fail(h, UBM_ERR_INVALID, "mvn: need 2 <= d <= 128 (R stops for d = 1, R/mvnorm_couplings.R:96)");
+    p->dim = s->d;
+    std::vector<double> blob;
+    mvn_pack_host(s, &p->mvn, &blob);
+    CU(p->model_blob.alloc(blob.size() * sizeof(double)));
+    CU(cudaMemcpyAsync(p->model_blob.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    mvn_bind_device(&p->mvn, p->model_blob.as<double>());
+    return UBM_OK;
+  }
+  return fail(h, UBM_ERR_UNSUPPORTED, "model kind not in the device registry (no CPU fallback)");
+}
+
+static int plan_build(ubm_handle* h, int mode, int32_t model_kind, const void* model, int32_t h_kind,
+                      const ubm_bins* bins, int64_t k, int64_t m, int64_t lag, int64_t max_it, int64_t max_nrep,
+                      int64_t stride, ubm_plan** out) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!model || !out) return fail(h, UBM_ERR_INVALID, "null model / out");
+  if (lag < 1) return fail(h, UBM_ERR_INVALID, "lag must be >= 1 (R/coupled_chains.R:50)");
+  if (max_nrep < 1) return fail(h, UBM_ERR_INVALID, "nrep must be >= 1");
+  if (mode == MODE_ESTIMATOR) {
+    if (k < 0) return fail(h, UBM_ERR_INVALID, "k must be >= 0");
+    if (k > m) return fail(h, UBM_ERR_INVALID, "error: k has to be less than m");       // R/unbiasedestimator.R:44-47
+    if (lag > m) return fail(h, UBM_ERR_INVALID, "error: lag has to be less than m");   // :48-51
+  }
+  if (h_kind < UBM_H_IDENTITY || h_kind > UBM_H_BOTH) return fail(h, UBM_ERR_UNSUPPORTED, "unknown test function h");
+  CU(cudaSetDevice(h->device));
+  ubm_plan* p = new ubm_plan();
+  p->h = h; p->mode = mode; p->h_kind = h_kind;
+  p->k = k; p->m = m; p->lag = lag; p->max_it = max_it; p->max_nrep = max_nrep; p->stride = stride;
+  int st = register_model(p, model_kind, model);
+  if (st != UBM_OK) { delete p; return st; }
+  p->dimh = (h_kind == UBM_H_BOTH) ? 2 * p->dim : p->dim;
+  if (mode == MODE_ESTIMATOR && bins && bins->nbreaks >= 2) {
+    if (bins->nbreaks > 257) { delete p; return fail(h, UBM_ERR_INVALID, "at most 256 bins"); }
+    if (bins->component < 0 || bins->component >= p->dim) { delete p; return fail(h, UBM_ERR_INVALID, "bins: component out of range"); }
+    for (int i = 1; i < bins->nbreaks; ++i)
+      if (!(bins->breaks[i] > bins->breaks[i - 1])) { delete p; return fail(h, UBM_ERR_INVALID, "bins: breaks must increase"); }
+    p->nbreaks = bins->nbreaks; p->nbins = bins->nbreaks - 1; p->component = bins->component;
+  }
+  auto alloc_all = [&]() -> cudaError_t {
+    cudaError_t e;
+    size_t n = (size_t)max_nrep;
+    if ((e = p->tau.alloc(n * 8)) != cudaSuccess) return e;
+    if ((e = p->cost.alloc(n * 8)) != cudaSuccess) return e;
+    if ((e = p->iter.alloc(n * 8)) != cudaSuccess) return e;
+    if (mode == MODE_ESTIMATOR) {
+      if ((e = p->uest.alloc(n * p->dimh * 8)) != cudaSuccess) return e;
+      if ((e = p->mcmc.alloc(n * p->dimh * 8)) != cudaSuccess) return e;
+      if ((e = p->corr.alloc(n * p->dimh * 8)) != cudaSuccess) return e;
+    }
+    if (p->nbins) {
+      if ((e = p->bin_acc.alloc((size_t)2 * p->nbins * 8)) != cudaSuccess) return e;
+      if ((e = p->breaks.alloc((size_t)p->nbreaks * 8)) != cudaSuccess) return e;
+      if ((e = cudaMemcpy(p->breaks.p, bins->breaks, (size_t)p->nbreaks * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    }
+    if ((e = p->summary.alloc((size_t)ubm_summary_len(p->dimh, p->nbins) * 8)) != cudaSuccess) return e;
+    if ((e = p->counter.alloc(8)) != cudaSuccess) return e;
+    if ((e = p->status.alloc(4)) != cudaSuccess) return e;
+    if (mode == MODE_CHAINS) {
+      size_t sz = n * (size_t)stride * p->dim * 8;
+      if ((e = p->samples1.alloc(sz)) != cudaSuccess) return e;
+      if ((e = p->samples2.alloc(sz)) != cudaSuccess) return e;
+    }
+    if ((e = cudaEventCreate(&p->e0)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&p->e1)) != cudaSuccess) return e;
+    if ((e = cudaEventCreate(&p->e2)) != cudaSuccess) return e;
+    return cudaSuccess;
+  };
+  cudaError_t e = alloc_all();
+  if (e != cudaSuccess) { delete p; return fail(h, e == cudaErrorMemoryAllocation ? UBM_ERR_NOMEM : UBM_ERR_CUDA, std::string("plan alloc: ") + cudaGetErrorString(e)); }
+  *out = p;
+  return UBM_OK;
+}
+
+static int plan_set_tapes(ubm_plan* p, const ubm_draws* d, int64_t nrep) {
+  ubm_handle* h = p->h;
+  auto up = [&](DevBuf& b, const double* src, int64_t len) -> cudaError_t {
+    if (!src || len <= 0) return b.alloc(0);
+    cudaError_t e = b.alloc((size_t)nrep * len * 8);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(b.p, src, (size_t)nrep * len * 8, cudaMemcpyHostToDevice);
+  };
+  CU(up(p->tape_u, d->tape_u, d->len_u));
+  CU(up(p->tape_n, d->tape_n, d->len_n));
+  CU(up(p->tape_e, d->tape_e, d->len_e));
+  p->len_u = d->tape_u ? d->len_u : 0; p->len_n = d->tape_n ? d->len_n : 0; p->len_e = d->tape_e ? d->len_e : 0;
+  return UBM_OK;
+}
+
+static int plan_run(ubm_plan* p, int draws_mode, uint64_t seed, int64_t nrep, int64_t rep_offset) {
+  ubm_handle* h = p->h;
+  if (nrep < 1 || nrep > p->max_nrep) return fail(h, UBM_ERR_INVALID, "nrep outside the plan's capacity");
+  CU(cudaSetDevice(h->device));
+  RunParams P{};
+  P.mode = p->mode; P.h_kind = p->h_kind;
+  P.k = p->k; P.m = p->m; P.lag = p->lag; P.max_it = p->max_it;
+  if (p->mode == MODE_CHAINS) {   // storage cap acts as max_iterations (include/ubm.h)
+    int64_t cap = p->stride - 1;
+    if (P.max_it <= 0 || P.max_it > cap) P.max_it = cap;
+  }
+  P.nrep = nrep; P.rep_offset = rep_offset;
+  P.draws_mode = draws_mode; P.seed = seed;
+  P.tape_u = p->tape_u.as<double>(); P.tape_n = p->tape_n.as<double>(); P.tape_e = p->tape_e.as<double>();
+  P.len_u = p->len_u; P.len_n = p->len_n; P.len_e = p->len_e;
+  P.component = p->component; P.nbreaks = p->nbreaks; P.breaks = p->breaks.as<double>();
+  P.uest = p->uest.as<double>(); P.mcmc = p->mcmc.as<double>(); P.corr = p->corr.as<double>();
+  P.tau = p->tau.as<double>(); P.cost = p->cost.as<double>(); P.iter = p->iter.as<int64_t>();
+  P.bins_out = p->want_bins_out ? p->bins_out.as<double>() : nullptr;
+  P.bin_acc = p->bin_acc.as<long long>();
+  P.samples1 = p->samples1.as<double>(); P.samples2 = p->samples2.as<double>(); P.stride = p->stride;
+  P.work_counter = p->counter.as<unsigned long long>(); P.status = p->status.as<int>();
+  cudaStream_t st = h->stream;
+  CU(cudaMemsetAsync(p->counter.p, 0, 8, st));
+  CU(cudaMemsetAsync(p->status.p, 0, 4, st));
+  if (p->nbins) CU(cudaMemsetAsync(p->bin_acc.p, 0, p->bin_acc.bytes, st));
+  const bool tape = draws_mode == UBM_DRAWS_TAPE;
+  const int nsm = h->prop.multiProcessorCount;
+  CU(cudaEventRecord(p->e0, st));
+  if (p->model_kind == UBM_MODEL_NORMAL_MIXTURE) {
+    const int threads = 128;
+    size_t smem = sizeof(double) * ((p->nbreaks + 1) & ~1) + (size_t)p->nbins * threads * sizeof(int);
+    auto kern = tape ? mix_driver_kernel<true> : mix_driver_kernel<false>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) return fail(h, UBM_ERR_INVALID, "normal mixture: too many bins for shared memory");
+    int64_t need = (nrep + threads - 1) / threads;
+    int grid = (int)std::min<int64_t>((int64_t)nsm * per_sm, need);
+    kern<<<grid, threads, smem, st>>>(p->mix, P);
+    h->launches += 1;
+  } else if (p->model_kind == UBM_MODEL_MVN) {
+    int stl = mvn_launch(p->mvn, P, tape, nsm, st, p->scratch, &h->launches, &h->err);
+    if (stl != UBM_OK) return stl;
+  } else {
+    return fail(h, UBM_ERR_UNSUPPORTED, "model kind not in the device registry");
+  }
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(p->e1, st));
+  SummaryArgs A{};
+  A.nrep = nrep; A.dimh = (p->mode == MODE_ESTIMATOR) ? p->dimh : 0; A.nbins = p->nbins;
+  A.tau = P.tau; A.cost = P.cost; A.iter = P.iter; A.uest = (p->mode == MODE_ESTIMATOR) ? P.uest : nullptr;
+  A.bin_acc = P.bin_acc; A.denom = (double)(p->m - p->k + 1); A.summary = p->summary.as<double>();
+  if (p->mode == MODE_ESTIMATOR) {
+    int cols = UBM_SUMMARY_HEAD + 2 * p->dimh + 2 * p->nbins;
+    summary_kernel<<<cols, 1024, 0, st>>>(A);
+  } else {
+    summary_kernel<<<UBM_SUMMARY_HEAD, 1024, 0, st>>>(A);
+  }
+  h->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(p->e2, st));
+  p->last_nrep = nrep;
+  return UBM_OK;
+}
+
+static int plan_fetch(ubm_plan* p, const ubm_estimator_out* out) {
+  ubm_handle* h = p->h;
+  cudaStream_t st = h->stream;
+  CU(cudaStreamSynchronize(st));
+  int status = 0;
+  CU(cudaMemcpy(&status, p->status.p, 4, cudaMemcpyDeviceToHost));
+  size_t n = (size_t)p->last_nrep;
+  if (out) {
+    if (p->mode == MODE_ESTIMATOR) {
+      if (out->uestimator) CU(cudaMemcpy(out->uestimator, p->uest.p, n * p->dimh * 8, cudaMemcpyDeviceToHost));
+      if (out->mcmcestimator) CU(cudaMemcpy(out->mcmcestimator, p->mcmc.p, n * p->dimh * 8, cudaMemcpyDeviceToHost));
+      if (out->correction) CU(cudaMemcpy(out->correction, p->corr.p, n * p->dimh * 8, cudaMemcpyDeviceToHost));
+      if (out->bins && p->nbins && p->want_bins_out)
+        CU(cudaMemcpy(out->bins, p->bins_out.p, n * p->nbins * 8, cudaMemcpyDeviceToHost));
+    }
+    if (out->meetingtime) CU(cudaMemcpy(out->meetingtime, p->tau.p, n * 8, cudaMemcpyDeviceToHost));
+    if (out->iteration) CU(cudaMemcpy(out->iteration, p->iter.p, n * 8, cudaMemcpyDeviceToHost));
+    if (out->cost) CU(cudaMemcpy(out->cost, p->cost.p, n * 8, cudaMemcpyDeviceToHost));
+    if (out->summary) {
+      size_t len = (p->mode == MODE_ESTIMATOR) ? (size_t)ubm_summary_len(p->dimh, p->nbins) : (size_t)UBM_SUMMARY_HEAD;
+      CU(cudaMemcpy(out->summary, p->summary.p, len * 8, cudaMemcpyDeviceToHost));
+    }
+  }
+  if (status == UBM_ERR_TAPE) return fail(h, UBM_ERR_TAPE, "replay tape exhausted before a replicate finished");
+  if (status != 0) return fail(h, status, "device-side failure");
+  return UBM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ubm_create(int device, ubm_handle** out) {
+  if (!out) return UBM_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0 || device < 0 || device >= n) return UBM_ERR_CUDA;   // no CPU fallback
+  ubm_handle* h = new ubm_handle();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&h->prop, device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return UBM_ERR_CUDA;
+  }
+  *out = h;
+  return UBM_OK;
+}
+
+int ubm_destroy(ubm_handle* h) {
+  if (!h) return UBM_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return UBM_OK;
+}
+
+const char* ubm_last_error(const ubm_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int ubm_device_info(const ubm_handle* h, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor) {
+  if (!h) return UBM_ERR_INVALID;
+  if (name && name_len > 0) { strncpy(name, h->prop.name, name_len - 1); name[name_len - 1] = 0; }
+  if (sm_count) *sm_count = h->prop.multiProcessorCount;
+  if (cc_major) *cc_major = h->prop.major;
+  if (cc_minor) *cc_minor = h->prop.minor;
+  return UBM_OK;
+}
+
+int64_t ubm_launch_count(const ubm_handle* h) { return h ? h->launches : 0; }
+
+int64_t ubm_summary_len(int32_t dimh, int32_t nbins) { return UBM_SUMMARY_HEAD + 2 * (int64_t)dimh + 2 * (int64_t)nbins; }
+
+int ubm_model_dim(int32_t model_kind, const void* model, int32_t* dim) {
+  if (!dim) return UBM_ERR_INVALID;
+  return model_dims(model_kind, model, dim);
+}
+int ubm_h_dim(int32_t model_kind, const void* model, int32_t h_kind, int32_t* dimh) {
+  int d = 0;
+  int st = model_dims(model_kind, model, &d);
+  if (st != UBM_OK) return st;
+  if (h_kind < UBM_H_IDENTITY || h_kind > UBM_H_BOTH || !dimh) return UBM_ERR_INVALID;
+  *dimh = (h_kind == UBM_H_BOTH) ? 2 * d : d;
+  return UBM_OK;
+}
+
+int ubm_plan_create(ubm_handle* h, int32_t model_kind, const void* model, int32_t h_kind, const ubm_bins* bins,
+                    int64_t k, int64_t m, int64_t lag, int64_t max_iterations, int64_t max_nrep, ubm_plan** out) {
+  return plan_build(h, MODE_ESTIMATOR, model_kind, model, h_kind, bins, k, m, lag, max_iterations, max_nrep, 0, out);
+}
+int ubm_plan_launch(ubm_plan* p, uint64_t seed, int64_t nrep, int64_t rep_offset) {
+  if (!p) return UBM_ERR_INVALID;
+  return plan_run(p, UBM_DRAWS_PHILOX, seed, nrep, rep_offset);
+}
+int ubm_plan_fetch(ubm_plan* p, const ubm_estimator_out* out) {
+  if (!p) return UBM_ERR_INVALID;
+  return plan_fetch(p, out);
+}
+int ubm_plan_summary_dev(ubm_plan* p, void** dev_ptr, int64_t* len) {
+  if (!p) return UBM_ERR_INVALID;
+  if (dev_ptr) *dev_ptr = p->summary.p;
+  if (len) *len = ubm_summary_len(p->dimh, p->nbins);
+  return UBM_OK;
+}
+int ubm_plan_stream(ubm_plan* p, void** cuda_stream) {
+  if (!p || !cuda_stream) return UBM_ERR_INVALID;
+  *cuda_stream = (void*)p->h->stream;
+  return UBM_OK;
+}
+int ubm_plan_last_ms(ubm_plan* p, float* ms_main_kernel, float* ms_total) {
+  if (!p) return UBM_ERR_INVALID;
+  ubm_handle* h = p->h;
+  CU(cudaEventSynchronize(p->e2));
+  if (ms_main_kernel) CU(cudaEventElapsedTime(ms_main_kernel, p->e0, p->e1));
+  if (ms_total) CU(cudaEventElapsedTime(ms_total, p->e0, p->e2));
+  return UBM_OK;
+}
+int ubm_plan_destroy(ubm_plan* p) {
+  if (!p) return UBM_OK;
+  cudaSetDevice(p->h->device);
+  cudaStreamSynchronize(p->h->stream);
+  delete p;
+  return UBM_OK;
+}
+
+int ubm_sample_meetingtime(ubm_handle* h, int32_t model_kind, const void* model, const ubm_draws* draws, int64_t lag,
+                           int64_t max_iterations, int64_t nrep, int64_t rep_offset, double* meetingtime) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!draws || !meetingtime) return fail(h, UBM_ERR_INVALID, "null draws / output");
+  ubm_plan* p = nullptr;
+  int st = plan_build(h, MODE_MEETING, model_kind, model, UBM_H_IDENTITY, nullptr, 0, 1, lag, max_iterations, nrep, 0, &p);
+  if (st != UBM_OK) return st;
+  if (draws->mode == UBM_DRAWS_TAPE) st = plan_set_tapes(p, draws, nrep);
+  if (st == UBM_OK) st = plan_run(p, draws->mode, draws->seed, nrep, rep_offset);
+  if (st == UBM_OK) {
+    ubm_estimator_out o{};
+    o.meetingtime = meetingtime;
+    st = plan_fetch(p, &o);
+  }
+  ubm_plan_destroy(p);
+  return st;
+}
+
+int ubm_sample_unbiasedestimator(ubm_handle* h, int32_t model_kind, const void* model, const ubm_draws* draws,
+                                 int32_t h_kind, const ubm_bins* bins, int64_t k, int64_t m, int64_t lag,
+                                 int64_t max_iterations, int64_t nrep, int64_t rep_offset, const ubm_estimator_out* out) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!draws || !out) return fail(h, UBM_ERR_INVALID, "null draws / out");
+  ubm_plan* p = nullptr;
+  int st = plan_build(h, MODE_ESTIMATOR, model_kind, model, h_kind, bins, k, m, lag, max_iterations, nrep, 0, &p);
+  if (st != UBM_OK) return st;
+  if (out->bins && p->nbins) {
+    p->want_bins_out = true;
+    if (p->bins_out.alloc((size_t)nrep * p->nbins * 8) != cudaSuccess) { ubm_plan_destroy(p); return fail(h, UBM_ERR_NOMEM, "bins_out alloc"); }
+  }
+  if (draws->mode == UBM_DRAWS_TAPE) st = plan_set_tapes(p, draws, nrep);
+  if (st == UBM_OK) st = plan_run(p, draws->mode, draws->seed, nrep, rep_offset);
+  if (st == UBM_OK) st = plan_fetch(p, out);
+  ubm_plan_destroy(p);
+  return st;
+}
+
+int ubm_sample_coupled_chains(ubm_handle* h, int32_t model_kind, const void* model, const ubm_draws* draws, int64_t m,
+                              int64_t lag, int64_t max_iterations, int64_t stride, int64_t nrep, int64_t rep_offset,
+                              double* samples1, double* samples2, double* meetingtime, int64_t* iteration, double* cost) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!draws || !samples1 || !samples2) return fail(h, UBM_ERR_INVALID, "null draws / sample buffers");
+  if (stride < lag + 2) return fail(h, UBM_ERR_INVALID, "stride must be at least lag + 2 rows");
+  ubm_plan* p = nullptr;
+  int st = plan_build(h, MODE_CHAINS, model_kind, model, UBM_H_IDENTITY, nullptr, 0, m, lag, max_iterations, nrep, stride, &p);
+  if (st != UBM_OK) return st;
+  if (draws->mode == UBM_DRAWS_TAPE) st = plan_set_tapes(p, draws, nrep);
+  if (st == UBM_OK) {
+    cudaMemsetAsync(p->samples1.p, 0xFF, p->samples1.bytes, h->stream);   // NaN fill: rows never written stay NaN
+    cudaMemsetAsync(p->samples2.p, 0xFF, p->samples2.bytes, h->stream);
+    st = plan_run(p, draws->mode, draws->seed, nrep, rep_offset);
+  }
+  if (st == UBM_OK) {
+    ubm_estimator_out o{};
+    o.meetingtime = meetingtime; o.iteration = iteration; o.cost = cost;
+    st = plan_fetch(p, &o);
+  }
+  if (st == UBM_OK || st == UBM_ERR_TAPE) {
+    cudaMemcpy(samples1, p->samples1.p, p->samples1.bytes, cudaMemcpyDeviceToHost);
+    cudaMemcpy(samples2, p->samples2.p, p->samples2.bytes, cudaMemcpyDeviceToHost);
+  }
+  ubm_plan_destroy(p);
+  return st;
+}
+
+int ubm_h_bar(ubm_handle* h, int32_t dim, int32_t h_kind, int64_t k, int64_t m, int64_t lag, int64_t stride,
+              int64_t nrep, const double* samples1, const double* samples2, const double* meetingtime,
+              const int64_t* iteration, double* hbar) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!samples1 || !samples2 || !meetingtime || !iteration || !hbar) return fail(h, UBM_ERR_INVALID, "null buffer");
+  if (h_kind < UBM_H_IDENTITY || h_kind > UBM_H_BOTH) return fail(h, UBM_ERR_UNSUPPORTED, "unknown test function h");
+  for (int64_t r = 0; r < nrep; ++r) {   // R/H_bar.R:21-28
+    if (k > iteration[r]) return fail(h, UBM_ERR_INVALID, "error: k has to be less than the horizon of the coupled chains");
+    if (m > iteration[r]) return fail(h, UBM_ERR_INVALID, "error: m has to be less than the horizon of the coupled chains");
+  }
+  CU(cudaSetDevice(h->device));
+  const int dimh = (h_kind == UBM_H_BOTH) ? 2 * dim : dim;
+  DevBuf s1, s2, mt, out;
+  size_t sz = (size_t)nrep * stride * dim * 8;
+  CU(s1.alloc(sz)); CU(s2.alloc(sz)); CU(mt.alloc((size_t)nrep * 8)); CU(out.alloc((size_t)nrep * dimh * 8));
+  CU(cudaMemcpyAsync(s1.p, samples1, sz, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(s2.p, samples2, sz, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(mt.p, meetingtime, (size_t)nrep * 8, cudaMemcpyHostToDevice, h->stream));
+  int64_t total = nrep * dimh;
+  hbar_kernel<<<(unsigned)((total + 127) / 128), 128, 0, h->stream>>>(s1.as<double>(), s2.as<double>(), mt.as<double>(), dim, h_kind, k, m, lag, stride, nrep, out.as<double>());
+  h->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(hbar, out.p, (size_t)nrep * dimh * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return UBM_OK;
+}
+
+int ubm_estimator_bins(ubm_handle* h, int32_t dim, const ubm_bins* bins, int64_t k, int64_t m, int64_t lag,
+                       int64_t stride, int64_t nrep, const double* samples1, const double* samples2,
+                       const double* meetingtime, double* binvals) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!bins || bins->nbreaks < 2 || !samples1 || !samples2 || !meetingtime || !binvals) return fail(h, UBM_ERR_INVALID, "null buffer / bins");
+  if (bins->component < 0 || bins->component >= dim) return fail(h, UBM_ERR_INVALID, "bins: component out of range");
+  CU(cudaSetDevice(h->device));
+  const int nbins = bins->nbreaks - 1;
+  DevBuf s1, s2, mt, br, out;
+  size_t sz = (size_t)nrep * stride * dim * 8;
+  CU(s1.alloc(sz)); CU(s2.alloc(sz)); CU(mt.alloc((size_t)nrep * 8)); CU(br.alloc((size_t)bins->nbreaks * 8));
+  CU(out.alloc((size_t)nrep * nbins * 8));
+  CU(cudaMemcpyAsync(s1.p, samples1, sz, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(s2.p, samples2, sz, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(mt.p, meetingtime, (size_t)nrep * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(br.p, bins->breaks, (size_t)bins->nbreaks * 8, cudaMemcpyHostToDevice, h->stream));
+  int64_t total = nrep * nbins;
+  estimator_bin_kernel<<<(unsigned)((total + 127) / 128), 128, 0, h->stream>>>(s1.as<double>(), s2.as<double>(), mt.as<double>(), dim, bins->component, br.as<double>(), nbins, k, m, lag, stride, nrep, out.as<double>());
+  h->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(binvals, out.p, (size_t)nrep * nbins * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return UBM_OK;
+}
+
+}  // extern "C"

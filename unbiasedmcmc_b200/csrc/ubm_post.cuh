@@ -1,0 +1,73 @@
+// ubm_post.cuh — estimators from STORED coupled chains, batched over replicates:
+//   hbar_kernel            R/H_bar.R:19-54
+//   estimator_bin_kernel   src/estimator_bin.cpp:10-42
+// Layout of the stored chains: samples1[r][t][dim], samples2[r][t][dim] (stride rows per replicate), as
+// written by the MODE_CHAINS drivers.  One thread per (replicate, output); each thread walks time in the
+// reference's order, so results equal the oracle's bit for bit.  These are the only HBM-streaming kernels
+// on the path (algorithmic bytes: 8 (m-k+1 + 2 (tau-k-lag)) per output).
+#pragma once
+#include "ubm_common.cuh"
+
+namespace ubm {
+
+__device__ inline double h_component(int h_kind, const double* x, int dim, int i) {
+  if (h_kind == UBM_H_IDENTITY) return x[i];
+  if (h_kind == UBM_H_SQUARE) return x[i] * x[i];
+  return (i < dim) ? x[i] : x[i - dim] * x[i - dim];
+}
+
+__global__ void hbar_kernel(const double* __restrict__ s1, const double* __restrict__ s2,
+                            const double* __restrict__ mt, int dim, int h_kind, int64_t k, int64_t m, int64_t lag,
+                            int64_t stride, int64_t nrep, double* __restrict__ out) {
+  const int dimh = (h_kind == UBM_H_BOTH) ? 2 * dim : dim;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nrep * dimh) return;
+  int64_t r = idx / dimh;
+  int i = (int)(idx - r * dimh);
+  const double* a = s1 + r * stride * dim;
+  const double* b = s2 + r * stride * dim;
+  double acc = 0.0;
+  for (int64_t t = k; t <= m; ++t) acc = acc + h_component(h_kind, a + t * dim, dim, i);       // :33-39
+  double tau = mt[r];
+  if (!(tau <= (double)(k + lag))) {                                                            // :42-51
+    int64_t T = (int64_t)tau;
+    for (int64_t t = k + lag; t <= T - 1; ++t) {
+      double w = (double)corr_weight(t, k, m, lag);
+      acc = acc + w * (h_component(h_kind, a + t * dim, dim, i) - h_component(h_kind, b + (t - lag) * dim, dim, i));
+    }
+  }
+  out[idx] = acc / (double)(m - k + 1);                                                         // :53
+}
+
+__global__ void estimator_bin_kernel(const double* __restrict__ s1, const double* __restrict__ s2,
+                                     const double* __restrict__ mt, int dim, int component,
+                                     const double* __restrict__ breaks, int nbins, int64_t k, int64_t m, int64_t lag,
+                                     int64_t stride, int64_t nrep, double* __restrict__ out) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nrep * nbins) return;
+  int64_t r = idx / nbins;
+  int b = (int)(idx - r * nbins);
+  const double lower = breaks[b], upper = breaks[b + 1];
+  const double* a = s1 + r * stride * dim + component;
+  const double* c = s2 + r * stride * dim + component;
+  double estimator = 0;
+  for (int64_t t = k; t <= m; ++t) {                                                            // :15-19
+    double x = a[t * dim];
+    if (x > lower && x < upper) estimator += 1;
+  }
+  double tau = mt[r];
+  if (tau > (double)(k + lag)) {                                                                // :21
+    int64_t T = (int64_t)tau;
+    for (int64_t t = k + lag; t <= T - 1; ++t) {
+      double coefficient = (double)corr_weight(t, k, m, lag);                                   // :26
+      double increment = 0.;
+      double x = a[t * dim], y = c[(t - lag) * dim];
+      if (x > lower && x < upper) increment += coefficient;
+      if (y > lower && y < upper) increment -= coefficient;
+      estimator += increment;
+    }
+  }
+  out[idx] = estimator / ((double)(m - k) + 1.);                                                // :41
+}
+
+}  // namespace ubm

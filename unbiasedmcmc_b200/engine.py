@@ -1,0 +1,175 @@
+"""Thin Python host over the C ABI of libubm.so (include/ubm.h).
+
+Everything here is argument marshalling: numpy arrays in, numpy arrays out, one C call per method.
+All computation happens in the CUDA kernels behind the C ABI; there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+
+
+class UbmError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"ubm status {status}: {message}")
+        self.status = status
+
+
+def alloc_estimator_out(nrep, dimh, nbins, per_replicate=True, want_bins=True):
+    res = {
+        "uestimator": np.zeros((nrep, dimh)), "mcmcestimator": np.zeros((nrep, dimh)),
+        "correction": np.zeros((nrep, dimh)), "meetingtime": np.zeros(nrep),
+        "iteration": np.zeros(nrep, dtype=np.int64), "cost": np.zeros(nrep),
+        "bins": np.zeros((nrep, nbins)) if (nbins and want_bins) else None,
+        "summary": np.zeros(A.summary_len(dimh, nbins)),
+    }
+    if not per_replicate:
+        for k in ("uestimator", "mcmcestimator", "correction", "meetingtime", "iteration", "cost", "bins"):
+            res[k] = None
+    out = A.ubm_estimator_out(A.dptr(res["uestimator"]), A.dptr(res["mcmcestimator"]), A.dptr(res["correction"]),
+                              A.dptr(res["meetingtime"]), A.i64ptr(res["iteration"]), A.dptr(res["cost"]),
+                              A.dptr(res["bins"]), A.dptr(res["summary"]))
+    return res, out
+
+
+class Engine:
+    """One handle = one device + one CUDA stream (include/ubm.h: ubm_create)."""
+
+    def __init__(self, device=0):
+        self.lib = A.load_lib()
+        self.h = C.c_void_p()
+        st = self.lib.ubm_create(int(device), C.byref(self.h))
+        if st != A.UBM_OK:
+            raise UbmError(st, "ubm_create failed: no usable CUDA device (the engine has no CPU fallback)")
+        self.device = int(device)
+
+    def close(self):
+        if self.h:
+            self.lib.ubm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != A.UBM_OK:
+            raise UbmError(st, self.lib.ubm_last_error(self.h).decode())
+
+    def device_info(self):
+        name = C.create_string_buffer(128)
+        sm, maj, mnr = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(self.lib.ubm_device_info(self.h, name, 128, C.byref(sm), C.byref(maj), C.byref(mnr)))
+        return {"name": name.value.decode(), "sm_count": sm.value, "cc": (maj.value, mnr.value)}
+
+    def launch_count(self):
+        return int(self.lib.ubm_launch_count(self.h))
+
+    # ---- the three drivers -------------------------------------------------------------------------
+    def sample_meetingtime(self, model, draws, lag=1, max_iterations=0, nrep=1, rep_offset=0):
+        mt = np.empty(nrep, dtype=np.float64)
+        ds = draws.struct(nrep)
+        self._check(self.lib.ubm_sample_meetingtime(self.h, model.kind, model.ref(), C.byref(ds), lag, max_iterations,
+                                                    nrep, rep_offset, A.dptr(mt)))
+        return {"meetingtime": mt}
+
+    def sample_unbiasedestimator(self, model, draws, h_kind=A.UBM_H_IDENTITY, bins=None, k=0, m=1, lag=1,
+                                 max_iterations=0, nrep=1, rep_offset=0, per_replicate=True, want_bins=True):
+        dimh = model.h_dim(h_kind)
+        nbins = bins.nbins if bins is not None else 0
+        res, out = alloc_estimator_out(nrep, dimh, nbins, per_replicate, want_bins)
+        ds = draws.struct(nrep)
+        bs = bins.struct() if bins is not None else None
+        self._check(self.lib.ubm_sample_unbiasedestimator(
+            self.h, model.kind, model.ref(), C.byref(ds), h_kind, C.byref(bs) if bs is not None else None, k, m, lag,
+            max_iterations, nrep, rep_offset, C.byref(out)))
+        return res
+
+    def sample_coupled_chains(self, model, draws, m=1, lag=1, max_iterations=0, stride=None, nrep=1, rep_offset=0):
+        d = model.dim
+        if stride is None:
+            raise ValueError("stride (rows of storage per replicate) is required")
+        s1 = np.empty((nrep, stride, d))
+        s2 = np.empty((nrep, stride, d))
+        mt = np.zeros(nrep)
+        it = np.zeros(nrep, dtype=np.int64)
+        cost = np.zeros(nrep)
+        ds = draws.struct(nrep)
+        self._check(self.lib.ubm_sample_coupled_chains(self.h, model.kind, model.ref(), C.byref(ds), m, lag,
+                                                       max_iterations, stride, nrep, rep_offset, A.dptr(s1),
+                                                       A.dptr(s2), A.dptr(mt), A.i64ptr(it), A.dptr(cost)))
+        return {"samples1": s1, "samples2": s2, "meetingtime": mt, "iteration": it, "cost": cost, "lag": lag}
+
+    # ---- estimators from stored chains -------------------------------------------------------------
+    def h_bar(self, chains, h_kind=A.UBM_H_IDENTITY, k=0, m=1):
+        s1, s2 = chains["samples1"], chains["samples2"]
+        nrep, stride, d = s1.shape
+        dimh = 2 * d if h_kind == A.UBM_H_BOTH else d
+        out = np.zeros((nrep, dimh))
+        self._check(self.lib.ubm_h_bar(self.h, d, h_kind, k, m, chains["lag"], stride, nrep, A.dptr(s1), A.dptr(s2),
+                                       A.dptr(chains["meetingtime"]), A.i64ptr(chains["iteration"]), A.dptr(out)))
+        return out
+
+    def estimator_bins(self, chains, bins, k=0, m=1):
+        s1, s2 = chains["samples1"], chains["samples2"]
+        nrep, stride, d = s1.shape
+        out = np.zeros((nrep, bins.nbins))
+        bs = bins.struct()
+        self._check(self.lib.ubm_estimator_bins(self.h, d, C.byref(bs), k, m, chains["lag"], stride, nrep, A.dptr(s1),
+                                                A.dptr(s2), A.dptr(chains["meetingtime"]), A.dptr(out)))
+        return out
+
+    # ---- device-resident plan (kernel-only timing, multi-GPU summaries) -----------------------------
+    def plan(self, model, h_kind=A.UBM_H_IDENTITY, bins=None, k=0, m=1, lag=1, max_iterations=0, max_nrep=1):
+        return Plan(self, model, h_kind, bins, k, m, lag, max_iterations, max_nrep)
+
+
+class Plan:
+    def __init__(self, eng, model, h_kind, bins, k, m, lag, max_iterations, max_nrep):
+        self.eng, self.model, self.bins = eng, model, bins
+        self.dimh = model.h_dim(h_kind)
+        self.nbins = bins.nbins if bins is not None else 0
+        self.max_nrep = max_nrep
+        self.p = C.c_void_p()
+        bs = bins.struct() if bins is not None else None
+        eng._check(eng.lib.ubm_plan_create(eng.h, model.kind, model.ref(), h_kind,
+                                           C.byref(bs) if bs is not None else None, k, m, lag, max_iterations,
+                                           max_nrep, C.byref(self.p)))
+
+    def launch(self, seed, nrep, rep_offset=0):
+        self.eng._check(self.eng.lib.ubm_plan_launch(self.p, int(seed) & (2**64 - 1), nrep, rep_offset))
+        self.last_nrep = nrep
+
+    def fetch(self, per_replicate=False):
+        res, out = alloc_estimator_out(self.last_nrep, self.dimh, self.nbins, per_replicate, want_bins=False)
+        self.eng._check(self.eng.lib.ubm_plan_fetch(self.p, C.byref(out)))
+        return res
+
+    def last_ms(self):
+        a, b = C.c_float(), C.c_float()
+        self.eng._check(self.eng.lib.ubm_plan_last_ms(self.p, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def summary_dev(self):
+        ptr, n = C.c_void_p(), C.c_int64()
+        self.eng._check(self.eng.lib.ubm_plan_summary_dev(self.p, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def stream(self):
+        s = C.c_void_p()
+        self.eng._check(self.eng.lib.ubm_plan_stream(self.p, C.byref(s)))
+        return s.value
+
+    def close(self):
+        if self.p:
+            self.eng.lib.ubm_plan_destroy(self.p)
+            self.p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,130 @@
+"""Device-side model registry, host view.
+
+Each class holds the numpy arrays of one registered model and exposes `.kind` and `.struct()` — the
+`ubm_model_*` struct of include/ubm.h.  These play the role of the closure triples
+(single_kernel, coupled_kernel, rinit) that the reference's drivers take (R/coupled_chains.R:39):
+R closures cannot run on a GPU, so kernels returned by `get_mh_kernels` & co. carry one of these specs.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _colmajor(a):
+    """Flat column-major (R layout) copy of a 2-D array."""
+    a = np.asarray(a, dtype=np.float64)
+    return np.ascontiguousarray(a.T).reshape(-1)
+
+
+class ModelSpec:
+    kind = 0
+    dim = 0
+
+    def struct(self):
+        raise NotImplementedError
+
+    def ref(self):
+        s = self.struct()
+        self._keep = s
+        return C.cast(C.pointer(s), C.c_void_p)
+
+    def h_dim(self, h_kind):
+        return 2 * self.dim if h_kind == A.UBM_H_BOTH else self.dim
+
+
+class NormalMixtureRWMH(ModelSpec):
+    """C1 — README.Rmd:69-84 target / rinit; R/get_mh_kernels.R:20-79 (reflection-max) or
+    inst/reproducebimodal/bimodal.run.R:14-63 (max coupling)."""
+    kind = A.UBM_MODEL_NORMAL_MIXTURE
+    dim = 1
+
+    def __init__(self, weights, means, sds, proposal_sd, init_mean, init_sd,
+                 coupling=A.UBM_COUPLING_REFLECTION_MAX):
+        self.weights, self.means, self.sds = _f64(weights), _f64(means), _f64(sds)
+        if not (len(self.weights) == len(self.means) == len(self.sds)) or not 1 <= len(self.weights) <= 8:
+            raise ValueError("mixture needs 1..8 components with matching weights/means/sds")
+        self.proposal_sd, self.init_mean, self.init_sd = float(proposal_sd), float(init_mean), float(init_sd)
+        self.coupling = int(coupling)
+
+    def struct(self):
+        return A.ubm_model_normal_mixture(len(self.weights), self.coupling, A.dptr(self.weights), A.dptr(self.means),
+                                          A.dptr(self.sds), self.proposal_sd, self.init_mean, self.init_sd)
+
+
+class MvnRWMH(ModelSpec):
+    """C2 — inst/reproducescalingdimension/scaling.rwmh.reflectionmaxcoupling.R:12-103.
+    Takes covariance matrices (like the R script) and factorises on the host with numpy, as R's
+    chol()/solve(chol()) do before the kernels are built (R/get_mh_kernels.R:25-26)."""
+    kind = A.UBM_MODEL_MVN
+
+    def __init__(self, mean_pi, Sigma_pi, Sigma_proposal, init_mean, init_Sigma):
+        self.mean_pi = _f64(mean_pi)
+        d = self.dim = len(self.mean_pi)
+        if not 2 <= d <= 128:
+            raise ValueError("MVN model supports 2 <= d <= 128 (d = 1: use NormalMixtureRWMH, as R does)")
+        up = lambda S: np.linalg.cholesky(np.asarray(S, dtype=np.float64)).T  # R's chol(): upper factor
+        self.chol_pi = up(Sigma_pi)
+        self.chol_inv_pi = np.triu(np.linalg.inv(self.chol_pi))
+        self.chol_prop = up(Sigma_proposal)
+        self.chol_inv_prop = np.triu(np.linalg.inv(self.chol_prop))
+        self.init_mean = _f64(init_mean)
+        self.init_chol = up(init_Sigma)
+        self._flat = [_colmajor(np.triu(m)) for m in (self.chol_inv_pi, self.chol_prop, self.chol_inv_prop,
+                                                      self.init_chol)]
+
+    def struct(self):
+        return A.ubm_model_mvn(self.dim, 0, A.dptr(self.mean_pi), A.dptr(self._flat[0]), A.dptr(self._flat[1]),
+                               A.dptr(self._flat[2]), A.dptr(self.init_mean), A.dptr(self._flat[3]))
+
+
+class Draws:
+    """Draw source: Philox (seed) or replay tapes (arrays [nrep, len])."""
+
+    def __init__(self, seed=None, tape_u=None, tape_n=None, tape_e=None):
+        if seed is None and tape_u is None and tape_n is None and tape_e is None:
+            raise ValueError("give a seed (Philox) or tapes (replay)")
+        self.seed = seed
+        self.tapes = [None if t is None else np.ascontiguousarray(np.asarray(t, dtype=np.float64))
+                      for t in (tape_u, tape_n, tape_e)]
+
+    @property
+    def is_tape(self):
+        return self.seed is None
+
+    def struct(self, nrep=None):
+        if not self.is_tape:
+            return A.ubm_draws(A.UBM_DRAWS_PHILOX, 0, int(self.seed) & (2**64 - 1), A.dptr(None), A.dptr(None),
+                               A.dptr(None), 0, 0, 0)
+        lens = []
+        for t in self.tapes:
+            if t is None:
+                lens.append(0)
+            else:
+                if t.ndim != 2 or (nrep is not None and t.shape[0] < nrep):
+                    raise ValueError("tapes must be [nrep, len] with at least nrep rows")
+                lens.append(t.shape[1])
+        return A.ubm_draws(A.UBM_DRAWS_TAPE, 0, 0, A.dptr(self.tapes[0]), A.dptr(self.tapes[1]),
+                           A.dptr(self.tapes[2]), lens[0], lens[1], lens[2])
+
+
+class Bins:
+    """estimator_bin_ over all bins of one component (src/estimator_bin.cpp:10-42); component 0-based."""
+
+    def __init__(self, component, breaks):
+        self.component = int(component)
+        self.breaks = _f64(breaks)
+        if len(self.breaks) < 2 or len(self.breaks) > 257 or np.any(np.diff(self.breaks) <= 0):
+            raise ValueError("breaks must be 2..257 strictly increasing values")
+
+    @property
+    def nbins(self):
+        return len(self.breaks) - 1
+
+    def struct(self):
+        return A.ubm_bins(self.component, len(self.breaks), A.dptr(self.breaks))
