@@ -46,6 +46,9 @@ const char* ubm_last_error(const ubm_handle* h);
 int ubm_device_info(const ubm_handle* h, char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor);
 /* number of kernel launches issued by this handle so far (bench.py's gpu_launches) */
 int64_t ubm_launch_count(const ubm_handle* h);
+/* live roofline denominators that MEASURED_PEAKS.json lacks: FP64 FMA TFLOP/s (2 flop per fma) and INT32
+ * multiply-add Top/s, from saturating micro-kernels on this device */
+int ubm_measure_peaks(ubm_handle* h, double* fp64_tflops, double* int32_tops);
 
 /* ---------------------------------------------------------------------------------------------
  * draw sources.  Replaces R's global RNG stream (GetRNGstate/PutRNGstate brackets, e.g.

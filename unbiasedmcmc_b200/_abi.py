@@ -114,6 +114,8 @@ def load_lib():
     lib.ubm_device_info.argtypes = [vp, C.c_char_p, C.c_int, c_int32_p, c_int32_p, c_int32_p]
     lib.ubm_launch_count.argtypes = [vp]
     lib.ubm_launch_count.restype = C.c_int64
+    lib.ubm_measure_peaks.argtypes = [vp, c_double_p, c_double_p]
+    lib.ubm_measure_peaks.restype = C.c_int
     lib.ubm_summary_len.argtypes = [C.c_int32, C.c_int32]
     lib.ubm_summary_len.restype = C.c_int64
     lib.ubm_model_dim.argtypes = [C.c_int32, vp, c_int32_p]

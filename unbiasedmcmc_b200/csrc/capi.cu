@@ -14,6 +14,7 @@
 #include "ubm_mvn.cuh"
 #include "ubm_summary.cuh"
 #include "ubm_post.cuh"
+#include "ubm_peaks.cuh"
 
 using namespace ubm;
 
@@ -331,6 +332,37 @@ int ubm_device_info(const ubm_handle* h, char* name, int name_len, int* sm_count
 }
 
 int64_t ubm_launch_count(const ubm_handle* h) { return h ? h->launches : 0; }
+
+int ubm_measure_peaks(ubm_handle* h, double* fp64_tflops, double* int32_tops) {
+  if (!h) return UBM_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  DevBuf out;
+  CU(out.alloc(64));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  const int grid = h->prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  float best_d = 1e30f, best_i = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(e0, h->stream));
+    peak_dfma_kernel<<<grid, threads, 0, h->stream>>>(out.as<double>(), iters, 0.999999, 1e-9);
+    CU(cudaEventRecord(e1, h->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best_d) best_d = ms;
+    CU(cudaEventRecord(e0, h->stream));
+    peak_imad_kernel<<<grid, threads, 0, h->stream>>>(out.as<unsigned>(), iters, 1664525u, 1013904223u);
+    CU(cudaEventRecord(e1, h->stream));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best_i) best_i = ms;
+    h->launches += 2;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  const double ops = (double)grid * threads * iters * 64.0;   // fma / imad per launch
+  if (fp64_tflops) *fp64_tflops = 2.0 * ops / (best_d * 1e-3) * 1e-12;
+  if (int32_tops) *int32_tops = 2.0 * ops / (best_i * 1e-3) * 1e-12;
+  return UBM_OK;
+}
 
 int64_t ubm_summary_len(int32_t dimh, int32_t nbins) { return UBM_SUMMARY_HEAD + 2 * (int64_t)dimh + 2 * (int64_t)nbins; }
 

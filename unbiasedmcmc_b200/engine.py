@@ -65,6 +65,11 @@ class Engine:
         self._check(self.lib.ubm_device_info(self.h, name, 128, C.byref(sm), C.byref(maj), C.byref(mnr)))
         return {"name": name.value.decode(), "sm_count": sm.value, "cc": (maj.value, mnr.value)}
 
+    def measure_peaks(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.ubm_measure_peaks(self.h, C.byref(a), C.byref(b)))
+        return {"fp64_tflops": a.value, "int32_tops": b.value}
+
     def launch_count(self):
         return int(self.lib.ubm_launch_count(self.h))
 
