@@ -1,0 +1,23 @@
+"""Small single-launch cases for ncu (one driver-kernel launch each). Usage: python tools/prof_case.py c2|c1 [nrep]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests import cases
+from unbiasedmcmc_b200 import _abi as A
+from unbiasedmcmc_b200 import registry as R
+from unbiasedmcmc_b200.engine import Engine
+
+which = sys.argv[1]
+eng = Engine(0)
+if which == "c2":
+    nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 16
+    res = eng.sample_unbiasedestimator(cases.c2_model(100), R.Draws(seed=1), k=400, m=2000, lag=1, nrep=nrep, want_bins=False)
+elif which == "c2meet":
+    nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 16
+    res = eng.sample_meetingtime(cases.c2_model(100), R.Draws(seed=1), lag=1, nrep=nrep)
+elif which == "c1":
+    nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 18
+    res = eng.sample_unbiasedestimator(cases.c1_model(), R.Draws(seed=1), bins=cases.c1_bins(), k=500, m=2000, lag=500,
+                                       nrep=nrep, want_bins=False, per_replicate=False)
+print(which, "ok", res["meetingtime"][:4] if res.get("meetingtime") is not None else res["summary"][:6])

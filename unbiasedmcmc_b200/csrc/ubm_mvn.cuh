@@ -14,10 +14,21 @@
 //   phase B  prop = x + xi^T C_prop  (and eta)     (all active rows)
 //   phase C  w = Cinv_pi^T (prop - mean_pi)        (all proposals) -> log-density
 // Every output element is accumulated by ONE thread, sequentially in k with fma, so results are bit-identical
-// to the oracle's plain loops.  Triangular work is balanced by pairing column group g with nCG-1-g.
-// Slots are refilled from a global counter as soon as a replicate finishes (work stealing).
-// Reductions over a d-vector use the canonical order "fma chain inside each 4-column group, xor-butterfly
-// over the <= 32 groups" (oracle: sum_g4_*).
+// to the oracle's plain loops (structural zeros only ever add exact zeros).  Triangular work is balanced by
+// pairing column group g with nCG-1-g.  Slots are refilled from a global counter as soon as a replicate
+// finishes (work stealing).  Reductions over a d-vector use the canonical order "fma chain inside each
+// 4-column group, xor-butterfly over the <= 32 groups" (oracle: sum_g4_*).
+//
+// Thread roles (256 threads): warps 0-3 (one per SM sub-partition) run the GEMM phases with software-pipelined
+// operand loads; all 8 warps share the per-slot work (draws, coupling algebra, accept/reject, state and estimator
+// updates), one warp per slot at a time, so that step needs no CTA-wide barrier.
+//
+// Shared-memory layout notes (ncu, profiles/r01_mvn_*.md: the first version had 12.5e9 bank conflicts):
+//   - packed group g starts at 8 g (g+1) + 2 (g mod 8) + 14 (g div 8) doubles: the 16-byte pads spread the
+//     per-thread LDS.128 of different groups over different banks (unpadded, every group starts on bank 0);
+//   - vectors use a row stride of DP + 2 doubles (== 2 mod 4), so rows of different slots read at the same k
+//     fall into different banks while staying 16-byte aligned;
+//   - GEMM units are numbered row-group fastest, so a warp touches few column groups (matrix bytes dominate).
 #pragma once
 #include <algorithm>
 #include <string>
@@ -27,40 +38,43 @@
 namespace ubm {
 
 struct MvnDevice {
-  int d, DP, nCG, nPairs, zero_mean;
+  int d, DP, DPS, nCG, nPairs, zero_mean;
   int packLen;                 // doubles per packed matrix
   double cst;                  // src/mvnorm.cpp:74-75
   const double *mean_pi, *init_mean, *packA, *packB, *packC, *packI;   // device
   size_t offs[6];              // host-side: offsets inside the blob
 };
 
-// offset of column-group g inside a packed matrix: rows k = 0 .. min(4g+4, d)-1, 4 doubles per row
-__host__ __device__ inline int mvn_group_rows(int g, int d) { int K = 4 * g + 4; return K < d ? K : d; }
+// column group g holds rows k = 0 .. 4g+3 (rows >= d and entries below the diagonal are zero), 4 doubles per row
+__host__ __device__ __forceinline__ int mvn_group_off(int g) { return 8 * g * (g + 1) + 2 * (g & 7) + 14 * (g >> 3); }
+__host__ __device__ __forceinline__ int mvn_pack_len(int nCG) { return mvn_group_off(nCG - 1) + 16 * nCG + 16; }
 
 inline void mvn_pack_matrix(const double* Ucm, int d, int nCG, std::vector<double>* blob) {
+  size_t base = blob->size();
+  blob->resize(base + mvn_pack_len(nCG), 0.0);
   for (int g = 0; g < nCG; ++g) {
-    int K = mvn_group_rows(g, d);
-    for (int k = 0; k < K; ++k)
+    double* p = blob->data() + base + mvn_group_off(g);
+    for (int k = 0; k < 4 * g + 4; ++k)
       for (int c = 0; c < 4; ++c) {
         int j = 4 * g + c;
-        blob->push_back((j < d && k <= j) ? Ucm[(size_t)j * d + k] : 0.0);
+        p[4 * k + c] = (j < d && k <= j) ? Ucm[(size_t)j * d + k] : 0.0;
       }
   }
 }
 
 inline void mvn_pack_host(const ubm_model_mvn* s, MvnDevice* M, std::vector<double>* blob) {
   const int d = s->d;
-  M->d = d; M->nCG = (d + 3) / 4; M->DP = 4 * M->nCG; M->nPairs = (M->nCG + 1) / 2;
+  M->d = d; M->nCG = (d + 3) / 4; M->DP = 4 * M->nCG; M->DPS = M->DP + 2; M->nPairs = (M->nCG + 1) / 2;
   M->zero_mean = 1;
   for (int j = 0; j < d; ++j) if (s->mean_pi[j] != 0.0) M->zero_mean = 0;
   double halflogdet = 0.0;
   for (int j = 0; j < d; ++j) halflogdet = halflogdet + ubm_log(s->chol_inv_pi[(size_t)j * d + j]);
   M->cst = -(-halflogdet) - (d * 0.9189385);     // truncated constant kept verbatim (src/mvnorm.cpp:75)
+  M->packLen = mvn_pack_len(M->nCG);
   blob->clear();
-  M->offs[0] = blob->size(); for (int j = 0; j < M->DP; ++j) blob->push_back(j < d ? s->mean_pi[j] : 0.0);
-  M->offs[1] = blob->size(); for (int j = 0; j < M->DP; ++j) blob->push_back(j < d ? s->init_mean[j] : 0.0);
+  M->offs[0] = blob->size(); for (int j = 0; j < M->DPS; ++j) blob->push_back(j < d ? s->mean_pi[j] : 0.0);
+  M->offs[1] = blob->size(); for (int j = 0; j < M->DPS; ++j) blob->push_back(j < d ? s->init_mean[j] : 0.0);
   M->offs[2] = blob->size(); mvn_pack_matrix(s->chol_inv_prop, d, M->nCG, blob);
-  M->packLen = (int)(blob->size() - M->offs[2]);
   M->offs[3] = blob->size(); mvn_pack_matrix(s->chol_prop, d, M->nCG, blob);
   M->offs[4] = blob->size(); mvn_pack_matrix(s->chol_inv_pi, d, M->nCG, blob);
   M->offs[5] = blob->size(); mvn_pack_matrix(s->init_chol, d, M->nCG, blob);
@@ -72,40 +86,59 @@ inline void mvn_bind_device(MvnDevice* M, const double* dev) {
 
 enum { SL_IDLE = 0, SL_INIT = 1, SL_SINGLE = 2, SL_COUPLED = 3 };
 #define MVN_MAXR 16
+#define MVN_T 256      // threads per CTA
+#define MVN_GT 128     // GEMM threads (warps 0-3)
 
 struct MvnSlots {   // per-slot scalars, in shared memory
-  long long rep[MVN_MAXR], fin_rep[MVN_MAXR], time[MVN_MAXR], tau[MVN_MAXR];
+  long long rep[MVN_MAXR], time[MVN_MAXR], tau[MVN_MAXR];
   unsigned long long iu[MVN_MAXR], in[MVN_MAXR];
-  double pdf1[MVN_MAXR], pdf2[MVN_MAXR], normz[MVN_MAXR], edotxi[MVN_MAXR], ppdf[2 * MVN_MAXR];
-  double fin_tau[MVN_MAXR], fin_cost[MVN_MAXR];
-  long long fin_iter[MVN_MAXR];
-  int phase[MVN_MAXR], met[MVN_MAXR], ident[MVN_MAXR], acc1[MVN_MAXR], acc2[MVN_MAXR], bad[MVN_MAXR];
-  int rowsA[MVN_MAXR], rowsB[2 * MVN_MAXR], rowsI[2 * MVN_MAXR], rowsC[2 * MVN_MAXR];
-  int nA, nB, nI, nC, nActive, exhausted;
+  double pdf1[MVN_MAXR], pdf2[MVN_MAXR];
+  int phase[MVN_MAXR], met[MVN_MAXR], ident[MVN_MAXR], bad[MVN_MAXR];
+  int exhausted;
 };
 
-// One GEMM unit: RT input rows against the column group g of a packed matrix; acc[r][c] += in_r[k] M[k][4g+c].
+// One GEMM unit: RT input rows (smem, 16-byte aligned) against column group g of a packed matrix:
+// acc[r][c] = sum_{k <= 4g+3} in_r[k] M[k][4g+c], sequential in k.  Operands for k+2, k+3 are loaded while
+// k, k+1 are computed (reads run at most 32 bytes past the group / row, inside the padding).
 template <int RT, bool SUBMEAN>
-__device__ __forceinline__ void mvn_unit(const double* __restrict__ pack, int g, int d, const double* const* in,
+__device__ __forceinline__ void mvn_unit(const double* __restrict__ pack, int g, const double* const* in,
                                          const double* __restrict__ mean, double (&acc)[RT][4]) {
-  const int K = mvn_group_rows(g, d);
-  // group offset: sum_{g' < g} 4 * min(4g'+4, d).  Groups with 4g'+4 <= d are full: 16 (1 + ... + g) = 8 g (g+1).
-  // Only the last group can be clipped, and it has no successor, so the closed form is exact for every g.
-  const double* mp = pack + 8 * g * (g + 1);
-#pragma unroll 4
-  for (int k = 0; k < K; ++k) {
-    const double2 m01 = *reinterpret_cast<const double2*>(mp + 4 * k);
-    const double2 m23 = *reinterpret_cast<const double2*>(mp + 4 * k + 2);
-    double mu = SUBMEAN ? mean[k] : 0.0;
+  const int K = 4 * g + 4;
+  const double* mp = pack + mvn_group_off(g);
+  double2 m0 = *reinterpret_cast<const double2*>(mp), m1 = *reinterpret_cast<const double2*>(mp + 2);
+  double2 m2 = *reinterpret_cast<const double2*>(mp + 4), m3 = *reinterpret_cast<const double2*>(mp + 6);
+  double2 v[RT];
+#pragma unroll
+  for (int r = 0; r < RT; ++r) v[r] = *reinterpret_cast<const double2*>(in[r]);
+  double2 mu = make_double2(0.0, 0.0);
+  if (SUBMEAN) mu = *reinterpret_cast<const double2*>(mean);
+#pragma unroll 2
+  for (int k = 0; k < K; k += 2) {
+    const double2 n0 = *reinterpret_cast<const double2*>(mp + 4 * k + 8);
+    const double2 n1 = *reinterpret_cast<const double2*>(mp + 4 * k + 10);
+    const double2 n2 = *reinterpret_cast<const double2*>(mp + 4 * k + 12);
+    const double2 n3 = *reinterpret_cast<const double2*>(mp + 4 * k + 14);
+    double2 vn[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) vn[r] = *reinterpret_cast<const double2*>(in[r] + k + 2);
+    double2 mun = make_double2(0.0, 0.0);
+    if (SUBMEAN) mun = *reinterpret_cast<const double2*>(mean + k + 2);
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
-      double v = in[r][k];
-      if (SUBMEAN) v = v - mu;
-      acc[r][0] = ubm_fma(v, m01.x, acc[r][0]);
-      acc[r][1] = ubm_fma(v, m01.y, acc[r][1]);
-      acc[r][2] = ubm_fma(v, m23.x, acc[r][2]);
-      acc[r][3] = ubm_fma(v, m23.y, acc[r][3]);
+      double2 x = v[r];
+      if (SUBMEAN) { x.x = x.x - mu.x; x.y = x.y - mu.y; }
+      acc[r][0] = ubm_fma(x.x, m0.x, acc[r][0]);
+      acc[r][1] = ubm_fma(x.x, m0.y, acc[r][1]);
+      acc[r][2] = ubm_fma(x.x, m1.x, acc[r][2]);
+      acc[r][3] = ubm_fma(x.x, m1.y, acc[r][3]);
+      acc[r][0] = ubm_fma(x.y, m2.x, acc[r][0]);
+      acc[r][1] = ubm_fma(x.y, m2.y, acc[r][1]);
+      acc[r][2] = ubm_fma(x.y, m3.x, acc[r][2]);
+      acc[r][3] = ubm_fma(x.y, m3.y, acc[r][3]);
     }
+    m0 = n0; m1 = n1; m2 = n2; m3 = n3; mu = mun;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) v[r] = vn[r];
   }
 }
 
@@ -115,440 +148,469 @@ __device__ __forceinline__ double warp_butterfly(double v) {
   return v;
 }
 
+// four consecutive standard normals of a replicate's N stream starting at index i0 (two Philox blocks when
+// i0 is even, three otherwise)
+template <bool TAPE>
+__device__ __forceinline__ void draw_n4(const RunParams& P, long long rep, unsigned long long i0, int nvalid,
+                                        double* out, bool* bad) {
+  if (TAPE) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[c] = (c < nvalid) ? draw_n_at<true>(P, rep, i0 + c, bad) : 0.0;
+    return;
+  }
+  const uint64_t grep = (uint64_t)(P.rep_offset + rep);
+  unsigned long long cur = ~0ull;
+  ubm_u32x4 blk;
+  blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c < nvalid) {
+      const unsigned long long idx = i0 + c, b = idx >> 1;
+      if (b != cur) { blk = ubm_stream_block(P.seed, grep, UBM_STREAM_N, b); cur = b; }
+      const double p = (idx & 1) ? ubm_u01_53(blk.w[2], blk.w[3]) : ubm_u01_53(blk.w[0], blk.w[1]);
+      out[c] = ubm_qnorm(p);
+    } else out[c] = 0.0;
+  }
+}
+
 struct MvnSmem {
-  double *packA, *packB, *packC;
-  double *X1, *X2, *XI, *ETA, *P1, *P2;   // [R][DP]
-  double* TG;                             // [2R][32]
-  double* ZERO;                           // [DP] zeros (padding rows of the last row group)
+  double *packA, *packB, *packC, *MEAN;
+  double *X1, *X2, *V1, *V2;      // [R][DPS]   V1: chain-1 row (diff -> xi -> proposal 1), V2: chain-2 row
+  double *ACC;                    // [R][2][dimh]  mcmc sums, correction sums (estimator mode)
+  double* TG;                     // [2R][32]
+  double* ZERO;                   // [DPS]
   MvnSlots* S;
 };
 
-__host__ __device__ inline size_t mvn_smem_bytes(int packLen, int DP, int R) {
-  return (size_t)(3 * packLen + 6 * R * DP + 2 * R * 32 + DP) * sizeof(double) + sizeof(MvnSlots) + 16;
+__host__ __device__ inline size_t mvn_smem_bytes(int packLen, int DPS, int R, int acc_per_slot) {
+  return (size_t)(3 * packLen + DPS + 4 * R * DPS + R * acc_per_slot + 2 * R * 32 + DPS) * sizeof(double) +
+         sizeof(MvnSlots) + 16;
 }
 
-// row code: slot * 2 + which (which = 0: chain-1 row [XI -> P1], 1: chain-2 row [ETA -> P2])
+// idx-th row of the compact row list "all set bits of m1 as chain-1 rows, then all set bits of m2 as chain-2
+// rows"; returns slot * 2 + which, or -1
+__device__ __forceinline__ int mvn_row_code(unsigned m1, unsigned m2, int idx) {
+  const int n1 = __popc(m1);
+  if (idx < n1) return 2 * (int)__fns(m1, 0, idx + 1);
+  idx -= n1;
+  if (idx < __popc(m2)) return 2 * (int)__fns(m2, 0, idx + 1) + 1;
+  return -1;
+}
+
+// GEMM phase over a compact row list.  Input vector of row code c = (c & 1 ? V2 : V1)[c >> 1].  Thread u owns
+// unit u = pr * nRG + rg (row group fastest).  Every thread owns at most ONE unit, so outputs can be parked in
+// registers across the barrier that protects in-place overwriting of the inputs.
+template <int RT, bool SUBMEAN>
+__device__ __forceinline__ void mvn_phase_compute(const double* __restrict__ pack, const MvnSmem& sm, unsigned m1,
+                                                  unsigned m2, int nrows, int DPS, int nCG, int nPairs,
+                                                  const double* mean, int u, int (&code)[RT], int (&gs)[2], int& ng,
+                                                  double (&acc)[2][RT][4]) {
+  const int nRG = (nrows + RT - 1) / RT;
+  ng = 0;
+  if (u >= nRG * nPairs) return;
+  const int pr = u / nRG, rg = u - pr * nRG;
+  const double* in[RT];
+#pragma unroll
+  for (int r = 0; r < RT; ++r) {
+    code[r] = mvn_row_code(m1, m2, RT * rg + r);
+    in[r] = (code[r] < 0) ? sm.ZERO : ((code[r] & 1) ? sm.V2 : sm.V1) + (code[r] >> 1) * DPS;
+  }
+  gs[0] = pr; gs[1] = nCG - 1 - pr;
+  ng = (gs[0] == gs[1]) ? 1 : 2;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) { acc[q][r][0] = acc[q][r][1] = acc[q][r][2] = acc[q][r][3] = 0.0; }
+    if (q < ng) mvn_unit<RT, SUBMEAN>(pack, gs[q], in, mean, acc[q]);
+  }
+}
+
 template <bool TAPE, bool ZERO_MEAN>
-__global__ void __launch_bounds__(128) mvn_driver_kernel(const MvnDevice M, const RunParams P, const int R,
-                                                         double* __restrict__ acc_scratch) {
+__global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, const RunParams P, const int R,
+                                                           const int acc_per_slot) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
-  const int d = M.d, DP = M.DP, nCG = M.nCG, nPairs = M.nPairs;
+  const int tid = threadIdx.x, T = MVN_T, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+  const int d = M.d, DPS = M.DPS, nCG = M.nCG, nPairs = M.nPairs;
   MvnSmem sm;
   {
     double* p = reinterpret_cast<double*>(smem_raw);
     sm.packA = p; p += M.packLen; sm.packB = p; p += M.packLen; sm.packC = p; p += M.packLen;
-    sm.X1 = p; p += R * DP; sm.X2 = p; p += R * DP; sm.XI = p; p += R * DP; sm.ETA = p; p += R * DP;
-    sm.P1 = p; p += R * DP; sm.P2 = p; p += R * DP;
+    sm.MEAN = p; p += DPS;
+    sm.X1 = p; p += R * DPS; sm.X2 = p; p += R * DPS; sm.V1 = p; p += R * DPS; sm.V2 = p; p += R * DPS;
+    sm.ACC = p; p += R * acc_per_slot;
     sm.TG = p; p += 2 * R * 32;
-    sm.ZERO = p; p += DP;
+    sm.ZERO = p; p += DPS;
     sm.S = reinterpret_cast<MvnSlots*>(p);
   }
   MvnSlots& S = *sm.S;
   for (int i = tid; i < M.packLen; i += T) { sm.packA[i] = M.packA[i]; sm.packB[i] = M.packB[i]; sm.packC[i] = M.packC[i]; }
-  for (int i = tid; i < 6 * R * DP; i += T) sm.X1[i] = 0.0;
-  for (int i = tid; i < 2 * R * 32 + DP; i += T) sm.TG[i] = 0.0;
+  for (int i = tid; i < DPS; i += T) sm.MEAN[i] = M.mean_pi[i];
+  for (int i = tid; i < 4 * R * DPS + R * acc_per_slot + 2 * R * 32 + DPS; i += T) sm.X1[i] = 0.0;
   if (tid < MVN_MAXR) {
-    S.rep[tid] = -1; S.fin_rep[tid] = -1; S.phase[tid] = SL_IDLE; S.time[tid] = 0; S.tau[tid] = 0; S.met[tid] = 0;
-    S.iu[tid] = 0; S.in[tid] = 0; S.bad[tid] = 0;
+    S.rep[tid] = -1; S.phase[tid] = SL_IDLE; S.time[tid] = 0; S.tau[tid] = 0; S.met[tid] = 0;
+    S.iu[tid] = 0; S.in[tid] = 0; S.bad[tid] = 0; S.ident[tid] = 0;
   }
-  if (tid == 0) { S.exhausted = 0; S.nActive = 0; }
+  if (tid == 0) S.exhausted = 0;
   __syncthreads();
 
   const int dimh = (P.h_kind == UBM_H_BOTH) ? 2 * d : d;
   const double denom = (double)(P.m - P.k + 1);
-  double* my_acc = acc_scratch ? acc_scratch + (size_t)blockIdx.x * R * 2 * dimh : nullptr;   // [R][2][dimh]
-  const double* mean_pi = M.mean_pi;
+  const unsigned FULL = 0xffffffffu;
 
   for (;;) {
-    // ---------------------------------------------------------------- S1: slot bookkeeping (owner threads)
-    if (tid < R) {
-      const int s = tid;
-      S.fin_rep[s] = -1;
+    // ================================================================ per-slot section (one warp per slot)
+    // finishes the step just computed (densities -> accept/reject -> state/estimator update), runs the slot state
+    // machine (finish / write-out / fetch the next replicate), and prepares the inputs of the next step.
+    int my_active = 0, my_coupled = 0;
+    for (int s = warp; s < R; s += nwarp) {
       int ph = S.phase[s];
+      long long rep = S.rep[s];
+      long long time = S.time[s];
+      int met = S.met[s];
       if (ph != SL_IDLE) {
-        long long time = S.time[s];
-        bool met = S.met[s] != 0;
+        // ---- log-densities of the proposals (src/mvnorm.cpp:81-84) and the MH accept step
+        const double ss1 = warp_butterfly(sm.TG[(2 * s) * 32 + lane]);
+        const double ss2 = warp_butterfly(sm.TG[(2 * s + 1) * 32 + lane]);
+        const double pp1 = -0.5 * ss1 + M.cst;
+        const int ident = S.ident[s];
+        const double pp2 = (ph == SL_COUPLED && ident) ? pp1 : (-0.5 * ss2 + M.cst);
+        int a1 = 0, a2 = 0, add_mcmc = 0, add_corr = 0;
+        double wgt = 0.0;
+        if (ph == SL_INIT) {
+          a1 = 1; a2 = 1;
+          if (lane == 0) { S.pdf1[s] = pp1; S.pdf2[s] = pp2; }
+        } else {
+          double logu = 0.0;
+          if (lane == 0) {
+            bool bad = false;
+            logu = ubm_log(draw_u_at<TAPE>(P, rep, S.iu[s], &bad));   // R/get_mh_kernels.R:34,57
+            S.iu[s] += 1;
+            if (bad) S.bad[s] = 1;
+          }
+          logu = __shfl_sync(FULL, logu, 0);
+          const double pdf1 = S.pdf1[s], pdf2 = S.pdf2[s];
+          if (ph == SL_SINGLE) {
+            a1 = (logu < pp1 - pdf1) ? 1 : 0;
+          } else {
+            if (isfinite(pp1)) a1 = (logu < pp1 - pdf1) ? 1 : 0;
+            if (isfinite(pp2)) a2 = (logu < pp2 - pdf2) ? 1 : 0;
+            if (ident && a1 && a2) met = 1;
+          }
+          time += 1;
+          if (lane == 0) {
+            if (a1) S.pdf1[s] = pp1;
+            if (a2) S.pdf2[s] = pp2;
+            S.time[s] = time;
+            if (met && !S.met[s]) { S.met[s] = 1; S.tau[s] = time; }
+          }
+          // what the estimator adds after this step (R/unbiasedestimator.R:66, :70-72, :80, :90, :93-95)
+          add_mcmc = (time <= P.lag) ? (time >= P.k) : (P.k <= time && time <= P.m);
+          add_corr = ((time >= P.k + P.lag) && (ph == SL_COUPLED || time == P.lag)) ? 1 : 0;
+          if (add_corr && P.mode == MODE_ESTIMATOR) wgt = (double)corr_weight(time, P.k, P.m, P.lag);
+        }
+        // ---- state update, estimator sums, trajectories
+        const bool coupled_step = (ph == SL_COUPLED);
+        for (int j = lane; j < d; j += 32) {
+          const int o = s * DPS + j;
+          if (a1) sm.X1[o] = sm.V1[o];
+          if (a2) sm.X2[o] = (coupled_step && ident) ? sm.V1[o] : sm.V2[o];
+          const double x1 = sm.X1[o];
+          const double x2 = sm.X2[o];
+          if (P.mode == MODE_ESTIMATOR) {
+            double* a = sm.ACC + s * acc_per_slot;
+            const int nh = (P.h_kind == UBM_H_BOTH) ? 2 : 1;
+            for (int hh = 0; hh < nh; ++hh) {
+              const bool sq = (P.h_kind == UBM_H_SQUARE) || hh == 1;
+              const int e = hh * d + j;
+              const double h1 = sq ? x1 * x1 : x1;
+              if (ph == SL_INIT) {
+                a[e] = (P.k == 0) ? h1 : 0.0;                        // R/unbiasedestimator.R:55-59
+                a[dimh + e] = 0.0;
+              } else {
+                if (add_mcmc) a[e] = a[e] + h1;
+                if (add_corr) {
+                  const double h2 = sq ? x2 * x2 : x2;
+                  a[dimh + e] = a[dimh + e] + wgt * (h1 - h2);
+                }
+              }
+            }
+          } else if (P.mode == MODE_CHAINS) {
+            double* S1 = P.samples1 + (rep * P.stride) * d;
+            double* S2 = P.samples2 + (rep * P.stride) * d;
+            if (ph == SL_INIT) { S1[j] = x1; S2[j] = x2; }
+            else {
+              S1[time * d + j] = x1;
+              if (time > P.lag) S2[(time - P.lag) * d + j] = (coupled_step ? x2 : x1);   // R/coupled_chains.R:60-62,77-78
+            }
+          }
+        }
+        __syncwarp();
+        // ---- slot state machine
         bool finished;
-        bool capped = (P.max_it > 0 && time >= P.max_it) || S.bad[s];
+        const bool capped = (P.max_it > 0 && time >= P.max_it) || S.bad[s];
         if (P.mode == MODE_MEETING) finished = met || (time >= P.lag && capped);
         else {
-          long long horizon = (S.tau[s] > P.m) ? S.tau[s] : P.m;
+          const long long tt = met ? S.tau[s] : 0;
+          const long long horizon = (tt > P.m) ? tt : P.m;
           finished = (met && time >= horizon) || (time >= P.lag && capped);
         }
+        if (ph == SL_INIT) finished = false;
         if (finished) {
-          long long tau = S.tau[s];
-          S.fin_rep[s] = S.rep[s];
-          S.fin_tau[s] = met ? (double)tau : dinf();
-          S.fin_iter[s] = time;
-          if (!met) S.fin_cost[s] = dinf();
-          else if (P.mode == MODE_MEETING) S.fin_cost[s] = (double)(P.lag + 2 * (tau - P.lag));
-          else S.fin_cost[s] = (double)(P.lag + 2 * (tau - P.lag) + ((time - tau) > 0 ? (time - tau) : 0));
-          if (S.bad[s]) atomicExch(P.status, UBM_ERR_TAPE);
+          if (lane == 0) {
+            const long long tt = S.tau[s];
+            double cost = dinf();
+            if (met) {
+              if (P.mode == MODE_MEETING) cost = (double)(P.lag + 2 * (tt - P.lag));
+              else cost = (double)(P.lag + 2 * (tt - P.lag) + ((time - tt) > 0 ? (time - tt) : 0));
+            }
+            if (P.tau) P.tau[rep] = met ? (double)tt : dinf();
+            if (P.cost) P.cost[rep] = cost;
+            if (P.iter) P.iter[rep] = time;
+            if (S.bad[s]) atomicExch(P.status, UBM_ERR_TAPE);
+          }
+          if (P.mode == MODE_ESTIMATOR) {
+            const double* a = sm.ACC + s * acc_per_slot;
+            const int nh = (P.h_kind == UBM_H_BOTH) ? 2 : 1;
+            for (int j = lane; j < d; j += 32)
+              for (int hh = 0; hh < nh; ++hh) {
+                const int e = hh * d + j;
+                const double mc = a[e], co = a[dimh + e];
+                const double ue = mc + co;
+                P.uest[rep * dimh + e] = ue / denom;
+                if (P.mcmc) P.mcmc[rep * dimh + e] = mc / denom;
+                if (P.corr) P.corr[rep * dimh + e] = co / denom;
+              }
+          }
           ph = SL_IDLE;
         } else if (time < P.lag) ph = SL_SINGLE;
         else ph = met ? SL_SINGLE : SL_COUPLED;
       }
-      if (ph == SL_IDLE && !S.exhausted) {
-        unsigned long long r = atomicAdd(P.work_counter, 1ull);
-        if (r < (unsigned long long)P.nrep) {
-          S.rep[s] = (long long)r; S.time[s] = 0; S.tau[s] = 0; S.met[s] = 0; S.iu[s] = 0; S.in[s] = 0; S.bad[s] = 0;
-          ph = SL_INIT;
-        } else {
-          S.rep[s] = -1;
-          S.exhausted = 1;   // benign race: every writer writes 1
+      if (ph == SL_IDLE) {
+        long long r = -1;
+        if (lane == 0 && !S.exhausted) {
+          const unsigned long long got = atomicAdd(P.work_counter, 1ull);
+          if (got < (unsigned long long)P.nrep) r = (long long)got;
+          else S.exhausted = 1;
         }
+        r = __shfl_sync(FULL, r, 0);
+        if (r >= 0) {
+          rep = r; time = 0; met = 0; ph = SL_INIT;
+          if (lane == 0) { S.rep[s] = r; S.time[s] = 0; S.tau[s] = 0; S.met[s] = 0; S.iu[s] = 0; S.in[s] = 0; S.bad[s] = 0; }
+        } else if (lane == 0) S.rep[s] = -1;
       }
-      S.phase[s] = ph;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int nA = 0, nAct = 0;
-      for (int s = 0; s < R; ++s) {
-        if (S.phase[s] != SL_IDLE) ++nAct;
-        if (S.phase[s] == SL_COUPLED) S.rowsA[nA++] = s;
-      }
-      S.nA = nA; S.nActive = nAct;
-    }
-    __syncthreads();
-    // ---------------------------------------------------------------- write-out of finished replicates
-    {
-      for (int s = 0; s < R; ++s) {
-        long long fr = S.fin_rep[s];
-        if (fr < 0) continue;
-        if (tid == 0) {
-          if (P.tau) P.tau[fr] = S.fin_tau[s];
-          if (P.cost) P.cost[fr] = S.fin_cost[s];
-          if (P.iter) P.iter[fr] = S.fin_iter[s];
-        }
-        if (P.mode == MODE_ESTIMATOR) {
-          double* a = my_acc + (size_t)s * 2 * dimh;
-          for (int e = tid; e < dimh; e += T) {
-            double mc = a[e], co = a[dimh + e];
-            double ue = mc + co;
-            P.uest[fr * dimh + e] = ue / denom;
-            if (P.mcmc) P.mcmc[fr * dimh + e] = mc / denom;
-            if (P.corr) P.corr[fr * dimh + e] = co / denom;
+      __syncwarp();
+      if (lane == 0) { S.phase[s] = ph; S.ident[s] = 0; }
+      // ---- inputs of the next step: draws (non-coupled slots) or x2 - x1 (coupled slots)
+      if (ph != SL_IDLE) {
+        my_active = 1;
+        const unsigned long long in0 = S.in[s];
+        if (ph == SL_COUPLED) {
+          my_coupled = 1;
+          for (int j = lane; j < d; j += 32) sm.V1[s * DPS + j] = sm.X2[s * DPS + j] - sm.X1[s * DPS + j];   // mu2 - mu1 (:191)
+        } else if (lane < nCG) {
+          const int g = lane;
+          bool bad = false;
+          double z[4];
+          draw_n4<TAPE>(P, rep, in0 + 4 * g, d - 4 * g, z, &bad);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sm.V1[s * DPS + 4 * g + c] = z[c];
+          if (ph == SL_INIT) {
+            draw_n4<TAPE>(P, rep, in0 + d + 4 * g, d - 4 * g, z, &bad);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sm.V2[s * DPS + 4 * g + c] = z[c];
           }
+          if (bad) S.bad[s] = 1;
         }
+        __syncwarp();
+        if (lane == 0 && ph != SL_COUPLED) S.in[s] = in0 + ((ph == SL_INIT) ? 2 * d : d);
       }
     }
-    if (S.nActive == 0) break;
-    // ---------------------------------------------------------------- S2: draws xi (and init eta), diff
-    for (int w = tid; w < R * nCG; w += T) {
-      const int s = w / nCG, g = w - s * nCG;
-      const int ph = S.phase[s];
-      if (ph == SL_IDLE) continue;
-      const long long rep = S.rep[s];
-      const unsigned long long in0 = S.in[s];
-      bool bad = false;
-      double* xi = sm.XI + s * DP + 4 * g;
-      double* eta = sm.ETA + s * DP + 4 * g;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int j = 4 * g + c;
-        xi[c] = (j < d) ? draw_n_at<TAPE>(P, rep, in0 + j, &bad) : 0.0;
-      }
-      if (ph == SL_INIT) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int j = 4 * g + c;
-          eta[c] = (j < d) ? draw_n_at<TAPE>(P, rep, in0 + d + j, &bad) : 0.0;
-        }
-      } else if (ph == SL_COUPLED) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) eta[c] = sm.X2[s * DP + 4 * g + c] - sm.X1[s * DP + 4 * g + c];   // mu2 - mu1 (:191)
-      }
-      if (bad) S.bad[s] = 1;
-    }
-    __syncthreads();
-    if (tid < R && S.phase[tid] != SL_IDLE) S.in[tid] += (S.phase[tid] == SL_INIT) ? 2 * d : d;
-    // ---------------------------------------------------------------- phase A: z = -(diff^T Cinv_prop) -> P2, |z|^2
+    const int any_active = __syncthreads_or(my_active);
+    if (!any_active) break;
+    const int any_coupled = __syncthreads_or(my_coupled);
+
+    // row masks of this step (every warp computes them from the slot phases)
+    unsigned mA, mI, mS;
     {
-      const int nA = S.nA;
-      const int nRG = (nA + 1) / 2;
-      for (int u = tid; u < nRG * nPairs; u += T) {
-        const int rg = u / nPairs, pr = u - rg * nPairs;
-        const double* in[2];
-        int slot[2];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          int idx = 2 * rg + r;
-          slot[r] = (idx < nA) ? S.rowsA[idx] : -1;
-          in[r] = (slot[r] >= 0) ? sm.ETA + slot[r] * DP : sm.ZERO;
-        }
-        const int gs[2] = {pr, nCG - 1 - pr};
-        const int ng = (gs[0] == gs[1]) ? 1 : 2;
+      const int ph = (lane < R) ? S.phase[lane] : SL_IDLE;
+      mA = __ballot_sync(FULL, ph == SL_COUPLED);
+      mI = __ballot_sync(FULL, ph == SL_INIT);
+      mS = __ballot_sync(FULL, ph == SL_SINGLE);
+    }
+    // ================================================================ phase A: z = -(diff^T Cinv_prop) -> V2, |z|^2
+    if (any_coupled) {
+      if (tid < MVN_GT) {
+        int code[2], gs[2], ng;
+        double acc[2][2][4];
+        mvn_phase_compute<2, false>(sm.packA, sm, mA, 0u, __popc(mA), DPS, nCG, nPairs, nullptr, tid, code, gs, ng, acc);
         for (int q = 0; q < ng; ++q) {
-          const int g = gs[q];
-          double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-          mvn_unit<2, false>(sm.packA, g, d, in, nullptr, acc);
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
-            if (slot[r] < 0) continue;
+            if (code[r] < 0) continue;
+            const int s = code[r] >> 1;
             double t = 0.0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              double z = -acc[r][c];                              // :198
-              sm.P2[slot[r] * DP + 4 * g + c] = z;
+              const double z = -acc[q][r][c];                        // :198
+              sm.V2[s * DPS + 4 * gs[q] + c] = z;
               t = ubm_fma(z, z, t);
             }
-            sm.TG[(2 * slot[r]) * 32 + g] = t;
+            sm.TG[(2 * s) * 32 + gs[q]] = t;
           }
         }
       }
-    }
-    __syncthreads();
-    // ---------------------------------------------------------------- S4a: normz per coupled slot
-    for (int i = warp; i < S.nA; i += nwarp) {
-      const int s = S.rowsA[i];
-      double v = warp_butterfly(sm.TG[(2 * s) * 32 + lane]);
-      if (lane == 0) S.normz[s] = sqrt(v);                        // :199
-    }
-    __syncthreads();
-    // ---------------------------------------------------------------- S4b: e = z / normz -> P2, e . xi partials
-    for (int w = tid; w < S.nA * nCG; w += T) {
-      const int i = w / nCG, g = w - i * nCG;
-      const int s = S.rowsA[i];
-      const double nz = S.normz[s];
-      if (nz < 1e-15) continue;
-      double t = 0.0;
+      __syncthreads();
+      // -------------------------------------------------------------- coupling algebra, one warp per coupled slot
+      for (int s = warp; s < R; s += nwarp) {
+        if (!((mA >> s) & 1u)) continue;
+        const long long rep = S.rep[s];
+        const double nz = sqrt(warp_butterfly(sm.TG[(2 * s) * 32 + lane]));   // :199
+        const unsigned long long in0 = S.in[s];
+        double z[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
+        double t = 0.0;
+        bool bad = false;
+        if (lane < nCG) {
+          draw_n4<TAPE>(P, rep, in0 + 4 * lane, d - 4 * lane, z, &bad);        // :193-195
+          if (!(nz < 1e-15)) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int j = 4 * g + c;
-        double e = sm.P2[s * DP + j] / nz;                        // :212
-        sm.P2[s * DP + j] = e;
-        t = ubm_fma(e, sm.XI[s * DP + j], t);                     // :216
-      }
-      sm.TG[(2 * s) * 32 + g] = t;
-    }
-    __syncthreads();
-    // ---------------------------------------------------------------- S4c: e.xi, utilde, identical?
-    for (int i = warp; i < S.nA; i += nwarp) {
-      const int s = S.rowsA[i];
-      const double nz = S.normz[s];
-      double edx = warp_butterfly(sm.TG[(2 * s) * 32 + lane]);
-      if (lane == 0) {
-        if (nz < 1e-15) { S.ident[s] = 1; S.edotxi[s] = 0.0; }    // :200-210, no uniform drawn
-        else {
-          bool bad = false;
-          double ut = draw_u_at<TAPE>(P, S.rep[s], S.iu[s], &bad);   // :213-215
-          S.iu[s] += 1;
-          if (bad) S.bad[s] = 1;
-          double a = edx + nz;
-          S.ident[s] = (ubm_log(ut) < (-0.5 * a * a + 0.5 * edx * edx)) ? 1 : 0;   // :217
-          S.edotxi[s] = edx;
-        }
-      }
-    }
-    __syncthreads();
-    // ---------------------------------------------------------------- S4d: eta (non-identical only), row lists
-    for (int w = tid; w < S.nA * nCG; w += T) {
-      const int i = w / nCG, g = w - i * nCG;
-      const int s = S.rowsA[i];
-      if (S.ident[s]) continue;
-      const double two_edx = 2. * S.edotxi[s];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int j = 4 * g + c;
-        sm.ETA[s * DP + j] = sm.XI[s * DP + j] - two_edx * sm.P2[s * DP + j];   // :221
-      }
-    }
-    if (tid == 0) {
-      int nB = 0, nI = 0, nC = 0;
-      for (int s = 0; s < R; ++s) {
-        const int ph = S.phase[s];
-        if (ph == SL_IDLE) continue;
-        if (ph == SL_INIT) { S.rowsI[nI++] = 2 * s; S.rowsI[nI++] = 2 * s + 1; S.rowsC[nC++] = 2 * s; S.rowsC[nC++] = 2 * s + 1; }
-        else {
-          S.rowsB[nB++] = 2 * s; S.rowsC[nC++] = 2 * s;
-          if (ph == SL_COUPLED && !S.ident[s]) { S.rowsB[nB++] = 2 * s + 1; S.rowsC[nC++] = 2 * s + 1; }
-        }
-      }
-      S.nB = nB; S.nI = nI; S.nC = nC;
-    }
-    __syncthreads();
-    // ---------------------------------------------------------------- phase B: proposals = x + in^T C_prop ; init
-    for (int pass = 0; pass < 2; ++pass) {
-      const int nrows = pass ? S.nI : S.nB;
-      const int* rows = pass ? S.rowsI : S.rowsB;
-      const double* pack = pass ? M.packI : sm.packB;
-      const int nRG = (nrows + 3) / 4;
-      for (int u = tid; u < nRG * nPairs; u += T) {
-        const int rg = u / nPairs, pr = u - rg * nPairs;
-        const double* in[4];
-        int code[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          int idx = 4 * rg + r;
-          code[r] = (idx < nrows) ? rows[idx] : -1;
-          in[r] = (code[r] < 0) ? sm.ZERO : ((code[r] & 1) ? sm.ETA : sm.XI) + (code[r] >> 1) * DP;
-        }
-        const int gs[2] = {pr, nCG - 1 - pr};
-        const int ng = (gs[0] == gs[1]) ? 1 : 2;
-        for (int q = 0; q < ng; ++q) {
-          const int g = gs[q];
-          double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-          mvn_unit<4, false>(pack, g, d, in, nullptr, acc);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            if (code[r] < 0) continue;
-            const int s = code[r] >> 1, which = code[r] & 1;
-            const double* base = pass ? (M.init_mean + 4 * g) : ((which ? sm.X2 : sm.X1) + s * DP + 4 * g);
-            double* out = (which ? sm.P2 : sm.P1) + s * DP + 4 * g;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) out[c] = (4 * g + c < d) ? (base[c] + acc[r][c]) : 0.0;   // :40-44, :224-225
+            for (int c = 0; c < 4; ++c) {
+              e[c] = sm.V2[s * DPS + 4 * lane + c] / nz;                       // :212
+              t = ubm_fma(e[c], z[c], t);                                      // :216
+            }
           }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sm.V1[s * DPS + 4 * lane + c] = z[c];
+        }
+        const double edx = warp_butterfly(t);
+        int ident = 0;
+        if (lane == 0) {
+          if (nz < 1e-15) ident = 1;                                           // :200-210, no uniform drawn
+          else {
+            const double ut = draw_u_at<TAPE>(P, rep, S.iu[s], &bad);          // :213-215
+            S.iu[s] += 1;
+            const double a = edx + nz;
+            ident = (ubm_log(ut) < (-0.5 * a * a + 0.5 * edx * edx)) ? 1 : 0;  // :217
+          }
+          S.ident[s] = ident;
+          S.in[s] = in0 + d;
+        }
+        if (bad) S.bad[s] = 1;
+        ident = __shfl_sync(FULL, ident, 0);
+        if (!ident && lane < nCG) {
+          const double two_edx = 2. * edx;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sm.V2[s * DPS + 4 * lane + c] = z[c] - two_edx * e[c];   // :221
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
-    // ---------------------------------------------------------------- phase C: w = Cinv_pi^T (prop - mean), |w|^2
+    // chain-2 rows of the coupled slots whose proposals differ
+    unsigned mD;
     {
-      const int nrows = S.nC;
-      const int nRG = (nrows + 3) / 4;
-      for (int u = tid; u < nRG * nPairs; u += T) {
-        const int rg = u / nPairs, pr = u - rg * nPairs;
-        const double* in[4];
-        int code[4];
+      const int differ = (lane < R) ? (((mA >> lane) & 1u) && !S.ident[lane]) : 0;
+      mD = __ballot_sync(FULL, differ);
+    }
+    // ================================================================ phase B: proposals = x + in^T C_prop (in place)
+    // and, for freshly fetched slots, x0 = init_mean + in^T init_chol (matrix read from global memory / L2)
+    for (int pass = 0; pass < 2; ++pass) {
+      const unsigned m1 = pass ? mI : (mA | mS);
+      const unsigned m2 = pass ? mI : mD;
+      const int nrows = __popc(m1) + __popc(m2);
+      if (nrows == 0) continue;   // block-uniform
+      int code[4] = {-1, -1, -1, -1}, gs[2] = {0, 0}, ng = 0, rt = 4;
+      double acc[2][4][4];
+      if (tid < MVN_GT) {
+        if (((nrows + 1) / 2) * nPairs <= MVN_GT) {
+          rt = 2;
+          int code2[2];
+          double acc2[2][2][4];
+          if (pass) mvn_phase_compute<2, false>(M.packI, sm, m1, m2, nrows, DPS, nCG, nPairs, nullptr, tid, code2, gs, ng, acc2);
+          else mvn_phase_compute<2, false>(sm.packB, sm, m1, m2, nrows, DPS, nCG, nPairs, nullptr, tid, code2, gs, ng, acc2);
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              code[r] = code2[r];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) acc[q][r][c] = acc2[q][r][c];
+            }
+        } else {
+          if (pass) mvn_phase_compute<4, false>(M.packI, sm, m1, m2, nrows, DPS, nCG, nPairs, nullptr, tid, code, gs, ng, acc);
+          else mvn_phase_compute<4, false>(sm.packB, sm, m1, m2, nrows, DPS, nCG, nPairs, nullptr, tid, code, gs, ng, acc);
+        }
+      }
+      __syncthreads();   // every read of V1 / V2 of this pass is done: overwrite inputs with outputs
+      for (int q = 0; q < ng; ++q) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          int idx = 4 * rg + r;
-          code[r] = (idx < nrows) ? S.rowsC[idx] : -1;
-          in[r] = (code[r] < 0) ? sm.ZERO : ((code[r] & 1) ? sm.P2 : sm.P1) + (code[r] >> 1) * DP;
+          if (r >= rt || code[r] < 0) continue;
+          const int s = code[r] >> 1, which = code[r] & 1;
+          const double* base = pass ? (M.init_mean + 4 * gs[q]) : ((which ? sm.X2 : sm.X1) + s * DPS + 4 * gs[q]);
+          double* out = (which ? sm.V2 : sm.V1) + s * DPS + 4 * gs[q];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) out[c] = (4 * gs[q] + c < d) ? (base[c] + acc[q][r][c]) : 0.0;   // :40-44, :224-225
         }
-        const int gs[2] = {pr, nCG - 1 - pr};
-        const int ng = (gs[0] == gs[1]) ? 1 : 2;
-        for (int q = 0; q < ng; ++q) {
-          const int g = gs[q];
-          double acc[4][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-          mvn_unit<4, !ZERO_MEAN>(sm.packC, g, d, in, mean_pi, acc);
+      }
+    }
+    __syncthreads();
+    // ================================================================ phase C: w = Cinv_pi^T (prop - mean), |w|^2
+    if (tid < MVN_GT) {
+      const unsigned m1 = mA | mS | mI, m2 = mD | mI;
+      const int nrows = __popc(m1) + __popc(m2);
+      if (((nrows + 1) / 2) * nPairs <= MVN_GT) {
+        int code[2], gs[2], ng;
+        double acc[2][2][4];
+        mvn_phase_compute<2, !ZERO_MEAN>(sm.packC, sm, m1, m2, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, gs, ng, acc);
+        for (int q = 0; q < ng; ++q)
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            if (code[r] < 0) continue;
+            double t = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) t = ubm_fma(acc[q][r][c], acc[q][r][c], t);
+            sm.TG[code[r] * 32 + gs[q]] = t;
+          }
+      } else {
+        int code[4], gs[2], ng;
+        double acc[2][4][4];
+        mvn_phase_compute<4, !ZERO_MEAN>(sm.packC, sm, m1, m2, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, gs, ng, acc);
+        for (int q = 0; q < ng; ++q)
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             if (code[r] < 0) continue;
             double t = 0.0;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) t = ubm_fma(acc[r][c], acc[r][c], t);
-            sm.TG[code[r] * 32 + g] = t;
+            for (int c = 0; c < 4; ++c) t = ubm_fma(acc[q][r][c], acc[q][r][c], t);
+            sm.TG[code[r] * 32 + gs[q]] = t;
           }
-        }
-      }
-    }
-    __syncthreads();
-    // ---------------------------------------------------------------- S8: log-densities, accept / reject
-    for (int i = warp; i < S.nC; i += nwarp) {
-      const int code = S.rowsC[i];
-      double ss = warp_butterfly(sm.TG[code * 32 + lane]);
-      if (lane == 0) S.ppdf[code] = -0.5 * ss + M.cst;             // src/mvnorm.cpp:81-84
-    }
-    __syncthreads();
-    if (tid < R) {
-      const int s = tid;
-      const int ph = S.phase[s];
-      if (ph == SL_INIT) {
-        S.acc1[s] = 1; S.acc2[s] = 1; S.pdf1[s] = S.ppdf[2 * s]; S.pdf2[s] = S.ppdf[2 * s + 1];
-      } else if (ph != SL_IDLE) {
-        bool bad = false;
-        double logu = ubm_log(draw_u_at<TAPE>(P, S.rep[s], S.iu[s], &bad));   // R/get_mh_kernels.R:34,57
-        S.iu[s] += 1;
-        if (bad) S.bad[s] = 1;
-        if (ph == SL_SINGLE) {
-          double pp = S.ppdf[2 * s];
-          int a1 = (logu < pp - S.pdf1[s]) ? 1 : 0;
-          S.acc1[s] = a1; S.acc2[s] = 0;
-          if (a1) S.pdf1[s] = pp;
-          S.time[s] += 1;
-        } else {
-          const int ident = S.ident[s];
-          double pp1 = S.ppdf[2 * s];
-          double pp2 = ident ? pp1 : S.ppdf[2 * s + 1];
-          int a1 = 0, a2 = 0;
-          if (isfinite(pp1)) a1 = (logu < pp1 - S.pdf1[s]) ? 1 : 0;
-          if (isfinite(pp2)) a2 = (logu < pp2 - S.pdf2[s]) ? 1 : 0;
-          S.acc1[s] = a1; S.acc2[s] = a2;
-          if (a1) S.pdf1[s] = pp1;
-          if (a2) S.pdf2[s] = pp2;
-          S.time[s] += 1;
-          if (ident && a1 && a2) { S.met[s] = 1; S.tau[s] = S.time[s]; }
-        }
-      }
-    }
-    __syncthreads();
-    // ---------------------------------------------------------------- S9: state update, estimator, trajectories
-    for (int w = tid; w < R * DP; w += T) {
-      const int s = w / DP, j = w - s * DP;
-      const int ph = S.phase[s];
-      if (ph == SL_IDLE || j >= d) continue;
-      const bool coupled_step = (ph == SL_COUPLED);
-      if (S.acc1[s]) sm.X1[w] = sm.P1[w];
-      if (S.acc2[s]) sm.X2[w] = (coupled_step && S.ident[s]) ? sm.P1[w] : sm.P2[w];
-      const long long time = S.time[s];
-      const long long rep = S.rep[s];
-      const double x1 = sm.X1[w];
-      const double x2 = sm.X2[w];
-      if (P.mode == MODE_ESTIMATOR) {
-        double* a = my_acc + (size_t)s * 2 * dimh;
-        const int nh = (P.h_kind == UBM_H_BOTH) ? 2 : 1;
-        for (int hh = 0; hh < nh; ++hh) {
-          const bool sq = (P.h_kind == UBM_H_SQUARE) || hh == 1;
-          const int e = hh * d + j;
-          const double h1 = sq ? x1 * x1 : x1;
-          if (ph == SL_INIT) {
-            a[e] = (P.k == 0) ? h1 : 0.0;                          // R/unbiasedestimator.R:55-59
-            a[dimh + e] = 0.0;
-          } else {
-            const bool in_window = (time <= P.lag) ? (time >= P.k) : (P.k <= time && time <= P.m);   // :66, :80, :90
-            if (in_window) a[e] = a[e] + h1;
-            // correction: after the last lag step (:70-72) and after every coupled step (:93-95)
-            const bool corr_now = (time >= P.k + P.lag) && (coupled_step || (time == P.lag));
-            if (corr_now) {
-              const double h2 = sq ? x2 * x2 : x2;
-              const double wgt = (double)corr_weight(time, P.k, P.m, P.lag);
-              a[dimh + e] = a[dimh + e] + wgt * (h1 - h2);
-            }
-          }
-        }
-      } else if (P.mode == MODE_CHAINS) {
-        double* S1 = P.samples1 + (rep * P.stride) * d;
-        double* S2 = P.samples2 + (rep * P.stride) * d;
-        if (ph == SL_INIT) { S1[j] = x1; S2[j] = x2; }
-        else {
-          S1[time * d + j] = x1;
-          if (time > P.lag) S2[(time - P.lag) * d + j] = (coupled_step ? x2 : x1);   // R/coupled_chains.R:60-62,77-78
-        }
       }
     }
     __syncthreads();
   }
 }
 
-struct DevBufFwd;   // (capi.cu's DevBuf)
-
 template <class Buf>
 inline int mvn_launch(const MvnDevice& M, const RunParams& P, bool tape, int nsm, cudaStream_t st, Buf& scratch,
                       int64_t* launches, std::string* err) {
+  (void)scratch;
   if (P.nbreaks >= 2) { *err = "mvn: histogram bins are not available for this model yet"; return UBM_ERR_UNSUPPORTED; }
   const size_t budget = 227 * 1024;
+  const int dimh = (P.h_kind == UBM_H_BOTH) ? 2 * M.d : M.d;
+  const int acc_per_slot = (P.mode == MODE_ESTIMATOR) ? 2 * dimh : 0;
   int R = MVN_MAXR;
-  while (R > 1 && mvn_smem_bytes(M.packLen, M.DP, R) > budget) --R;
-  size_t smem = mvn_smem_bytes(M.packLen, M.DP, R);
-  if (smem > budget) { *err = "mvn: d too large for shared memory"; return UBM_ERR_UNSUPPORTED; }
-  const int T = 128;
+  while (R > 1 && mvn_smem_bytes(M.packLen, M.DPS, R, acc_per_slot) > budget) --R;
+  // every phase must fit one unit per GEMM thread: 4-row tiles over at most 2R rows
+  while (R > 1 && ((2 * R + 3) / 4) * M.nPairs > MVN_GT) --R;
+  size_t smem = mvn_smem_bytes(M.packLen, M.DPS, R, acc_per_slot);
+  if (smem > budget || ((2 * R + 3) / 4) * M.nPairs > MVN_GT) { *err = "mvn: d too large for shared memory"; return UBM_ERR_UNSUPPORTED; }
   int64_t need = (P.nrep + R - 1) / R;
   int grid = (int)std::min<int64_t>(nsm, need);
-  const int dimh = (P.h_kind == UBM_H_BOTH) ? 2 * M.d : M.d;
-  double* acc = nullptr;
-  if (P.mode == MODE_ESTIMATOR) {
-    size_t bytes = (size_t)grid * R * 2 * dimh * sizeof(double);
-    if (scratch.bytes < bytes) { if (scratch.alloc(bytes) != cudaSuccess) { *err = "mvn: scratch alloc failed"; return UBM_ERR_NOMEM; } }
-    acc = scratch.template as<double>();
-  }
-  void (*kern)(const MvnDevice, const RunParams, const int, double*);
+  void (*kern)(const MvnDevice, const RunParams, const int, const int);
   if (tape) kern = M.zero_mean ? mvn_driver_kernel<true, true> : mvn_driver_kernel<true, false>;
   else kern = M.zero_mean ? mvn_driver_kernel<false, true> : mvn_driver_kernel<false, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { *err = std::string("mvn: smem attribute: ") + cudaGetErrorString(e); return UBM_ERR_CUDA; }
-  kern<<<grid, T, smem, st>>>(M, P, R, acc);
+  kern<<<grid, MVN_T, smem, st>>>(M, P, R, acc_per_slot);
   *launches += 1;
   return UBM_OK;
 }
