@@ -106,6 +106,21 @@ typedef struct {
   const double* init_chol;          /* d x d upper */
 } ubm_model_mvn;
 
+/* C4: 32 x 32 periodic Ising model, parallel tempering over `nchains` inverse temperatures, single-site
+ * systematic-scan Gibbs sweeps.  Kernels: R/ising.R:45-77 (single), :87-141 (coupled: shared uniforms per
+ * site and per swap), rinit R/ising.R:30-36; sweeps src/ising.cpp:43-92, natural statistic src/ising.cpp:11-35.
+ * The chain state exposed to h / trajectories is the vector of natural statistics (dim = nchains), as in
+ * ising_unbiased_estimator (R/ising.R:148-240). */
+#define UBM_ISING_SCAN_SEQUENTIAL 0   /* the reference's in-place row-major scan, reproduced exactly */
+typedef struct {
+  int32_t size;           /* must be 32 */
+  int32_t nchains;        /* 1 .. 32 */
+  const double* betas;    /* [nchains] */
+  double proba_swapmove;
+  int32_t scan;
+  int32_t reserved;
+} ubm_model_ising_pt;
+
 /* ---------------------------------------------------------------------------------------------
  * test functions h and histogram bins
  * ------------------------------------------------------------------------------------------- */

@@ -2,4 +2,7 @@
 // Dispatch hook for the remaining registry models (Ising PT, PG logistic, variable selection).
 #pragma once
 #include "oracle_core.hpp"
-#define ORC_MORE_DISPATCH(CALL)
+#include "oracle_ising.hpp"
+
+#define ORC_MORE_DISPATCH(CALL)                                                                      \
+  case UBM_MODEL_ISING_PT: { orc::IsingModel M((const ubm_model_ising_pt*)model); return CALL; }

@@ -37,3 +37,8 @@ def c2_model(d=100, kind="dense", init="target", mean=None):
     if init == "target":
         return R.MvnRWMH(mean_pi, Sigma, Sigma / d, mean_pi, Sigma)
     return R.MvnRWMH(mean_pi, Sigma, Sigma / d, np.ones(d), np.eye(d))
+
+
+def c4_model(nchains=16, pswap=0.01, lo=0.3, hi=0.55):
+    """inst/reproduceisingmodel/run.batch.ising.R:169-171: betas = seq(0.3, 0.55, length.out = 16), pswap 0.01."""
+    return R.IsingPT(np.linspace(lo, hi, nchains), pswap)

@@ -12,6 +12,7 @@
 #include "ubm_common.cuh"
 #include "ubm_mix.cuh"
 #include "ubm_mvn.cuh"
+#include "ubm_ising.cuh"
 #include "ubm_summary.cuh"
 #include "ubm_post.cuh"
 #include "ubm_peaks.cuh"
@@ -58,6 +59,7 @@ struct ubm_plan {
   // models
   MixParams mix{};
   MvnDevice mvn{};
+  IsingDevice ising{};
   DevBuf model_blob;
   // results
   DevBuf uest, mcmc, corr, tau, cost, iter, bins_out, bin_acc, breaks, summary, counter, status, scratch;
@@ -81,6 +83,7 @@ static int model_dims(int32_t kind, const void* model, int* dim) {
   switch (kind) {
     case UBM_MODEL_NORMAL_MIXTURE: *dim = 1; return UBM_OK;
     case UBM_MODEL_MVN: *dim = ((const ubm_model_mvn*)model)->d; return UBM_OK;
+    case UBM_MODEL_ISING_PT: *dim = ((const ubm_model_ising_pt*)model)->nchains; return UBM_OK;
     default: return UBM_ERR_UNSUPPORTED;
   }
 }
@@ -114,6 +117,16 @@ static int register_model(ubm_plan* p, int32_t kind, const void* model) {
     CU(cudaMemcpyAsync(p->model_blob.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     mvn_bind_device(&p->mvn, p->model_blob.as<double>());
+    return UBM_OK;
+  }
+  if (kind == UBM_MODEL_ISING_PT) {
+    const ubm_model_ising_pt* s = (const ubm_model_ising_pt*)model;
+    if (s->size != 32) return fail(h, UBM_ERR_UNSUPPORTED, "ising: the device kernel is specialised for 32 x 32 lattices");
+    if (s->nchains < 1 || s->nchains > ISING_MAXN) return fail(h, UBM_ERR_INVALID, "ising: 1..32 temperatures");
+    if (s->scan != UBM_ISING_SCAN_SEQUENTIAL) return fail(h, UBM_ERR_UNSUPPORTED, "ising: unknown scan order");
+    if (!(s->proba_swapmove >= 0.0 && s->proba_swapmove <= 1.0)) return fail(h, UBM_ERR_INVALID, "ising: proba_swapmove in [0,1]");
+    ising_pack_host(s, &p->ising);
+    p->dim = s->nchains;
     return UBM_OK;
   }
   return fail(h, UBM_ERR_UNSUPPORTED, "model kind not in the device registry (no CPU fallback)");
@@ -239,6 +252,9 @@ static int plan_run(ubm_plan* p, int draws_mode, uint64_t seed, int64_t nrep, in
     h->launches += 1;
   } else if (p->model_kind == UBM_MODEL_MVN) {
     int stl = mvn_launch(p->mvn, P, tape, nsm, st, p->scratch, &h->launches, &h->err);
+    if (stl != UBM_OK) return stl;
+  } else if (p->model_kind == UBM_MODEL_ISING_PT) {
+    int stl = ising_launch(p->ising, P, tape, nsm, st, &h->launches, &h->err);
     if (stl != UBM_OK) return stl;
   } else {
     return fail(h, UBM_ERR_UNSUPPORTED, "model kind not in the device registry");

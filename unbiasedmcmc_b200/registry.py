@@ -128,3 +128,21 @@ class Bins:
 
     def struct(self):
         return A.ubm_bins(self.component, len(self.breaks), A.dptr(self.breaks))
+
+
+class IsingPT(ModelSpec):
+    """C4 — 32x32 periodic Ising, parallel tempering (R/ising.R:30-141; run.batch.ising.R:169-173 shape).
+    The chain state seen by h is the vector of natural statistics, one per inverse temperature."""
+    kind = A.UBM_MODEL_ISING_PT
+
+    def __init__(self, betas, proba_swapmove, size=32):
+        self.betas = _f64(betas)
+        if size != 32:
+            raise ValueError("the device kernel is specialised for the reference's 32x32 lattice")
+        if not 1 <= len(self.betas) <= 32:
+            raise ValueError("1..32 temperatures")
+        self.dim = len(self.betas)
+        self.proba_swapmove = float(proba_swapmove)
+
+    def struct(self):
+        return A.ubm_model_ising_pt(32, self.dim, A.dptr(self.betas), self.proba_swapmove, 0, 0)
