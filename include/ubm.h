@@ -208,6 +208,29 @@ int ubm_estimator_bins(ubm_handle* h, int32_t dim, const ubm_bins* bins, int64_t
                        const double* meetingtime, double* binvals /* [nrep][nbins] */);
 
 /* ---------------------------------------------------------------------------------------------
+ * stand-alone coupling / MVN primitives of the R API, batched over n samples.  Sample i draws from the typed
+ * streams of replicate index rep_offset + i (from draw 0), or from row i of the tapes.
+ *   ubm_rnorm_max_coupling        R/rnorm_max_coupling.R:17-23 (R/get_max_coupling.R:24-39)   xy [n][2]
+ *   ubm_rnorm_reflectionmax       R/rnorm_reflectionmax.R:18-39                                xy [n][2]
+ *   ubm_rmvnorm_reflectionmax     R/mvnorm_couplings.R:94-100 -> src/mvnorm.cpp:185-236        xy [n][2][d]
+ *                                 (d = 1 is UBM_ERR_INVALID with the reference's stop() message)
+ *   ubm_fast_rmvnorm_chol         R/mvnorm.R:32 -> src/mvnorm.cpp:30-46                        out [n][d]
+ *   ubm_fast_dmvnorm_chol_inverse R/mvnorm.R:69 -> src/mvnorm.cpp:71-86    x [n][d] row-major   out [n]
+ * chol / chol_inv: d x d column-major upper-triangular, as R's chol() / solve(chol()).
+ * ------------------------------------------------------------------------------------------- */
+int ubm_rnorm_max_coupling(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, double mu1, double mu2,
+                           double sigma1, double sigma2, double* xy, int32_t* identical);
+int ubm_rnorm_reflectionmax(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, double mu1, double mu2,
+                            double sigma, double* xy, int32_t* identical);
+int ubm_rmvnorm_reflectionmax(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d,
+                              const double* mu1, const double* mu2, const double* chol, const double* chol_inv,
+                              double* xy, int32_t* identical);
+int ubm_fast_rmvnorm_chol(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d,
+                          const double* mean, const double* chol, double* out);
+int ubm_fast_dmvnorm_chol_inverse(ubm_handle* h, int64_t n, int32_t d, const double* x, const double* mean,
+                                  const double* chol_inv, double* out);
+
+/* ---------------------------------------------------------------------------------------------
  * device-resident variant used for kernel-only timing (bench.py `value`): the model is uploaded once,
  * the run leaves per-replicate results and the summary in device memory owned by the handle.
  * ------------------------------------------------------------------------------------------- */

@@ -185,6 +185,54 @@ int orc_estimator_bins(int32_t dim, const ubm_bins* bins, int64_t k, int64_t m, 
   return UBM_OK;
 }
 
+// stand-alone primitives (same argument meaning as the product's ubm_* entry points)
+int orc_rnorm_coupling(int32_t mode, const ubm_draws* draws, int64_t n, int64_t rep_offset, double mu1, double mu2,
+                       double s1, double s2, double* xy, int32_t* identical) {
+  ubm_model_normal_mixture dummy{};
+  double one = 1.0, zero = 0.0;
+  dummy.ncomp = 1; dummy.weights = &one; dummy.means = &zero; dummy.sds = &one; dummy.proposal_sd = 1.0; dummy.init_sd = 1.0;
+  MixtureModel M(&dummy);
+  int bad = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    Draws D = make_draws(draws, i, rep_offset);
+    bool id;
+    if (mode == 0) id = M.reflmax(mu1, mu2, s1, D, &xy[2 * i], &xy[2 * i + 1]);
+    else id = M.maxcoupling(mu1, mu2, s1, ubm_log(s1), s2, ubm_log(s2), D, &xy[2 * i], &xy[2 * i + 1]);
+    identical[i] = id ? 1 : 0;
+    if (D.exhausted) bad = 1;
+  }
+  return bad ? UBM_ERR_TAPE : UBM_OK;
+}
+
+int orc_mvn_sample(int32_t mode, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d, const double* mu1,
+                   const double* mu2, const double* chol, const double* chol_inv, double* out, int32_t* identical) {
+  std::vector<double> eye((size_t)d * d, 0.0), zero(d, 0.0);
+  for (int j = 0; j < d; ++j) eye[(size_t)j * d + j] = 1.0;
+  ubm_model_mvn s{};
+  s.d = d; s.mean_pi = zero.data(); s.chol_inv_pi = eye.data(); s.chol_prop = chol;
+  s.chol_inv_prop = chol_inv ? chol_inv : eye.data(); s.init_mean = zero.data(); s.init_chol = eye.data();
+  MvnModel M(&s);
+  int bad = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    Draws D = make_draws(draws, i, rep_offset);
+    if (mode == 0) M.rmvnorm_chol(mu1, M.c_prop, D, out + (size_t)i * d);
+    else identical[i] = M.reflmax(mu1, mu2, D, out + (size_t)i * 2 * d, out + (size_t)i * 2 * d + d) ? 1 : 0;
+    if (D.exhausted) bad = 1;
+  }
+  return bad ? UBM_ERR_TAPE : UBM_OK;
+}
+
+int orc_dmvnorm_chol_inverse(int64_t n, int32_t d, const double* x, const double* mean, const double* chol_inv, double* out) {
+  std::vector<double> eye((size_t)d * d, 0.0);
+  for (int j = 0; j < d; ++j) eye[(size_t)j * d + j] = 1.0;
+  ubm_model_mvn s{};
+  s.d = d; s.mean_pi = mean; s.chol_inv_pi = chol_inv; s.chol_prop = eye.data(); s.chol_inv_prop = eye.data();
+  s.init_mean = mean; s.init_chol = eye.data();
+  MvnModel M(&s);
+  for (int64_t i = 0; i < n; ++i) out[i] = M.target(x + (size_t)i * d);
+  return UBM_OK;
+}
+
 // numerics probes (tests/test_numerics.py)
 void orc_vec_log(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ubm_log(x[i]); }
 void orc_vec_exp(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ubm_exp(x[i]); }

@@ -153,3 +153,68 @@ def estimator_bins(chains, bins, k=0, m=1):
     _check(lib().orc_estimator_bins(d, C.byref(bs), k, m, chains["lag"], stride, nrep, A.dptr(s1), A.dptr(s2),
                                     A.dptr(chains["meetingtime"]), A.dptr(out)))
     return out
+
+
+# ---- stand-alone primitives (oracle side) ---------------------------------------------------------------------
+def _prim_lib():
+    L = lib()
+    if not getattr(L, "_prims_bound", False):
+        dp = C.POINTER(A.ubm_draws)
+        L.orc_rnorm_coupling.argtypes = [C.c_int32, dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                         C.c_double, A.c_double_p, A.c_int32_p]
+        L.orc_mvn_sample.argtypes = [C.c_int32, dp, C.c_int64, C.c_int64, C.c_int32, A.c_double_p, A.c_double_p,
+                                     A.c_double_p, A.c_double_p, A.c_double_p, A.c_int32_p]
+        L.orc_dmvnorm_chol_inverse.argtypes = [C.c_int64, C.c_int32, A.c_double_p, A.c_double_p, A.c_double_p,
+                                               A.c_double_p]
+        L._prims_bound = True
+    return L
+
+
+def _cm(m):
+    return np.ascontiguousarray(np.asarray(m, dtype=np.float64).T).reshape(-1)
+
+
+def rnorm_max_coupling(mu1, mu2, sigma1, sigma2, draws, n=1, rep_offset=0):
+    xy, ident = np.zeros((n, 2)), np.zeros(n, dtype=np.int32)
+    ds = draws.struct(n)
+    _check(_prim_lib().orc_rnorm_coupling(1, C.byref(ds), n, rep_offset, mu1, mu2, sigma1, sigma2, A.dptr(xy), A.i32ptr(ident)))
+    return {"xy": xy, "identical": ident.astype(bool)}
+
+
+def rnorm_reflectionmax(mu1, mu2, sigma, draws, n=1, rep_offset=0):
+    xy, ident = np.zeros((n, 2)), np.zeros(n, dtype=np.int32)
+    ds = draws.struct(n)
+    _check(_prim_lib().orc_rnorm_coupling(0, C.byref(ds), n, rep_offset, mu1, mu2, sigma, sigma, A.dptr(xy), A.i32ptr(ident)))
+    return {"xy": xy, "identical": ident.astype(bool)}
+
+
+def rmvnorm_reflectionmax(mu1, mu2, Cholesky, Cholesky_inverse, draws, n=1, rep_offset=0):
+    mu1, mu2 = np.ascontiguousarray(mu1, dtype=np.float64), np.ascontiguousarray(mu2, dtype=np.float64)
+    d = len(mu1)
+    ch, ci = _cm(Cholesky), _cm(Cholesky_inverse)
+    xy, ident = np.zeros((n, 2, d)), np.zeros(n, dtype=np.int32)
+    ds = draws.struct(n)
+    _check(_prim_lib().orc_mvn_sample(1, C.byref(ds), n, rep_offset, d, A.dptr(mu1), A.dptr(mu2), A.dptr(ch), A.dptr(ci),
+                                      A.dptr(xy), A.i32ptr(ident)))
+    return {"xy": xy, "identical": ident.astype(bool)}
+
+
+def fast_rmvnorm_chol(nparticles, mean, chol, draws, rep_offset=0):
+    mean = np.ascontiguousarray(mean, dtype=np.float64)
+    d = len(mean)
+    ch = _cm(chol)
+    out = np.zeros((nparticles, d))
+    ds = draws.struct(nparticles)
+    _check(_prim_lib().orc_mvn_sample(0, C.byref(ds), nparticles, rep_offset, d, A.dptr(mean), A.dptr(None), A.dptr(ch),
+                                      A.dptr(None), A.dptr(out), A.i32ptr(None)))
+    return out
+
+
+def fast_dmvnorm_chol_inverse(x, mean, chol_inverse):
+    x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+    mean = np.ascontiguousarray(mean, dtype=np.float64)
+    n, d = x.shape
+    ci = _cm(chol_inverse)
+    out = np.zeros(n)
+    _check(_prim_lib().orc_dmvnorm_chol_inverse(n, d, A.dptr(x), A.dptr(mean), A.dptr(ci), A.dptr(out)))
+    return out

@@ -1,0 +1,52 @@
+"""GPU parity: stand-alone coupling / MVN primitives through the C ABI vs the oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from unbiasedmcmc_b200 import _abi as A
+from unbiasedmcmc_b200 import registry as R
+
+pytestmark = pytest.mark.gpu
+
+
+def test_scalar_couplings_bit_exact(engine, oracle):
+    for seed, args in ((1, (0.2, -0.8, 0.4, 1.7)), (2, (3.0, 3.0, 1.0, 1.0))):
+        g = engine.rnorm_max_coupling(*args, R.Draws(seed=seed), n=5000, rep_offset=11)
+        c = oracle.rnorm_max_coupling(*args, R.Draws(seed=seed), n=5000, rep_offset=11)
+        assert np.array_equal(g["xy"], c["xy"]) and np.array_equal(g["identical"], c["identical"])
+    g = engine.rnorm_reflectionmax(0.2, 1.5, 0.8, R.Draws(seed=3), n=5000)
+    c = oracle.rnorm_reflectionmax(0.2, 1.5, 0.8, R.Draws(seed=3), n=5000)
+    assert np.array_equal(g["xy"], c["xy"]) and np.array_equal(g["identical"], c["identical"])
+    # replay tapes
+    rng = np.random.default_rng(0)
+    dr = R.Draws(tape_u=rng.uniform(size=(64, 200)), tape_n=rng.standard_normal((64, 200)))
+    g = engine.rnorm_max_coupling(0.0, 2.0, 1.0, 0.5, dr, n=64)
+    c = oracle.rnorm_max_coupling(0.0, 2.0, 1.0, 0.5, dr, n=64)
+    assert np.array_equal(g["xy"], c["xy"])
+
+
+@pytest.mark.parametrize("d", [2, 7, 100])
+def test_mvn_primitives_bit_exact(engine, oracle, d):
+    rng = np.random.default_rng(d)
+    G = rng.standard_normal((d, d))
+    Sigma = G @ G.T / d + np.eye(d)
+    U = np.linalg.cholesky(Sigma).T
+    Ui = np.triu(np.linalg.inv(U))
+    mu1, mu2 = rng.standard_normal(d), rng.standard_normal(d) * 0.1
+    n = 300
+    g = engine.rmvnorm_reflectionmax(mu1, mu2, U, Ui, R.Draws(seed=9), n=n)
+    c = oracle.rmvnorm_reflectionmax(mu1, mu2, U, Ui, R.Draws(seed=9), n=n)
+    assert np.array_equal(g["xy"], c["xy"]) and np.array_equal(g["identical"], c["identical"])
+    gs = engine.fast_rmvnorm_chol(n, mu1, U, R.Draws(seed=10))
+    cs = oracle.fast_rmvnorm_chol(n, mu1, U, R.Draws(seed=10))
+    assert np.array_equal(gs, cs)
+    assert np.array_equal(engine.fast_dmvnorm_chol_inverse(gs, mu1, Ui), oracle.fast_dmvnorm_chol_inverse(cs, mu1, Ui))
+    # identical arguments: norm(z) < 1e-15 branch (src/mvnorm.cpp:200-210)
+    g = engine.rmvnorm_reflectionmax(mu1, mu1, U, Ui, R.Draws(seed=9), n=8)
+    assert g["identical"].all() and np.array_equal(g["xy"][:, 0], g["xy"][:, 1])
+
+
+def test_rmvnorm_reflectionmax_rejects_univariate(engine):
+    from unbiasedmcmc_b200.engine import UbmError
+    with pytest.raises(UbmError) as e:     # R/mvnorm_couplings.R:96-98 stop()
+        engine.rmvnorm_reflectionmax([0.0], [1.0], [[1.0]], [[1.0]], R.Draws(seed=1), n=2)
+    assert e.value.status == A.UBM_ERR_INVALID

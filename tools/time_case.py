@@ -1,0 +1,18 @@
+"""Steady-state single-launch timing case for the MVN kernel (the debug timing build prints per-phase cycles).
+Usage: python tools/time_case.py [nrep] [k m]"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests import cases
+from unbiasedmcmc_b200 import registry as R
+from unbiasedmcmc_b200.engine import Engine
+
+eng = Engine(0)
+nrep = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 16 * 2
+k, m = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (2000, 10000)
+t = time.time()
+res = eng.sample_unbiasedestimator(cases.c2_model(100), R.Draws(seed=1), k=k, m=m, lag=1, nrep=nrep, want_bins=False)
+dt = time.time() - t
+print("nrep", nrep, "wall", dt, "est/s", nrep / dt, "mean tau", res["meetingtime"].mean())

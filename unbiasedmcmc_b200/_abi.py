@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libubm.so")
+LIB_PATH = os.environ.get("UBM_LIB_PATH") or os.path.join(HERE, "_lib", "libubm.so")   # override: debug builds only
 
 UBM_OK, UBM_ERR_INVALID, UBM_ERR_CUDA, UBM_ERR_UNSUPPORTED, UBM_ERR_TAPE, UBM_ERR_NOMEM = range(6)
 UBM_DRAWS_PHILOX, UBM_DRAWS_TAPE = 0, 1
@@ -132,6 +132,19 @@ def load_lib():
                               c_double_p, c_double_p, c_double_p, c_int64_p, c_double_p]
     lib.ubm_estimator_bins.argtypes = [vp, C.c_int32, C.POINTER(ubm_bins), C.c_int64, C.c_int64, C.c_int64,
                                        C.c_int64, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]
+    dp = C.POINTER(ubm_draws)
+    lib.ubm_rnorm_max_coupling.argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                           C.c_double, c_double_p, c_int32_p]
+    lib.ubm_rnorm_reflectionmax.argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double,
+                                            c_double_p, c_int32_p]
+    lib.ubm_rmvnorm_reflectionmax.argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_int32, c_double_p, c_double_p,
+                                              c_double_p, c_double_p, c_double_p, c_int32_p]
+    lib.ubm_fast_rmvnorm_chol.argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p]
+    lib.ubm_fast_dmvnorm_chol_inverse.argtypes = [vp, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p,
+                                                  c_double_p]
+    for name in ("ubm_rnorm_max_coupling", "ubm_rnorm_reflectionmax", "ubm_rmvnorm_reflectionmax",
+                 "ubm_fast_rmvnorm_chol", "ubm_fast_dmvnorm_chol_inverse"):
+        getattr(lib, name).restype = C.c_int
     lib.ubm_plan_create.argtypes = [vp, C.c_int32, vp, C.c_int32, C.POINTER(ubm_bins), C.c_int64, C.c_int64,
                                     C.c_int64, C.c_int64, C.c_int64, C.POINTER(vp)]
     lib.ubm_plan_launch.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int64]

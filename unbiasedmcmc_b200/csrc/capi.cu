@@ -16,6 +16,7 @@
 #include "ubm_summary.cuh"
 #include "ubm_post.cuh"
 #include "ubm_peaks.cuh"
+#include "ubm_prims.cuh"
 
 using namespace ubm;
 
@@ -548,6 +549,135 @@ int ubm_estimator_bins(ubm_handle* h, int32_t dim, const ubm_bins* bins, int64_t
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(binvals, out.p, (size_t)nrep * nbins * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return UBM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stand-alone primitives, batched over samples
+// ---------------------------------------------------------------------------------------------------
+static int prim_params(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, RunParams* P, DevBuf* tu,
+                       DevBuf* tn, DevBuf* status) {
+  if (!draws) return fail(h, UBM_ERR_INVALID, "null draws");
+  if (n < 1) return fail(h, UBM_ERR_INVALID, "n must be >= 1");
+  CU(cudaSetDevice(h->device));
+  *P = RunParams{};
+  P->nrep = n; P->rep_offset = rep_offset; P->draws_mode = draws->mode; P->seed = draws->seed;
+  if (draws->mode == UBM_DRAWS_TAPE) {
+    if (draws->tape_u && draws->len_u > 0) {
+      CU(tu->alloc((size_t)n * draws->len_u * 8));
+      CU(cudaMemcpy(tu->p, draws->tape_u, (size_t)n * draws->len_u * 8, cudaMemcpyHostToDevice));
+      P->tape_u = tu->as<double>(); P->len_u = draws->len_u;
+    }
+    if (draws->tape_n && draws->len_n > 0) {
+      CU(tn->alloc((size_t)n * draws->len_n * 8));
+      CU(cudaMemcpy(tn->p, draws->tape_n, (size_t)n * draws->len_n * 8, cudaMemcpyHostToDevice));
+      P->tape_n = tn->as<double>(); P->len_n = draws->len_n;
+    }
+  }
+  CU(status->alloc(4));
+  CU(cudaMemset(status->p, 0, 4));
+  P->status = status->as<int>();
+  return UBM_OK;
+}
+static int prim_finish(ubm_handle* h, DevBuf* status) {
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  int st = 0;
+  CU(cudaMemcpy(&st, status->p, 4, cudaMemcpyDeviceToHost));
+  if (st == UBM_ERR_TAPE) return fail(h, UBM_ERR_TAPE, "replay tape exhausted");
+  return UBM_OK;
+}
+
+static int scalar_coupling(ubm_handle* h, const ubm_draws* draws, int mode, int64_t n, int64_t rep_offset, double mu1,
+                           double mu2, double s1, double s2, double* xy, int32_t* identical) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!xy || !identical) return fail(h, UBM_ERR_INVALID, "null output");
+  if (!(s1 > 0) || !(s2 > 0)) return fail(h, UBM_ERR_INVALID, "standard deviations must be > 0");
+  RunParams P; DevBuf tu, tn, status, dxy, did;
+  int st = prim_params(h, draws, n, rep_offset, &P, &tu, &tn, &status);
+  if (st != UBM_OK) return st;
+  CU(dxy.alloc((size_t)n * 16)); CU(did.alloc((size_t)n * 4));
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (draws->mode == UBM_DRAWS_TAPE)
+    prim_scalar_coupling_kernel<true><<<grid, 128, 0, h->stream>>>(P, mode, mu1, mu2, s1, s2, ubm_log(s1), ubm_log(s2), dxy.as<double>(), did.as<int>());
+  else
+    prim_scalar_coupling_kernel<false><<<grid, 128, 0, h->stream>>>(P, mode, mu1, mu2, s1, s2, ubm_log(s1), ubm_log(s2), dxy.as<double>(), did.as<int>());
+  h->launches += 1;
+  st = prim_finish(h, &status);
+  CU(cudaMemcpy(xy, dxy.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(identical, did.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return st;
+}
+
+int ubm_rnorm_max_coupling(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, double mu1, double mu2,
+                           double sigma1, double sigma2, double* xy, int32_t* identical) {
+  return scalar_coupling(h, draws, 1, n, rep_offset, mu1, mu2, sigma1, sigma2, xy, identical);
+}
+int ubm_rnorm_reflectionmax(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, double mu1, double mu2,
+                            double sigma, double* xy, int32_t* identical) {
+  return scalar_coupling(h, draws, 0, n, rep_offset, mu1, mu2, sigma, sigma, xy, identical);
+}
+
+static int mvn_sample(ubm_handle* h, const ubm_draws* draws, int mode, int64_t n, int64_t rep_offset, int32_t d,
+                      const double* mu1, const double* mu2, const double* chol, const double* chol_inv, double* out,
+                      int32_t* identical) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!mu1 || !chol || !out || (mode == 1 && (!mu2 || !chol_inv || !identical))) return fail(h, UBM_ERR_INVALID, "null argument");
+  if (mode == 1 && d < 2)   // R/mvnorm_couplings.R:96-98
+    return fail(h, UBM_ERR_INVALID, "function 'rmvnorm_reflectionmax' is meant for multivariate Normals; for univariate Normals, use 'rnorm_reflectionmax'");
+  if (d < 1 || d > PRIM_MAXD) return fail(h, UBM_ERR_INVALID, "1 <= d <= 128");
+  RunParams P; DevBuf tu, tn, status, dm1, dm2, dc, dci, dout, did;
+  int st = prim_params(h, draws, n, rep_offset, &P, &tu, &tn, &status);
+  if (st != UBM_OK) return st;
+  const size_t vb = (size_t)d * 8, mb = (size_t)d * d * 8, ob = (size_t)n * d * 8 * (mode == 1 ? 2 : 1);
+  CU(dm1.alloc(vb)); CU(dc.alloc(mb)); CU(dout.alloc(ob)); CU(did.alloc((size_t)n * 4));
+  CU(cudaMemcpy(dm1.p, mu1, vb, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dc.p, chol, mb, cudaMemcpyHostToDevice));
+  if (mode == 1) {
+    CU(dm2.alloc(vb)); CU(dci.alloc(mb));
+    CU(cudaMemcpy(dm2.p, mu2, vb, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dci.p, chol_inv, mb, cudaMemcpyHostToDevice));
+  }
+  const unsigned grid = (unsigned)((n + 63) / 64);
+  if (draws->mode == UBM_DRAWS_TAPE)
+    prim_mvn_sample_kernel<true><<<grid, 64, 0, h->stream>>>(P, mode, d, dm1.as<double>(), dm2.as<double>(), dc.as<double>(), dci.as<double>(), dout.as<double>(), did.as<int>());
+  else
+    prim_mvn_sample_kernel<false><<<grid, 64, 0, h->stream>>>(P, mode, d, dm1.as<double>(), dm2.as<double>(), dc.as<double>(), dci.as<double>(), dout.as<double>(), did.as<int>());
+  h->launches += 1;
+  st = prim_finish(h, &status);
+  CU(cudaMemcpy(out, dout.p, ob, cudaMemcpyDeviceToHost));
+  if (mode == 1) CU(cudaMemcpy(identical, did.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return st;
+}
+
+int ubm_fast_rmvnorm_chol(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d,
+                          const double* mean, const double* chol, double* out) {
+  return mvn_sample(h, draws, 0, n, rep_offset, d, mean, nullptr, chol, nullptr, out, nullptr);
+}
+int ubm_rmvnorm_reflectionmax(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d,
+                              const double* mu1, const double* mu2, const double* chol, const double* chol_inv,
+                              double* xy, int32_t* identical) {
+  return mvn_sample(h, draws, 1, n, rep_offset, d, mu1, mu2, chol, chol_inv, xy, identical);
+}
+int ubm_fast_dmvnorm_chol_inverse(ubm_handle* h, int64_t n, int32_t d, const double* x, const double* mean,
+                                  const double* chol_inv, double* out) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!x || !mean || !chol_inv || !out || n < 1) return fail(h, UBM_ERR_INVALID, "null argument");
+  if (d < 1 || d > PRIM_MAXD) return fail(h, UBM_ERR_INVALID, "1 <= d <= 128");
+  CU(cudaSetDevice(h->device));
+  double halflogdet = 0.0;
+  for (int j = 0; j < d; ++j) halflogdet = halflogdet + ubm_log(chol_inv[(size_t)j * d + j]);
+  const double cst = -(-halflogdet) - (d * 0.9189385);      // src/mvnorm.cpp:74-75
+  DevBuf dx, dm, dci, dout;
+  CU(dx.alloc((size_t)n * d * 8)); CU(dm.alloc((size_t)d * 8)); CU(dci.alloc((size_t)d * d * 8)); CU(dout.alloc((size_t)n * 8));
+  CU(cudaMemcpy(dx.p, x, (size_t)n * d * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dm.p, mean, (size_t)d * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(dci.p, chol_inv, (size_t)d * d * 8, cudaMemcpyHostToDevice));
+  prim_dmvnorm_kernel<<<(unsigned)((n + 63) / 64), 64, 0, h->stream>>>(n, d, dx.as<double>(), dm.as<double>(), dci.as<double>(), cst, dout.as<double>());
+  h->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
   return UBM_OK;
 }
 

@@ -257,7 +257,16 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
   const double denom = (double)(P.m - P.k + 1);
   const unsigned FULL = 0xffffffffu;
 
+#ifdef UBM_MVN_TIMING
+  long long tacc[5] = {0, 0, 0, 0, 0}, tsteps = 0;
+#define TMARK(i) do { long long now_ = clock64(); tacc[i] += now_ - tprev; tprev = now_; } while (0)
+#else
+#define TMARK(i) do { } while (0)
+#endif
   for (;;) {
+#ifdef UBM_MVN_TIMING
+    long long tprev = clock64(); tsteps++;
+#endif
     // ================================================================ per-slot section (one warp per slot)
     // finishes the step just computed (densities -> accept/reject -> state/estimator update), runs the slot state
     // machine (finish / write-out / fetch the next replicate), and prepares the inputs of the next step.
@@ -428,6 +437,7 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
     const int any_active = __syncthreads_or(my_active);
     if (!any_active) break;
     const int any_coupled = __syncthreads_or(my_coupled);
+    TMARK(0);
 
     // row masks of this step (every warp computes them from the slot phases)
     unsigned mA, mI, mS;
@@ -504,6 +514,7 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
       }
       __syncthreads();
     }
+    TMARK(1);
     // chain-2 rows of the coupled slots whose proposals differ
     unsigned mD;
     {
@@ -553,6 +564,7 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
       }
     }
     __syncthreads();
+    TMARK(2);
     // ================================================================ phase C: w = Cinv_pi^T (prop - mean), |w|^2
     if (tid < MVN_GT) {
       const unsigned m1 = mA | mS | mI, m2 = mD | mI;
@@ -586,7 +598,13 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
       }
     }
     __syncthreads();
+    TMARK(3);
   }
+#ifdef UBM_MVN_TIMING
+  if (tid == 0 && blockIdx.x == 0)
+    printf("mvn timing (cycles/step, block 0): steps %lld slot %.0f A+coupling %.0f B %.0f C %.0f\n", tsteps,
+           (double)tacc[0] / tsteps, (double)tacc[1] / tsteps, (double)tacc[2] / tsteps, (double)tacc[3] / tsteps);
+#endif
 }
 
 template <class Buf>

@@ -1,0 +1,129 @@
+// ubm_prims.cuh — the reference's stand-alone coupling / MVN primitives, batched: one THREAD per sample, sample i
+// drawing from the typed streams of replicate index rep_offset + i (from draw 0).  These are the exported R
+// functions of the path that are not drivers (NAMESPACE: rnorm_max_coupling, rnorm_reflectionmax,
+// rmvnorm_reflectionmax, fast_rmvnorm_chol, fast_dmvnorm_chol_inverse); the driver kernels inline the same
+// arithmetic.  Utility kernels: matrices are read from global memory, vectors live in local memory (d <= 128).
+#pragma once
+#include "ubm_common.cuh"
+#include "ubm_mix.cuh"
+
+namespace ubm {
+
+#define PRIM_MAXD 128
+
+// R/rnorm_max_coupling.R:17-23 over R/get_max_coupling.R:24-39 (mode 1) ; R/rnorm_reflectionmax.R:18-39 (mode 0)
+template <bool TAPE>
+__global__ void prim_scalar_coupling_kernel(const RunParams P, int mode, double mu1, double mu2, double s1, double s2,
+                                            double ls1, double ls2, double* __restrict__ xy, int* __restrict__ ident) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nrep) return;
+  ScalarDraws<TAPE> D;
+  D.init(P, i);
+  double x, y;
+  bool id;
+  if (mode == 0) {
+    const double xdot = D.n();
+    const double z = (mu1 - mu2) / s1;
+    const double normz = sqrt(z * z);
+    const double e = z / normz;
+    const double utilde = D.u();
+    const double a = xdot + z;
+    id = ubm_log(utilde) < (-((UBM_LN_SQRT_2PI + 0.5 * a * a) + 0.0)) - (-((UBM_LN_SQRT_2PI + 0.5 * xdot * xdot) + 0.0));
+    const double ydot = id ? (xdot + z) : (xdot - 2 * (e * xdot) * e);
+    x = mu1 + s1 * xdot;
+    y = mu2 + s1 * ydot;
+  } else {
+    x = mu1 + s1 * D.n();
+    if (MixModel::dnorm_log(x, mu1, s1, ls1) + ubm_log(D.u()) < MixModel::dnorm_log(x, mu2, s2, ls2)) { id = true; y = x; }
+    else {
+      id = false;
+      bool reject = true;
+      y = 0.0;
+      while (reject && !D.bad) {
+        y = mu2 + s2 * D.n();
+        reject = MixModel::dnorm_log(y, mu2, s2, ls2) + ubm_log(D.u()) < MixModel::dnorm_log(y, mu1, s1, ls1);
+      }
+    }
+  }
+  xy[2 * i] = x; xy[2 * i + 1] = y; ident[i] = id ? 1 : 0;
+  if (D.bad) atomicExch(P.status, UBM_ERR_TAPE);
+}
+
+// y_j = sum_{i <= j} v_i U[i, j], U column-major upper triangular (sequential fma, as the driver kernels)
+__device__ inline void prim_vec_times_upper(const double* v, const double* __restrict__ U, int d, double* out) {
+  for (int j = 0; j < d; ++j) {
+    double acc = 0.0;
+    for (int i = 0; i <= j; ++i) acc = ubm_fma(v[i], U[(size_t)j * d + i], acc);
+    out[j] = acc;
+  }
+}
+__device__ inline double prim_sum_g4(const double* a, const double* b, int d) {   // canonical reduction order
+  double s[32];
+  for (int q = 0; q < 32; ++q) s[q] = 0.0;
+  for (int j = 0; j < d; ++j) s[j >> 2] = ubm_fma(a[j], b[j], s[j >> 2]);
+  return ubm_butterfly32(s);
+}
+
+// mode 0: fast_rmvnorm_cholesky_ (src/mvnorm.cpp:30-46) -> out [n][d]
+// mode 1: rmvnorm_reflection_max_coupling_ (src/mvnorm.cpp:185-236) -> out [n][2][d], ident [n]
+template <bool TAPE>
+__global__ void prim_mvn_sample_kernel(const RunParams P, int mode, int d, const double* __restrict__ mu1,
+                                       const double* __restrict__ mu2, const double* __restrict__ chol,
+                                       const double* __restrict__ chol_inv, double* __restrict__ out,
+                                       int* __restrict__ ident) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nrep) return;
+  ScalarDraws<TAPE> D;
+  D.init(P, i);
+  double xi[PRIM_MAXD], z[PRIM_MAXD], t[PRIM_MAXD];
+  if (mode == 0) {
+    for (int j = 0; j < d; ++j) xi[j] = D.n();
+    prim_vec_times_upper(xi, chol, d, t);
+    for (int j = 0; j < d; ++j) out[i * d + j] = t[j] + mu1[j];
+  } else {
+    for (int j = 0; j < d; ++j) t[j] = mu2[j] - mu1[j];
+    prim_vec_times_upper(t, chol_inv, d, z);                               // :191
+    for (int j = 0; j < d; ++j) xi[j] = D.n();                             // :193-195
+    for (int j = 0; j < d; ++j) z[j] = -z[j];                              // :198
+    const double normz = sqrt(prim_sum_g4(z, z, d));                       // :199
+    double* X = out + (size_t)i * 2 * d;
+    double* Y = X + d;
+    bool id;
+    if (normz < 1e-15) {                                                   // :200-210
+      id = true;
+      prim_vec_times_upper(xi, chol, d, t);
+      for (int j = 0; j < d; ++j) { X[j] = mu1[j] + t[j]; Y[j] = X[j]; }
+    } else {
+      for (int j = 0; j < d; ++j) z[j] = z[j];
+      double e[PRIM_MAXD];
+      for (int j = 0; j < d; ++j) e[j] = z[j] / normz;                     // :212
+      const double utilde = D.u();
+      const double edx = prim_sum_g4(e, xi, d);                            // :216
+      const double a = edx + normz;
+      id = ubm_log(utilde) < (-0.5 * a * a + 0.5 * edx * edx);             // :217
+      prim_vec_times_upper(xi, chol, d, t);                                // :224
+      for (int j = 0; j < d; ++j) X[j] = mu1[j] + t[j];
+      if (id) { for (int j = 0; j < d; ++j) Y[j] = X[j]; }                 // :228-229
+      else {
+        for (int j = 0; j < d; ++j) e[j] = xi[j] - 2. * edx * e[j];        // :221 (eta)
+        prim_vec_times_upper(e, chol, d, t);                               // :225
+        for (int j = 0; j < d; ++j) Y[j] = mu2[j] + t[j];
+      }
+    }
+    ident[i] = id ? 1 : 0;
+  }
+  if (D.bad) atomicExch(P.status, UBM_ERR_TAPE);
+}
+
+// fast_dmvnorm_cholesky_inverse_ (src/mvnorm.cpp:71-86): x [n][d] -> out [n]
+__global__ void prim_dmvnorm_kernel(int64_t n, int d, const double* __restrict__ x, const double* __restrict__ mean,
+                                    const double* __restrict__ chol_inv, double cst, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double xc[PRIM_MAXD], w[PRIM_MAXD];
+  for (int j = 0; j < d; ++j) xc[j] = x[i * d + j] - mean[j];
+  prim_vec_times_upper(xc, chol_inv, d, w);
+  out[i] = -0.5 * prim_sum_g4(w, w, d) + cst;
+}
+
+}  // namespace ubm

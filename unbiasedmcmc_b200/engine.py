@@ -127,6 +127,51 @@ class Engine:
                                                 A.dptr(s2), A.dptr(chains["meetingtime"]), A.dptr(out)))
         return out
 
+    # ---- stand-alone primitives of the R API, batched over n samples ----------------------------------
+    def rnorm_max_coupling(self, mu1, mu2, sigma1, sigma2, draws, n=1, rep_offset=0):
+        xy, ident = np.zeros((n, 2)), np.zeros(n, dtype=np.int32)
+        ds = draws.struct(n)
+        self._check(self.lib.ubm_rnorm_max_coupling(self.h, C.byref(ds), n, rep_offset, mu1, mu2, sigma1, sigma2,
+                                                    A.dptr(xy), A.i32ptr(ident)))
+        return {"xy": xy, "identical": ident.astype(bool)}
+
+    def rnorm_reflectionmax(self, mu1, mu2, sigma, draws, n=1, rep_offset=0):
+        xy, ident = np.zeros((n, 2)), np.zeros(n, dtype=np.int32)
+        ds = draws.struct(n)
+        self._check(self.lib.ubm_rnorm_reflectionmax(self.h, C.byref(ds), n, rep_offset, mu1, mu2, sigma, A.dptr(xy),
+                                                     A.i32ptr(ident)))
+        return {"xy": xy, "identical": ident.astype(bool)}
+
+    def rmvnorm_reflectionmax(self, mu1, mu2, Cholesky, Cholesky_inverse, draws, n=1, rep_offset=0):
+        mu1, mu2 = np.ascontiguousarray(mu1, dtype=np.float64), np.ascontiguousarray(mu2, dtype=np.float64)
+        d = len(mu1)
+        ch = np.ascontiguousarray(np.asarray(Cholesky, dtype=np.float64).T).reshape(-1)       # column-major
+        ci = np.ascontiguousarray(np.asarray(Cholesky_inverse, dtype=np.float64).T).reshape(-1)
+        xy, ident = np.zeros((n, 2, d)), np.zeros(n, dtype=np.int32)
+        ds = draws.struct(n)
+        self._check(self.lib.ubm_rmvnorm_reflectionmax(self.h, C.byref(ds), n, rep_offset, d, A.dptr(mu1), A.dptr(mu2),
+                                                       A.dptr(ch), A.dptr(ci), A.dptr(xy), A.i32ptr(ident)))
+        return {"xy": xy, "identical": ident.astype(bool)}
+
+    def fast_rmvnorm_chol(self, nparticles, mean, chol, draws, rep_offset=0):
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        d = len(mean)
+        ch = np.ascontiguousarray(np.asarray(chol, dtype=np.float64).T).reshape(-1)
+        out = np.zeros((nparticles, d))
+        ds = draws.struct(nparticles)
+        self._check(self.lib.ubm_fast_rmvnorm_chol(self.h, C.byref(ds), nparticles, rep_offset, d, A.dptr(mean),
+                                                   A.dptr(ch), A.dptr(out)))
+        return out
+
+    def fast_dmvnorm_chol_inverse(self, x, mean, chol_inverse):
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        n, d = x.shape
+        ci = np.ascontiguousarray(np.asarray(chol_inverse, dtype=np.float64).T).reshape(-1)
+        out = np.zeros(n)
+        self._check(self.lib.ubm_fast_dmvnorm_chol_inverse(self.h, n, d, A.dptr(x), A.dptr(mean), A.dptr(ci), A.dptr(out)))
+        return out
+
     # ---- device-resident plan (kernel-only timing, multi-GPU summaries) -----------------------------
     def plan(self, model, h_kind=A.UBM_H_IDENTITY, bins=None, k=0, m=1, lag=1, max_iterations=0, max_nrep=1):
         return Plan(self, model, h_kind, bins, k, m, lag, max_iterations, max_nrep)
