@@ -73,6 +73,23 @@ def workload(name):
             site_updates = 0.99 * 16 * 1024 * (sum_iter + (sum_tau - S[0]))
             return 25.0 * site_updates
         return mdl, kw, 2368, desc, flops, "int32"
+    if name == "c3":
+        mdl = cases.c3_model()
+        n, p_ = 1000, 49
+        kw = dict(h_kind=A.UBM_H_IDENTITY, bins=None, k=110, m=1100, lag=1)
+        desc = ("C3: logistic regression n=1000, p=49 (synthetic X, prior N(0, 10 I)), coupled Polya-Gamma Gibbs "
+                "(per-observation max-coupled PG draws + max-coupled MVN beta), lag=1, k=110, m=1100, h = beta")
+
+        def flops(S, nrep):
+            # single step = X beta (n p fma) + Gram (n p (p+1)/2 fma) + Cholesky/solves (~p^3/2 fma)
+            # + n PG draws (~3e2 flop-equivalents each); a coupled step does all of it for both chains (Gram shares
+            # the products) plus the Sigma / second-Cholesky work of rmvnorm_max
+            n_all, sum_tau, sum_iter = S[0] + S[1], S[2], S[5]
+            gram = n * p_ * (p_ + 1) / 2 * 2.0
+            single = 2.0 * n * p_ + gram + p_ ** 3 + 300.0 * n
+            coupled = 2.0 * (2.0 * n * p_ + gram + 2.0 * p_ ** 3 + 300.0 * n)
+            return single * (sum_iter - (sum_tau - S[0])) + coupled * (sum_tau - S[0])
+        return mdl, kw, 1184, desc, flops, "fp64"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -268,7 +285,8 @@ def main():
     peak = peaks["fp64_tflops"] if bound == "fp64" else peaks["int32_tops"]
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s" if bound == "fp64" else "Top/s",
                 "frac": achieved / peak, "traffic": None,
-                "kernel": {"c1": "mix_driver_kernel", "c2": "mvn_driver_kernel", "c4": "ising_driver_kernel"}[args.workload],
+                "kernel": {"c1": "mix_driver_kernel", "c2": "mvn_driver_kernel", "c3": "pg_driver_kernel",
+                           "c4": "ising_driver_kernel"}[args.workload],
                 "kernel_share_of_step": kernel_ms / dev_ms,
                 "peak_source": "measured live by ubm_measure_peaks (independent DFMA / IMAD chains, 2 ops each); "
                                "MEASURED_PEAKS.json holds no FP64 / INT32 figure; HBM is not the bound (state stays on "

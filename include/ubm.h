@@ -121,6 +121,20 @@ typedef struct {
   int32_t reserved;
 } ubm_model_ising_pt;
 
+/* C3: Bayesian logistic regression, Polya-Gamma Gibbs sampler (Polson, Scott & Windle), coupled as in
+ * inst/reproducegermancredit/germancredit.run.R:23-49: PG draws max-coupled per observation
+ * (src/logisticregressioncoupling.cpp:79-115 over src/PolyaGamma.cpp:175-226), beta from a max-coupled pair of
+ * multivariate Normals (R/logistic_regression.R:180-209, src/mvnorm.cpp:91-129) whose parameters come from
+ * m_sigma_function_ (src/logisticregression.cpp:32-56).  Prior beta ~ N(b, B); rinit: beta ~ N(b, B), w = 0.
+ * The chain state exposed to h / trajectories is beta (dim = p), as the reference's scripts store it. */
+typedef struct {
+  int32_t n, p;           /* n <= 4096 observations, p <= 64 covariates */
+  const double* X;        /* n x p column-major design matrix */
+  const double* Y;        /* [n] responses in {0, 1} */
+  const double* b;        /* [p] prior mean */
+  const double* B;        /* p x p prior covariance (column-major, symmetric positive definite) */
+} ubm_model_pg_logistic;
+
 /* ---------------------------------------------------------------------------------------------
  * test functions h and histogram bins
  * ------------------------------------------------------------------------------------------- */

@@ -233,6 +233,13 @@ int orc_dmvnorm_chol_inverse(int64_t n, int32_t d, const double* x, const double
   return UBM_OK;
 }
 
+// Polya-Gamma probes: n draws of PG(1, z) (cell i of a fresh replicate stream), log Phi
+void orc_pg_draws(uint64_t seed, double z, int64_t n, double* out) {
+  Draws D; D.seed = seed; D.rep = 0;
+  for (int64_t i = 0; i < n; ++i) { CellDraws c(&D, (uint64_t)i); out[i] = pg_draw(z, c); }
+}
+void orc_vec_pnorm_log(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ubm_pnorm_log(x[i]); }
+
 // numerics probes (tests/test_numerics.py)
 void orc_vec_log(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ubm_log(x[i]); }
 void orc_vec_exp(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ubm_exp(x[i]); }

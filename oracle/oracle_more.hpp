@@ -3,6 +3,8 @@
 #pragma once
 #include "oracle_core.hpp"
 #include "oracle_ising.hpp"
+#include "oracle_pg.hpp"
 
 #define ORC_MORE_DISPATCH(CALL)                                                                      \
-  case UBM_MODEL_ISING_PT: { orc::IsingModel M((const ubm_model_ising_pt*)model); return CALL; }
+  case UBM_MODEL_ISING_PT: { orc::IsingModel M((const ubm_model_ising_pt*)model); return CALL; }       \
+  case UBM_MODEL_PG_LOGISTIC: { orc::PgLogisticModel M((const ubm_model_pg_logistic*)model); return CALL; }

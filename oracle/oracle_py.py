@@ -40,7 +40,9 @@ def lib():
         L.orc_estimator_bins.argtypes = [C.c_int32, C.POINTER(A.ubm_bins), C.c_int64, C.c_int64, C.c_int64,
                                          C.c_int64, C.c_int64, A.c_double_p, A.c_double_p, A.c_double_p,
                                          A.c_double_p]
-        for f in ("orc_vec_log", "orc_vec_exp", "orc_vec_log1p", "orc_vec_qnorm"):
+        L.orc_pg_draws.argtypes = [C.c_uint64, C.c_double, C.c_int64, A.c_double_p]
+        L.orc_pg_draws.restype = None
+        for f in ("orc_vec_log", "orc_vec_exp", "orc_vec_log1p", "orc_vec_qnorm", "orc_vec_pnorm_log"):
             getattr(L, f).argtypes = [A.c_double_p, A.c_double_p, C.c_int64]
             getattr(L, f).restype = None
         L.orc_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
@@ -67,6 +69,12 @@ def vec(fn, x):
     y = np.empty_like(x)
     getattr(lib(), "orc_vec_" + fn)(A.dptr(x), A.dptr(y), x.size)
     return y
+
+
+def pg_draws(seed, z, n):
+    out = np.empty(n, dtype=np.float64)
+    lib().orc_pg_draws(int(seed), float(z), n, A.dptr(out))
+    return out
 
 
 def philox(ctr, key):

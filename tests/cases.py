@@ -42,3 +42,20 @@ def c2_model(d=100, kind="dense", init="target", mean=None):
 def c4_model(nchains=16, pswap=0.01, lo=0.3, hi=0.55):
     """inst/reproduceisingmodel/run.batch.ising.R:169-171: betas = seq(0.3, 0.55, length.out = 16), pswap 0.01."""
     return R.IsingPT(np.linspace(lo, hi, nchains), pswap)
+
+
+def c3_data(n=1000, p=49, seed=SEED):
+    """X = [1 | iid N(0,1) columns, standardised], beta* ~ N(0, 0.5^2 I), Y ~ Bernoulli(expit(X beta*))."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, p))
+    X[:, 1:] = (X[:, 1:] - X[:, 1:].mean(0)) / X[:, 1:].std(0, ddof=1)
+    X[:, 0] = 1.0
+    beta = 0.5 * rng.standard_normal(p)
+    Y = (rng.uniform(size=n) < 1.0 / (1.0 + np.exp(-X @ beta))).astype(np.float64)
+    return Y, X
+
+
+def c3_model(n=1000, p=49, seed=SEED):
+    """germancredit.run.R:18-20: prior b = 0, B = 10 I."""
+    Y, X = c3_data(n, p, seed)
+    return R.PgLogistic(Y, X, np.zeros(p), 10.0 * np.eye(p))

@@ -1,0 +1,51 @@
+"""CPU: oracle pins for C3 (Polya-Gamma logistic) and C4 (Ising PT) — analytic moments and MCMC cross-checks
+(PG(1,z) mean tanh(z/2)/(2z) and variance from src/PolyaGamma.cpp:232-263; unbiased estimator vs a
+long single chain as in inst/check/check_ising.R:112-164)."""
+import numpy as np
+from scipy.special import log_ndtr
+
+from tests import cases
+from unbiasedmcmc_b200 import _abi as A
+from unbiasedmcmc_b200 import registry as R
+
+
+def test_pnorm_log_matches_scipy(oracle):
+    x = np.concatenate([np.linspace(-38, 9, 100001), np.random.default_rng(0).uniform(-1, 1, 50000)])
+    y, ref = oracle.vec("pnorm_log", x), log_ndtr(x)
+    assert np.max(np.abs(y - ref) / np.maximum(np.abs(ref), 1e-300)) < 1e-13
+
+
+def test_polya_gamma_moments(oracle):
+    for z in (0.0, 0.5, 2.0, 5.0, 12.0):
+        w = oracle.pg_draws(11, z, 400000)
+        mean = np.tanh(z / 2) / (2 * z) if z > 0 else 0.25
+        var = (np.sinh(z) - z) / (4 * z ** 3 * np.cosh(z / 2) ** 2) if z > 0 else 1.0 / 24
+        assert abs(w.mean() - mean) < 4.5 * np.sqrt(var / len(w))
+        assert abs(w.var() / var - 1) < 0.03
+        assert w.min() > 0
+
+
+def test_c3_unbiased_estimator_matches_long_chain(oracle):
+    mdl = cases.c3_model(120, 5, seed=3)
+    e = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=1), k=30, m=150, lag=1, nrep=1500, nthreads=8)
+    assert np.isfinite(e["meetingtime"]).all() and e["meetingtime"].max() < 60
+    u = e["uestimator"]
+    ch = oracle.sample_coupled_chains(mdl, R.Draws(seed=7), m=20000, lag=1, stride=20100, nrep=1)
+    s = ch["samples1"][0, 1000:20001]
+    # long-chain standard error via batch means
+    bm = s[: (len(s) // 50) * 50].reshape(50, -1, s.shape[1]).mean(1)
+    se = np.sqrt(bm.var(0, ddof=1) / 50 + u.var(0) / len(u))
+    assert np.all(np.abs(u.mean(0) - s.mean(0)) < 5 * se)
+
+
+def test_c4_natural_statistic_and_meeting(oracle):
+    mdl = cases.c4_model(3, 0.1, 0.2, 0.3)
+    e = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=2), k=50, m=200, lag=1, nrep=64, nthreads=8)
+    assert np.isfinite(e["meetingtime"]).all()
+    u = e["uestimator"]
+    # natural statistic grows with the inverse temperature; per-site value between 0 and 2
+    assert np.all(np.diff(u.mean(0)) > 0)
+    assert np.all(u.mean(0) > 0) and np.all(u.mean(0) < 2048)
+    # estimator == H_bar of the stored natural statistics
+    ch = oracle.sample_coupled_chains(mdl, R.Draws(seed=2), m=200, lag=1, stride=4000, nrep=8)
+    np.testing.assert_allclose(oracle.h_bar(ch, A.UBM_H_IDENTITY, k=50, m=200), u[:8], rtol=1e-12)

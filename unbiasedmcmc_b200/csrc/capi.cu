@@ -13,6 +13,7 @@
 #include "ubm_mix.cuh"
 #include "ubm_mvn.cuh"
 #include "ubm_ising.cuh"
+#include "ubm_pg.cuh"
 #include "ubm_summary.cuh"
 #include "ubm_post.cuh"
 #include "ubm_peaks.cuh"
@@ -61,6 +62,7 @@ struct ubm_plan {
   MixParams mix{};
   MvnDevice mvn{};
   IsingDevice ising{};
+  PgDevice pg{};
   DevBuf model_blob;
   // results
   DevBuf uest, mcmc, corr, tau, cost, iter, bins_out, bin_acc, breaks, summary, counter, status, scratch;
@@ -85,6 +87,7 @@ static int model_dims(int32_t kind, const void* model, int* dim) {
     case UBM_MODEL_NORMAL_MIXTURE: *dim = 1; return UBM_OK;
     case UBM_MODEL_MVN: *dim = ((const ubm_model_mvn*)model)->d; return UBM_OK;
     case UBM_MODEL_ISING_PT: *dim = ((const ubm_model_ising_pt*)model)->nchains; return UBM_OK;
+    case UBM_MODEL_PG_LOGISTIC: *dim = ((const ubm_model_pg_logistic*)model)->p; return UBM_OK;
     default: return UBM_ERR_UNSUPPORTED;
   }
 }
@@ -128,6 +131,19 @@ static int register_model(ubm_plan* p, int32_t kind, const void* model) {
     if (!(s->proba_swapmove >= 0.0 && s->proba_swapmove <= 1.0)) return fail(h, UBM_ERR_INVALID, "ising: proba_swapmove in [0,1]");
     ising_pack_host(s, &p->ising);
     p->dim = s->nchains;
+    return UBM_OK;
+  }
+  if (kind == UBM_MODEL_PG_LOGISTIC) {
+    const ubm_model_pg_logistic* s = (const ubm_model_pg_logistic*)model;
+    if (s->p < 1 || s->p > PG_MAXP || s->n < 1 || s->n > 4096) return fail(h, UBM_ERR_INVALID, "pg logistic: 1 <= p <= 64, 1 <= n <= 4096");
+    if (!s->X || !s->Y || !s->b || !s->B) return fail(h, UBM_ERR_INVALID, "pg logistic: null data");
+    p->dim = s->p;
+    std::vector<double> blob;
+    pg_pack_host(s, &p->pg, &blob);
+    CU(p->model_blob.alloc(blob.size() * sizeof(double)));
+    CU(cudaMemcpyAsync(p->model_blob.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    pg_bind_device(&p->pg, p->model_blob.as<double>());
     return UBM_OK;
   }
   return fail(h, UBM_ERR_UNSUPPORTED, "model kind not in the device registry (no CPU fallback)");
@@ -253,6 +269,9 @@ static int plan_run(ubm_plan* p, int draws_mode, uint64_t seed, int64_t nrep, in
     h->launches += 1;
   } else if (p->model_kind == UBM_MODEL_MVN) {
     int stl = mvn_launch(p->mvn, P, tape, nsm, st, p->scratch, &h->launches, &h->err);
+    if (stl != UBM_OK) return stl;
+  } else if (p->model_kind == UBM_MODEL_PG_LOGISTIC) {
+    int stl = pg_launch(p->pg, P, tape, nsm, st, &h->launches, &h->err);
     if (stl != UBM_OK) return stl;
   } else if (p->model_kind == UBM_MODEL_ISING_PT) {
     int stl = ising_launch(p->ising, P, tape, nsm, st, &h->launches, &h->err);

@@ -1,0 +1,634 @@
+// ubm_pg.cuh — C3: Polya-Gamma Gibbs sampler for Bayesian logistic regression, coupled.
+//
+// Replaces, fused into one persistent kernel per launch:
+//   drivers   R/meetingtime.R:24-48, R/coupled_chains.R:39-87, R/unbiasedestimator.R:43-104
+//   kernels   inst/reproducegermancredit/germancredit.run.R:23-49 (single, coupled, rinit)
+//   numerics  src/PolyaGamma.cpp:65-226 (Devroye PG(1,z) sampler), src/logisticregressioncoupling.cpp:9-115
+//             (logcosh, xbeta_, w_max_couplingC), src/logisticregression.cpp:32-56 (m_sigma_function_),
+//             R/logistic_regression.R:180-209 (sample_beta), src/mvnorm.cpp:9-26, :49-67, :91-129 (rmvnorm_max)
+//
+// Design (B200): one CTA (512 threads) per replicate.
+//   1. PG sweep: one thread per observation computes x_i'beta for both chains (X column-major in L2, coalesced),
+//      then runs the Devroye sampler and the per-observation max coupling with divergent rejection loops.  Draws are
+//      addressed by CELL (sweep, observation) in the replicate's typed Philox streams, so the sweep is parallel and
+//      independent of scheduling (oracle/oracle_pg.hpp states the same contract).
+//   2. Gram build A_c = X' diag(w_c) X + B^-1 for both chains at once: X is streamed once per sweep through shared
+//      memory in 32-row tiles; each thread owns entries (j1 <= j2) and accumulates sequentially over observations
+//      with fma, i.e. in the reference's order (src/logisticregression.cpp:40-48).
+//   3. p x p linear algebra (Cholesky, solves, triangular inverse, Sigma = Linv' Linv, Cholesky of Sigma) at warp
+//      level: warp 0 owns chain 1, warp 1 chain 2 (lane = row(s)); every sum runs in the oracle's order.
+//   4. max-coupled multivariate Normal draw of (beta1, beta2) by warp 0.
+// Everything lives in shared memory; HBM sees X (392 KB, L2-resident) and the per-replicate results.
+#pragma once
+#include <string>
+#include <vector>
+#include "ubm_common.cuh"
+#include "../../include/ubm_pg.h"
+
+namespace ubm {
+
+#define PG_T 512
+#define PG_TILE 32
+#define PG_MAXP 64
+#define PG_PI_D 3.141592653589793238462643383279502884197
+#define PG_TRUNC_D 0.64
+#define PG_BASE (1ull << 40)
+#define PG_CELL_U (1ull << 22)
+#define PG_CELL_NE (1ull << 21)
+
+struct PgDevice {
+  int n, p, ne;
+  const double *X, *invB, *ktk, *b, *cholB;   // device: X n x p col-major; invB p x p; ktk, b [p]; cholB upper p x p
+  size_t offs[5];
+};
+
+// host-side precomputation (logisticregression_precomputation, R/logistic_regression.R:34-50, and chol(B) for rinit)
+inline void pg_chol_lower_host(std::vector<double>& A, int p) {
+  for (int j = 0; j < p; ++j) {
+    double s = A[(size_t)j * p + j];
+    for (int k = 0; k < j; ++k) s = ubm_fma(-A[(size_t)k * p + j], A[(size_t)k * p + j], s);
+    double ljj = sqrt(s);
+    A[(size_t)j * p + j] = ljj;
+    for (int i = j + 1; i < p; ++i) {
+      double t = A[(size_t)j * p + i];
+      for (int k = 0; k < j; ++k) t = ubm_fma(-A[(size_t)k * p + i], A[(size_t)k * p + j], t);
+      A[(size_t)j * p + i] = t / ljj;
+    }
+  }
+  for (int j = 0; j < p; ++j) for (int i = 0; i < j; ++i) A[(size_t)j * p + i] = 0.0;
+}
+inline void pg_pack_host(const ubm_model_pg_logistic* s, PgDevice* M, std::vector<double>* blob) {
+  const int n = s->n, p = s->p;
+  M->n = n; M->p = p; M->ne = p * (p + 1) / 2;
+  std::vector<double> LB(s->B, s->B + (size_t)p * p);
+  pg_chol_lower_host(LB, p);
+  std::vector<double> cholB((size_t)p * p, 0.0), Li((size_t)p * p, 0.0), invB((size_t)p * p, 0.0), ktk(p, 0.0);
+  for (int j = 0; j < p; ++j) for (int i = 0; i <= j; ++i) cholB[(size_t)j * p + i] = LB[(size_t)i * p + j];
+  for (int j = 0; j < p; ++j) {
+    Li[(size_t)j * p + j] = 1.0 / LB[(size_t)j * p + j];
+    for (int i = j + 1; i < p; ++i) {
+      double acc = 0.0;
+      for (int k = j; k < i; ++k) acc = ubm_fma(LB[(size_t)k * p + i], Li[(size_t)j * p + k], acc);
+      Li[(size_t)j * p + i] = -acc / LB[(size_t)i * p + i];
+    }
+  }
+  for (int a = 0; a < p; ++a)
+    for (int c = a; c < p; ++c) {
+      double acc = 0.0;
+      for (int i = c; i < p; ++i) acc = ubm_fma(Li[(size_t)a * p + i], Li[(size_t)c * p + i], acc);
+      invB[(size_t)c * p + a] = acc; invB[(size_t)a * p + c] = acc;
+    }
+  for (int j = 0; j < p; ++j) {
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) acc = ubm_fma(s->X[(size_t)j * n + i], s->Y[i] - 0.5, acc);
+    for (int k = 0; k < p; ++k) acc = ubm_fma(invB[(size_t)k * p + j], s->b[k], acc);
+    ktk[j] = acc;
+  }
+  blob->clear();
+  auto put = [&](const double* src, size_t len) { size_t o = blob->size(); blob->insert(blob->end(), src, src + len); return o; };
+  M->offs[0] = put(s->X, (size_t)n * p);
+  M->offs[1] = put(invB.data(), invB.size());
+  M->offs[2] = put(ktk.data(), ktk.size());
+  M->offs[3] = put(s->b, p);
+  M->offs[4] = put(cholB.data(), cholB.size());
+}
+inline void pg_bind_device(PgDevice* M, const double* dev) {
+  M->X = dev + M->offs[0]; M->invB = dev + M->offs[1]; M->ktk = dev + M->offs[2]; M->b = dev + M->offs[3];
+  M->cholB = dev + M->offs[4];
+}
+
+// ---- per-cell typed draws (random access into the replicate's Philox streams) ----------------------------------
+struct PgCell {
+  uint64_t seed, grep, u0, n0, e0;
+  unsigned ku, kn, ke;
+  ubm_u32x4 bu, bn, be;
+  unsigned long long cbu, cbn, cbe;
+  __device__ PgCell(uint64_t seed_, uint64_t grep_, uint64_t cell)
+      : seed(seed_), grep(grep_), u0(PG_BASE + cell * PG_CELL_U), n0(PG_BASE + cell * PG_CELL_NE),
+        e0(PG_BASE + cell * PG_CELL_NE), ku(0), kn(0), ke(0), cbu(~0ull), cbn(~0ull), cbe(~0ull) {}
+  __device__ double u() {
+    const uint64_t i = u0 + ((uint64_t)(ku++) % PG_CELL_U);
+    if ((i >> 2) != cbu) { cbu = i >> 2; bu = ubm_stream_block(seed, grep, UBM_STREAM_U, cbu); }
+    const unsigned s = (unsigned)i & 3u;
+    return ubm_u01_32((s == 0) ? bu.w[0] : (s == 1) ? bu.w[1] : (s == 2) ? bu.w[2] : bu.w[3]);
+  }
+  __device__ double n() {
+    const uint64_t i = n0 + ((uint64_t)(kn++) % PG_CELL_NE);
+    if ((i >> 1) != cbn) { cbn = i >> 1; bn = ubm_stream_block(seed, grep, UBM_STREAM_N, cbn); }
+    return ubm_qnorm((i & 1) ? ubm_u01_53(bn.w[2], bn.w[3]) : ubm_u01_53(bn.w[0], bn.w[1]));
+  }
+  __device__ double e() {
+    const uint64_t i = e0 + ((uint64_t)(ke++) % PG_CELL_NE);
+    if ((i >> 1) != cbe) { cbe = i >> 1; be = ubm_stream_block(seed, grep, UBM_STREAM_E, cbe); }
+    return -ubm_log((i & 1) ? ubm_u01_53(be.w[2], be.w[3]) : ubm_u01_53(be.w[0], be.w[1]));
+  }
+};
+
+// PolyaGamma::a — src/PolyaGamma.cpp:65-79
+__device__ inline double pg_a(int n, double x) {
+  const double K = (n + 0.5) * PG_PI_D;
+  double y = 0;
+  if (x > PG_TRUNC_D) y = K * ubm_exp(-0.5 * K * K * x);
+  else if (x > 0) {
+    const double expnt = -1.5 * (ubm_log(0.5 * PG_PI_D) + ubm_log(x)) + ubm_log(K) - 2.0 * (n + 0.5) * (n + 0.5) / x;
+    y = ubm_exp(expnt);
+  }
+  return y;
+}
+// PolyaGamma::mass_texpon — src/PolyaGamma.cpp:89-104
+__device__ inline double pg_mass_texpon(double Z) {
+  const double t = PG_TRUNC_D;
+  const double fz = 0.125 * PG_PI_D * PG_PI_D + 0.5 * Z * Z;
+  const double b = sqrt(1.0 / t) * (t * Z - 1);
+  const double a = sqrt(1.0 / t) * (t * Z + 1) * -1.0;
+  const double x0 = ubm_log(fz) + fz * t;
+  const double xb = x0 - Z + ubm_pnorm_log(b);
+  const double xa = x0 + Z + ubm_pnorm_log(a);
+  const double qdivp = 4 / PG_PI_D * (ubm_exp(xb) + ubm_exp(xa));
+  return 1.0 / (1.0 + qdivp);
+}
+// PolyaGamma::rtigauss — src/PolyaGamma.cpp:106-139
+__device__ inline double pg_rtigauss(double Z, PgCell& r) {
+  Z = fabs(Z);
+  const double t = PG_TRUNC_D;
+  double X = t + 1.0;
+  if ((1.0 / 0.64) > Z) {
+    double alpha = 0.0;
+    while (r.u() > alpha) {
+      double E1 = r.e(); double E2 = r.e();
+      while (E1 * E1 > 2 * E2 / t) { E1 = r.e(); E2 = r.e(); }
+      X = 1 + E1 * t;
+      X = t / (X * X);
+      alpha = ubm_exp(-0.5 * Z * Z * X);
+    }
+  } else {
+    const double mu = 1.0 / Z;
+    while (X > t) {
+      double Y = r.n(); Y *= Y;
+      const double half_mu = 0.5 * mu;
+      const double mu_Y = mu * Y;
+      X = mu + half_mu * mu_Y - half_mu * sqrt(4 * mu_Y + mu_Y * mu_Y);
+      if (r.u() > mu / (mu + X)) X = mu * mu / X;
+    }
+  }
+  return X;
+}
+// PolyaGamma::draw_like_devroye — src/PolyaGamma.cpp:175-226
+__device__ inline double pg_draw(double Zin, PgCell& r) {
+  const double Z = fabs(Zin) * 0.5;
+  const double fz = 0.125 * PG_PI_D * PG_PI_D + 0.5 * Z * Z;
+  double X = 0.0, S = 1.0, Y = 0.0;
+  const double mass = pg_mass_texpon(Z);
+  while (true) {
+    if (r.u() < mass) X = PG_TRUNC_D + r.e() / fz;
+    else X = pg_rtigauss(Z, r);
+    S = pg_a(0, X);
+    Y = r.u() * S;
+    int n = 0;
+    bool go = true;
+    while (go) {
+      ++n;
+      if (n % 2 == 1) {
+        S = S - pg_a(n, X);
+        if (Y <= S) return 0.25 * X;
+      } else {
+        S = S + pg_a(n, X);
+        if (Y > S) go = false;
+      }
+    }
+  }
+}
+// logcosh — src/logisticregressioncoupling.cpp:9-17
+__device__ inline double pg_logcosh(double x) {
+  if (x > 0.) return x + ubm_log(1.0 + ubm_exp(-2.0 * x)) - 0.6931472;
+  return -x + ubm_log(1.0 + ubm_exp(2.0 * x)) - 0.6931472;
+}
+
+// ---- warp-level p x p linear algebra on column-major shared-memory matrices (stride p) --------------------------
+// in place: lower triangle of A becomes L (A = L L'); strict upper part is zeroed.  Same sums as the oracle's chol_lower.
+__device__ inline void pg_warp_chol(double* A, int p, int lane) {
+  for (int j = 0; j < p; ++j) {
+    double t[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = lane + 32 * q;
+      t[q] = 0.0;
+      if (i >= j && i < p) {
+        double s = A[j * p + i];
+        for (int k = 0; k < j; ++k) s = ubm_fma(-A[k * p + i], A[k * p + j], s);
+        t[q] = s;
+      }
+    }
+    const double sjj = __shfl_sync(0xffffffffu, (j >= 32) ? t[1] : t[0], j & 31);
+    const double ljj = sqrt(sjj);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = lane + 32 * q;
+      if (i == j) A[j * p + i] = ljj;
+      else if (i > j && i < p) A[j * p + i] = t[q] / ljj;
+      else if (i < j) A[j * p + i] = 0.0;
+    }
+    __syncwarp();
+  }
+}
+// solve L y = rhs (forward), y overwrites `v` (shared); terms taken in increasing column order
+__device__ inline void pg_warp_forward(const double* L, int p, int lane, double* v) {
+  double s[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) { const int i = lane + 32 * q; s[q] = (i < p) ? v[i] : 0.0; }
+  for (int k = 0; k < p; ++k) {
+    const double sk = __shfl_sync(0xffffffffu, (k >= 32) ? s[1] : s[0], k & 31);
+    const double yk = sk / L[k * p + k];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = lane + 32 * q;
+      if (i == k) s[q] = yk;
+      else if (i > k && i < p) s[q] = ubm_fma(-L[k * p + i], yk, s[q]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) { const int i = lane + 32 * q; if (i < p) v[i] = s[q]; }
+  __syncwarp();
+}
+// solve L' x = y (backward), in place in `v`; terms taken from the last row upwards (as the oracle)
+__device__ inline void pg_warp_backward(const double* L, int p, int lane, double* v) {
+  double s[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) { const int i = lane + 32 * q; s[q] = (i < p) ? v[i] : 0.0; }
+  for (int k = p - 1; k >= 0; --k) {
+    const double sk = __shfl_sync(0xffffffffu, (k >= 32) ? s[1] : s[0], k & 31);
+    const double xk = sk / L[k * p + k];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = lane + 32 * q;
+      if (i == k) s[q] = xk;
+      else if (i < k) s[q] = ubm_fma(-L[i * p + k], xk, s[q]);     // L(k, i)
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 2; ++q) { const int i = lane + 32 * q; if (i < p) v[i] = s[q]; }
+  __syncwarp();
+}
+// Li = L^-1 (lower): lane owns columns j = lane, lane + 32 and runs the oracle's forward substitution for each
+__device__ inline void pg_warp_tri_inverse(const double* L, double* Li, int p, int lane) {
+  for (int q = 0; q < 2; ++q) {
+    const int j = lane + 32 * q;
+    if (j >= p) continue;
+    for (int i = 0; i < j; ++i) Li[j * p + i] = 0.0;
+    Li[j * p + j] = 1.0 / L[j * p + j];
+    for (int i = j + 1; i < p; ++i) {
+      double s = 0.0;
+      for (int k = j; k < i; ++k) s = ubm_fma(L[k * p + i], Li[j * p + k], s);
+      Li[j * p + i] = -s / L[i * p + i];
+    }
+  }
+  __syncwarp();
+}
+// S = Li' Li (both triangles), S[a,c] = sum_{i >= c} Li(i,a) Li(i,c), c >= a
+__device__ inline void pg_warp_ltl(const double* Li, double* S, int p, int lane) {
+  const int ne = p * (p + 1) / 2;
+  for (int e = lane; e < ne; e += 32) {
+    // e -> (a, c), a <= c, enumerated a-major
+    int a = 0, rem = e;
+    while (rem >= p - a) { rem -= p - a; ++a; }
+    const int c = a + rem;
+    double s = 0.0;
+    for (int i = c; i < p; ++i) s = ubm_fma(Li[a * p + i], Li[c * p + i], s);
+    S[c * p + a] = s; S[a * p + c] = s;
+  }
+  __syncwarp();
+}
+// fast_dmvnorm_ (src/mvnorm.cpp:49-67) with the lower factor Ls of the covariance; tmp: shared scratch [p]
+__device__ inline double pg_warp_dmvnorm(const double* x, const double* mean, const double* Ls, int p, int lane, double* tmp) {
+  for (int i = lane; i < p; i += 32) tmp[i] = x[i] - mean[i];
+  __syncwarp();
+  pg_warp_forward(Ls, p, lane, tmp);
+  double res = 0.0;
+  if (lane == 0) {
+    double halflogdet = 0.0;
+    for (int j = 0; j < p; ++j) halflogdet = halflogdet + ubm_log(Ls[j * p + j]);
+    const double cst = -(halflogdet) - (p * 0.9189385);
+    double sq = 0.0;
+    for (int i = 0; i < p; ++i) sq = ubm_fma(tmp[i], tmp[i], sq);
+    res = -0.5 * sq + cst;
+  }
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, res, 0);
+}
+
+struct PgShared {   // scalars
+  long long rep;
+  unsigned long long in, iu;   // sequential region of the N / U streams (beta updates)
+  int flag;
+};
+
+// Gram build for one or two chains: A_c[j2, j1] (lower) = invB[j1, j2] + sum_i X(i,j1) X(i,j2) w_c[i]
+template <bool TWO>
+__device__ inline void pg_gram(const PgDevice& M, const double* w1, const double* w2, double* A1, double* A2,
+                               double* xs /* [PG_TILE][p] */, int tid) {
+  const int n = M.n, p = M.p, ne = M.ne;
+  // up to 5 entries per thread (ne <= 2080 for p = 64, 512 threads -> 5)
+  int j1[5], j2[5];
+  double a1[5], a2[5];
+  int cnt = 0;
+  for (int e = tid; e < ne && cnt < 5; e += PG_T) {
+    int a = 0, rem = e;
+    while (rem >= p - a) { rem -= p - a; ++a; }
+    j1[cnt] = a; j2[cnt] = a + rem;
+    a1[cnt] = M.invB[(size_t)(a + rem) * p + a];
+    a2[cnt] = a1[cnt];
+    ++cnt;
+  }
+  for (int i0 = 0; i0 < n; i0 += PG_TILE) {
+    const int rows = (n - i0 < PG_TILE) ? (n - i0) : PG_TILE;
+    __syncthreads();
+    for (int q = tid; q < PG_TILE * p; q += PG_T) {
+      const int ii = q % PG_TILE, j = q / PG_TILE;
+      xs[ii * p + j] = (ii < rows) ? M.X[(size_t)j * n + i0 + ii] : 0.0;
+    }
+    __syncthreads();
+    for (int ii = 0; ii < rows; ++ii) {
+      const double wa = w1[i0 + ii];
+      const double wb = TWO ? w2[i0 + ii] : 0.0;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        if (c < cnt) {
+          const double z = xs[ii * p + j1[c]] * xs[ii * p + j2[c]];
+          a1[c] = ubm_fma(z, wa, a1[c]);
+          if (TWO) a2[c] = ubm_fma(z, wb, a2[c]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    if (c < cnt) {
+      A1[j1[c] * p + j2[c]] = a1[c]; A1[j2[c] * p + j1[c]] = a1[c];
+      if (TWO) { A2[j1[c] * p + j2[c]] = a2[c]; A2[j2[c] * p + j1[c]] = a2[c]; }
+    }
+  }
+  __syncthreads();
+}
+
+// warp-level: from A (shared, p x p) compute L (in place), m (shared vector), Linv (second matrix)
+__device__ inline void pg_warp_m_sigma(const PgDevice& M, double* A, double* Linv, double* m, int lane) {
+  const int p = M.p;
+  pg_warp_chol(A, p, lane);                              // src/logisticregression.cpp:49-50
+  for (int i = lane; i < p; i += 32) m[i] = M.ktk[i];
+  __syncwarp();
+  pg_warp_forward(A, p, lane, m);                        // :51  L y = b
+  pg_warp_backward(A, p, lane, m);                       //      L' x = y
+  pg_warp_tri_inverse(A, Linv, p, lane);                 // :55
+}
+
+__global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const RunParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = M.n, p = M.p;
+  double* sp = reinterpret_cast<double*>(smem_raw);
+  double* w1 = sp; sp += n;
+  double* w2 = sp; sp += n;
+  double* MA1 = sp; sp += p * p;   // chain 1: A -> L -> Sigma -> Ls
+  double* MB1 = sp; sp += p * p;   //          Linv
+  double* MA2 = sp; sp += p * p;
+  double* MB2 = sp; sp += p * p;
+  double* xs = sp; sp += PG_TILE * p;
+  double* beta1 = sp; sp += PG_MAXP;
+  double* beta2 = sp; sp += PG_MAXP;
+  double* m1 = sp; sp += PG_MAXP;
+  double* m2 = sp; sp += PG_MAXP;
+  double* x1 = sp; sp += PG_MAXP;
+  double* x2 = sp; sp += PG_MAXP;
+  double* tmp = sp; sp += PG_MAXP;
+  double* zz = sp; sp += PG_MAXP;
+  double* acc = sp; sp += 4 * PG_MAXP;      // mcmc [2p], corr [2p]
+  PgShared& sh = *reinterpret_cast<PgShared*>(sp);
+  const int dimh = (P.h_kind == UBM_H_BOTH) ? 2 * p : p;
+  const double denom = (double)(P.m - P.k + 1);
+
+  for (;;) {
+    if (tid == 0) {
+      const unsigned long long got = atomicAdd(P.work_counter, 1ull);
+      sh.rep = (got < (unsigned long long)P.nrep) ? (long long)got : -1;
+      sh.in = 0; sh.iu = 0;
+    }
+    __syncthreads();
+    const long long rep = sh.rep;
+    if (rep < 0) break;
+    const uint64_t grep = (uint64_t)(P.rep_offset + rep);
+    // ---- rinit (germancredit.run.R:47-49): beta ~ N(b, B) via fast_rmvnorm (src/mvnorm.cpp:9-26), chain 1 then chain 2
+    if (warp == 0) {
+      for (int c = 0; c < 2; ++c) {
+        for (int j = lane; j < p; j += 32) zz[j] = ubm_philox_n(P.seed, grep, (uint64_t)(c * p + j));
+        __syncwarp();
+        for (int j = lane; j < p; j += 32) {
+          double a = 0.0;
+          for (int i = 0; i <= j; ++i) a = ubm_fma(zz[i], M.cholB[(size_t)j * p + i], a);
+          (c ? beta2 : beta1)[j] = a + M.b[j];
+        }
+        __syncwarp();
+      }
+      if (lane == 0) sh.in = 2ull * p;
+    }
+    for (int e = tid; e < 4 * PG_MAXP; e += PG_T) acc[e] = 0.0;
+    __syncthreads();
+    if (P.mode == MODE_ESTIMATOR && P.k == 0 && tid < p) {
+      const double x = beta1[tid];
+      if (P.h_kind == UBM_H_IDENTITY) acc[tid] = x;
+      else if (P.h_kind == UBM_H_SQUARE) acc[tid] = x * x;
+      else { acc[tid] = x; acc[p + tid] = x * x; }
+    }
+    if (P.mode == MODE_CHAINS && tid < p) {
+      P.samples1[(rep * P.stride) * p + tid] = beta1[tid];
+      P.samples2[(rep * P.stride) * p + tid] = beta2[tid];
+    }
+    long long time = 0, tau = 0;
+    bool met = false;
+    // ---- time loop (generic drivers; CTA-uniform control flow)
+    for (;;) {
+      bool go;
+      if (time < P.lag) go = true;
+      else {
+        const bool capped = (P.max_it > 0 && time >= P.max_it);
+        if (P.mode == MODE_MEETING) go = !met && !capped;
+        else go = (!met || time < (tau > P.m ? tau : P.m)) && !capped;
+      }
+      if (!go) break;
+      time += 1;
+      const bool coupled_step = (time > P.lag) && !met;
+      const unsigned long long sweep = (unsigned long long)time;
+      __syncthreads();
+      // ---- 1. PG sweep (one thread per observation)
+      int all_equal = 1;
+      for (int i = tid; i < n; i += PG_T) {
+        double xb1 = 0.0, xb2 = 0.0;
+        for (int j = 0; j < p; ++j) {                                     // xbeta_ (logisticregressioncoupling.cpp:22-32)
+          const double xv = M.X[(size_t)j * n + i];
+          xb1 = ubm_fma(xv, beta1[j], xb1);
+          if (coupled_step) xb2 = ubm_fma(xv, beta2[j], xb2);
+        }
+        PgCell cell(P.seed, grep, sweep * (unsigned long long)n + (unsigned long long)i);
+        const double z1 = fabs(xb1);
+        const double a1 = pg_draw(z1, cell);
+        w1[i] = a1;
+        if (coupled_step) {                                               // w_max_couplingC (:87-113)
+          const double z2 = fabs(xb2);
+          double a2;
+          const double u1 = cell.u();
+          const double la1 = pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * a1 - (pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * a1);
+          if (ubm_log(u1) <= la1) a2 = a1;
+          else {
+            bool accept = false;
+            a2 = a1;
+            while (!accept) {
+              a2 = pg_draw(z2, cell);
+              const double u2 = cell.u();
+              const double la2 = pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * a2 - (pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * a2);
+              if (ubm_log(u2) > la2) accept = true;
+            }
+          }
+          w2[i] = a2;
+          if (a1 != a2) all_equal = 0;
+        }
+      }
+      all_equal = __syncthreads_and(all_equal);
+      // ---- 2. Gram build(s)
+      if (coupled_step) pg_gram<true>(M, w1, w2, MA1, MA2, xs, tid);
+      else pg_gram<false>(M, w1, w2, MA1, MA2, xs, tid);
+      // ---- 3. m, L, Linv per chain (warp 0: chain 1, warp 1: chain 2)
+      if (warp == 0) pg_warp_m_sigma(M, MA1, MB1, m1, lane);
+      else if (warp == 1 && coupled_step) pg_warp_m_sigma(M, MA2, MB2, m2, lane);
+      __syncthreads();
+      if (!coupled_step) {
+        // single kernel: beta = fast_rmvnorm_chol(1, m, Linv) (germancredit.run.R:27-28): y_j = sum_{i >= j} z_i Linv(i, j)
+        if (warp == 0) {
+          const unsigned long long in0 = sh.in;
+          for (int j = lane; j < p; j += 32) zz[j] = ubm_philox_n(P.seed, grep, in0 + j);
+          __syncwarp();
+          for (int j = lane; j < p; j += 32) {
+            double a = 0.0;
+            for (int i = j; i < p; ++i) a = ubm_fma(zz[i], MB1[j * p + i], a);
+            beta1[j] = a + m1[j];
+          }
+          if (lane == 0) sh.in = in0 + p;
+        }
+      } else {
+        // sample_beta (R/logistic_regression.R:180-209): Sigma_c = Linv_c' Linv_c, then LLT of Sigma_c (src/mvnorm.cpp:12,52)
+        if (warp == 0) { pg_warp_ltl(MB1, MA1, p, lane); pg_warp_chol(MA1, p, lane); }
+        else if (warp == 1) { pg_warp_ltl(MB2, MA2, p, lane); pg_warp_chol(MA2, p, lane); }
+        __syncthreads();
+        if (warp == 0) {                                                  // rmvnorm_max_coupling_ (src/mvnorm.cpp:91-129)
+          unsigned long long in0 = sh.in, iu0 = sh.iu;
+          // x1 = z U1 + m1, U1 = Ls1': y_j = sum_{i <= j} z_i Ls1(j, i)
+          for (int j = lane; j < p; j += 32) zz[j] = ubm_philox_n(P.seed, grep, in0 + j);
+          in0 += p;
+          __syncwarp();
+          for (int j = lane; j < p; j += 32) {
+            double a = 0.0;
+            for (int i = 0; i <= j; ++i) a = ubm_fma(zz[i], MA1[i * p + j], a);
+            x1[j] = a + m1[j];
+          }
+          __syncwarp();
+          const double logu = ubm_log(ubm_philox_u(P.seed, grep, iu0));   // :103-106
+          iu0 += 1;
+          const double d11 = pg_warp_dmvnorm(x1, m1, MA1, p, lane, tmp);
+          const double d12 = pg_warp_dmvnorm(x1, m2, MA2, p, lane, tmp);
+          if (d11 + logu < d12) {                                         // :107
+            for (int j = lane; j < p; j += 32) x2[j] = x1[j];
+          } else {
+            bool accept = false;
+            while (!accept) {                                             // :113-123
+              for (int j = lane; j < p; j += 32) zz[j] = ubm_philox_n(P.seed, grep, in0 + j);
+              in0 += p;
+              __syncwarp();
+              for (int j = lane; j < p; j += 32) {
+                double a = 0.0;
+                for (int i = 0; i <= j; ++i) a = ubm_fma(zz[i], MA2[i * p + j], a);
+                x2[j] = a + m2[j];
+              }
+              __syncwarp();
+              const double lu = ubm_log(ubm_philox_u(P.seed, grep, iu0));
+              iu0 += 1;
+              const double d22 = pg_warp_dmvnorm(x2, m2, MA2, p, lane, tmp);
+              const double d21 = pg_warp_dmvnorm(x2, m1, MA1, p, lane, tmp);
+              if (d22 + lu > d21) accept = true;
+            }
+          }
+          __syncwarp();
+          for (int j = lane; j < p; j += 32) {
+            beta1[j] = x1[j];
+            beta2[j] = all_equal ? x1[j] : x2[j];                         // germancredit.run.R:38-41
+          }
+          if (lane == 0) { sh.in = in0; sh.iu = iu0; }
+        }
+        if (all_equal) { met = true; tau = time; }
+      }
+      __syncthreads();
+      // ---- estimator / trajectories
+      if (tid < p) {
+        const double xa = beta1[tid];
+        const double xb = (time > P.lag && !coupled_step) ? xa : beta2[tid];   // after meeting chain 2 copies chain 1
+        if (P.mode == MODE_ESTIMATOR) {
+          const bool in_window = (time <= P.lag) ? (time >= P.k) : (P.k <= time && time <= P.m);
+          const bool corr_now = (time >= P.k + P.lag) && (coupled_step || time == P.lag);
+          const double wgt = corr_now ? (double)corr_weight(time, P.k, P.m, P.lag) : 0.0;
+          const int nh = (P.h_kind == UBM_H_BOTH) ? 2 : 1;
+          for (int hh = 0; hh < nh; ++hh) {
+            const bool sq = (P.h_kind == UBM_H_SQUARE) || hh == 1;
+            const int e = hh * p + tid;
+            const double h1 = sq ? xa * xa : xa;
+            if (in_window) acc[e] = acc[e] + h1;
+            if (corr_now) { const double h2 = sq ? xb * xb : xb; acc[2 * PG_MAXP + e] = acc[2 * PG_MAXP + e] + wgt * (h1 - h2); }
+          }
+        } else if (P.mode == MODE_CHAINS) {
+          P.samples1[(rep * P.stride + time) * p + tid] = xa;
+          if (time > P.lag) P.samples2[(rep * P.stride + (time - P.lag)) * p + tid] = xb;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- results
+    if (tid == 0) {
+      double cost = dinf();
+      if (met) {
+        if (P.mode == MODE_MEETING) cost = (double)(P.lag + 2 * (tau - P.lag));
+        else cost = (double)(P.lag + 2 * (tau - P.lag) + ((time - tau) > 0 ? (time - tau) : 0));
+      }
+      if (P.tau) P.tau[rep] = met ? (double)tau : dinf();
+      if (P.cost) P.cost[rep] = cost;
+      if (P.iter) P.iter[rep] = time;
+    }
+    if (P.mode == MODE_ESTIMATOR && tid < dimh) {
+      const double mc = acc[tid], co = acc[2 * PG_MAXP + tid];
+      const double ue = mc + co;
+      P.uest[rep * dimh + tid] = ue / denom;
+      if (P.mcmc) P.mcmc[rep * dimh + tid] = mc / denom;
+      if (P.corr) P.corr[rep * dimh + tid] = co / denom;
+    }
+    __syncthreads();
+  }
+}
+
+inline size_t pg_smem_bytes(int n, int p) {
+  return (size_t)(2 * n + 4 * p * p + PG_TILE * p + 8 * PG_MAXP + 4 * PG_MAXP) * sizeof(double) + sizeof(PgShared) + 16;
+}
+
+inline int pg_launch(const PgDevice& M, const RunParams& P, bool tape, int nsm, cudaStream_t st, int64_t* launches,
+                     std::string* err) {
+  if (tape) { *err = "pg logistic: replay tapes are not available for this model (draws are addressed by cell)"; return UBM_ERR_UNSUPPORTED; }
+  if (P.nbreaks >= 2) { *err = "pg logistic: histogram bins are not available for this model yet"; return UBM_ERR_UNSUPPORTED; }
+  const size_t smem = pg_smem_bytes(M.n, M.p);
+  if (smem > 227 * 1024) { *err = "pg logistic: n / p too large for shared memory"; return UBM_ERR_UNSUPPORTED; }
+  cudaError_t e = cudaFuncSetAttribute(pg_driver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { *err = std::string("pg logistic: smem attribute: ") + cudaGetErrorString(e); return UBM_ERR_CUDA; }
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_driver_kernel, PG_T, smem);
+  if (e != cudaSuccess || per_sm < 1) { *err = "pg logistic: occupancy query failed"; return UBM_ERR_CUDA; }
+  const int grid = (int)std::min<int64_t>((int64_t)nsm * per_sm, P.nrep);
+  pg_driver_kernel<<<grid, PG_T, smem, st>>>(M, P);
+  *launches += 1;
+  return UBM_OK;
+}
+
+}  // namespace ubm

@@ -146,3 +146,23 @@ class IsingPT(ModelSpec):
 
     def struct(self):
         return A.ubm_model_ising_pt(32, self.dim, A.dptr(self.betas), self.proba_swapmove, 0, 0)
+
+
+class PgLogistic(ModelSpec):
+    """C3 — Polya-Gamma Gibbs sampler for Bayesian logistic regression, coupled as in
+    inst/reproducegermancredit/germancredit.run.R:23-49.  Prior beta ~ N(b, B)."""
+    kind = A.UBM_MODEL_PG_LOGISTIC
+
+    def __init__(self, Y, X, b, B):
+        X = np.asarray(X, dtype=np.float64)
+        self.n, self.p = X.shape
+        if not (1 <= self.p <= 64 and 1 <= self.n <= 4096):
+            raise ValueError("PG logistic: n <= 4096, p <= 64")
+        self.dim = self.p
+        self.X = _colmajor(X)
+        self.Y = _f64(Y)
+        self.b = _f64(b).reshape(-1)
+        self.B = _colmajor(B)
+
+    def struct(self):
+        return A.ubm_model_pg_logistic(self.n, self.p, A.dptr(self.X), A.dptr(self.Y), A.dptr(self.b), A.dptr(self.B))
