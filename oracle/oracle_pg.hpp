@@ -9,8 +9,8 @@
 //
 // Draw addressing.  The reference consumes one sequential stream, observation after observation; a device cannot
 // (the n Polya-Gamma draws of a step run in parallel).  The engine therefore addresses the PG draws of a step by
-// CELL: cell c = (sweep * n + observation) owns uniforms 2^40 + [c 2^22, (c+1) 2^22), normals and exponentials
-// 2^40 + [c 2^21, (c+1) 2^21) (wrapping inside the cell, never an error) of the replicate's typed streams; `sweep` = index of the kernel call (= time).
+// CELL: cell c = (sweep * n + observation) owns its own blocks of the replicate's typed streams (struct CellDraws
+// below gives the exact address); `sweep` = index of the kernel call (= time).
 // The multivariate-normal draws of the beta update (and rinit) use the ordinary sequential region from index 0.  Same distribution as the reference's order; this is the contract the CUDA kernel matches.
 //
 // Arithmetic pinned where the reference leaves it to the compiler / Eigen / BLAS: a + b * c is one fma;
@@ -26,22 +26,46 @@ static const double PG_PI = 3.141592653589793238462643383279502884197;   // src/
 static const double PG_TRUNC = 0.64;                                      // :37
 static const double PG_TRUNC_RECIP = 1.0 / 0.64;                          // :38
 
-#define ORC_PG_CELL_U (1ull << 22)
-#define ORC_PG_CELL_NE (1ull << 21)
-#define ORC_PG_BASE (1ull << 40)   // PG cells live far above the sequential region used by the beta update
 
-// typed cell view over the replicate's streams: sequential within the cell, absolute addressing above
-// ORC_PG_BASE so that it never meets the replicate's ordinary sequential region (the beta-update draws)
+// Cell draws.  A cell = (sweep, observation); it is divided into ATTEMPTS of 128 uniforms / 64 normals / 64
+// exponentials (32 Philox blocks of each typed stream): attempt 0 holds the first PG draw and its coupling test,
+// attempt a >= 1 the a-th candidate of the max-coupling rejection loop.  Attempts are independent of one another,
+// which lets the device evaluate 32 of them at once and keep the first accepted one — the same answer as this
+// sequential loop.  Block address inside the replicate's typed stream:
+//     blk = 2^59 | (cell mod 2^26) << 33 | (attempt mod 2^28) << 5 | local,   local in [0, 32)
+// (the ordinary sequential region of the streams, used by the beta update, lives below 2^59), and attempts beyond
+// 2^28 move to replicate index rep + (attempt >> 28) << 44, so the loop never revisits a draw.
+// Draws inside an attempt are sequential and wrap inside the attempt's 32 blocks (never an error).
 struct CellDraws {
-  Draws* D;
-  uint64_t u0, n0, e0, ku = 0, kn = 0, ke = 0;
-  bool overflow = false;   // never set: a cell that runs past its budget wraps around inside the cell
-  CellDraws(Draws* d, uint64_t cell)
-      : D(d), u0(ORC_PG_BASE + cell * ORC_PG_CELL_U), n0(ORC_PG_BASE + cell * ORC_PG_CELL_NE),
-        e0(ORC_PG_BASE + cell * ORC_PG_CELL_NE) {}
-  double u() { uint64_t sv = D->iu; D->iu = u0 + (ku++ % ORC_PG_CELL_U); double v = D->u(); D->iu = sv; return v; }
-  double n() { uint64_t sv = D->in; D->in = n0 + (kn++ % ORC_PG_CELL_NE); double v = D->n(); D->in = sv; return v; }
-  double e() { uint64_t sv = D->ie; D->ie = e0 + (ke++ % ORC_PG_CELL_NE); double v = D->e(); D->ie = sv; return v; }
+  uint64_t seed, rep, cell, base = 0, rep_eff = 0;
+  uint32_t ku = 0, kn = 0, ke = 0;
+  uint64_t cbu = ~0ull, cbn = ~0ull, cbe = ~0ull, cru = ~0ull, crn = ~0ull, cre = ~0ull;
+  ubm_u32x4 bu{}, bn{}, be{};
+  bool overflow = false;   // never set
+  CellDraws(Draws* d, uint64_t cell_) : seed(d->seed), rep(d->rep), cell(cell_) { set_attempt(0); }
+  void set_attempt(uint64_t a) {
+    base = (1ull << 59) | ((cell & ((1ull << 26) - 1)) << 33) | ((a & ((1ull << 28) - 1)) << 5);
+    rep_eff = rep + ((a >> 28) << 44);
+    ku = kn = ke = 0;
+  }
+  double u() {
+    const uint32_t k = (ku++) & 127u;
+    const uint64_t blk = base | (k >> 2);
+    if (blk != cbu || rep_eff != cru) { cbu = blk; cru = rep_eff; bu = ubm_stream_block(seed, rep_eff, UBM_STREAM_U, blk); }
+    return ubm_u01_32(bu.w[k & 3]);
+  }
+  double n() {
+    const uint32_t k = (kn++) & 63u;
+    const uint64_t blk = base | (k >> 1);
+    if (blk != cbn || rep_eff != crn) { cbn = blk; crn = rep_eff; bn = ubm_stream_block(seed, rep_eff, UBM_STREAM_N, blk); }
+    return ubm_qnorm(ubm_block_u53(bn, k & 1));
+  }
+  double e() {
+    const uint32_t k = (ke++) & 63u;
+    const uint64_t blk = base | (k >> 1);
+    if (blk != cbe || rep_eff != cre) { cbe = blk; cre = rep_eff; be = ubm_stream_block(seed, rep_eff, UBM_STREAM_E, blk); }
+    return -ubm_log(ubm_block_u53(be, k & 1));
+  }
 };
 
 // PolyaGamma::a — src/PolyaGamma.cpp:65-79
@@ -319,7 +343,9 @@ struct PgLogisticModel {
       else {
         bool accept = false;
         a2 = a1;
-        while (!accept && !c.overflow) {
+        uint64_t attempt = 0;
+        while (!accept) {
+          c.set_attempt(++attempt);
           a2 = pg_draw(z2, c);
           const double u2 = c.u();
           const double logaccept2 = pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * a2 - (pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * a2);

@@ -32,9 +32,6 @@ namespace ubm {
 #define PG_MAXP 64
 #define PG_PI_D 3.141592653589793238462643383279502884197
 #define PG_TRUNC_D 0.64
-#define PG_BASE (1ull << 40)
-#define PG_CELL_U (1ull << 22)
-#define PG_CELL_NE (1ull << 21)
 
 struct PgDevice {
   int n, p, ne;
@@ -98,29 +95,36 @@ inline void pg_bind_device(PgDevice* M, const double* dev) {
 }
 
 // ---- per-cell typed draws (random access into the replicate's Philox streams) ----------------------------------
-struct PgCell {
-  uint64_t seed, grep, u0, n0, e0;
+struct PgCell {   // a cell = (sweep, observation); an attempt = 32 blocks of each typed stream (oracle/oracle_pg.hpp: CellDraws)
+  uint64_t seed, rep, cell, base, rep_eff;
   unsigned ku, kn, ke;
   ubm_u32x4 bu, bn, be;
-  unsigned long long cbu, cbn, cbe;
-  __device__ PgCell(uint64_t seed_, uint64_t grep_, uint64_t cell)
-      : seed(seed_), grep(grep_), u0(PG_BASE + cell * PG_CELL_U), n0(PG_BASE + cell * PG_CELL_NE),
-        e0(PG_BASE + cell * PG_CELL_NE), ku(0), kn(0), ke(0), cbu(~0ull), cbn(~0ull), cbe(~0ull) {}
+  unsigned long long cbu, cbn, cbe, cru, crn, cre;
+  __device__ PgCell(uint64_t seed_, uint64_t grep_, uint64_t cell_)
+      : seed(seed_), rep(grep_), cell(cell_), cbu(~0ull), cbn(~0ull), cbe(~0ull), cru(~0ull), crn(~0ull), cre(~0ull) { set_attempt(0); }
+  __device__ void set_attempt(uint64_t a) {
+    base = (1ull << 59) | ((cell & ((1ull << 26) - 1)) << 33) | ((a & ((1ull << 28) - 1)) << 5);
+    rep_eff = rep + ((a >> 28) << 44);
+    ku = kn = ke = 0;
+  }
   __device__ double u() {
-    const uint64_t i = u0 + ((uint64_t)(ku++) % PG_CELL_U);
-    if ((i >> 2) != cbu) { cbu = i >> 2; bu = ubm_stream_block(seed, grep, UBM_STREAM_U, cbu); }
-    const unsigned s = (unsigned)i & 3u;
+    const unsigned k = (ku++) & 127u;
+    const uint64_t blk = base | (k >> 2);
+    if (blk != cbu || rep_eff != cru) { cbu = blk; cru = rep_eff; bu = ubm_stream_block(seed, rep_eff, UBM_STREAM_U, blk); }
+    const unsigned s = k & 3u;
     return ubm_u01_32((s == 0) ? bu.w[0] : (s == 1) ? bu.w[1] : (s == 2) ? bu.w[2] : bu.w[3]);
   }
   __device__ double n() {
-    const uint64_t i = n0 + ((uint64_t)(kn++) % PG_CELL_NE);
-    if ((i >> 1) != cbn) { cbn = i >> 1; bn = ubm_stream_block(seed, grep, UBM_STREAM_N, cbn); }
-    return ubm_qnorm((i & 1) ? ubm_u01_53(bn.w[2], bn.w[3]) : ubm_u01_53(bn.w[0], bn.w[1]));
+    const unsigned k = (kn++) & 63u;
+    const uint64_t blk = base | (k >> 1);
+    if (blk != cbn || rep_eff != crn) { cbn = blk; crn = rep_eff; bn = ubm_stream_block(seed, rep_eff, UBM_STREAM_N, blk); }
+    return ubm_qnorm((k & 1) ? ubm_u01_53(bn.w[2], bn.w[3]) : ubm_u01_53(bn.w[0], bn.w[1]));
   }
   __device__ double e() {
-    const uint64_t i = e0 + ((uint64_t)(ke++) % PG_CELL_NE);
-    if ((i >> 1) != cbe) { cbe = i >> 1; be = ubm_stream_block(seed, grep, UBM_STREAM_E, cbe); }
-    return -ubm_log((i & 1) ? ubm_u01_53(be.w[2], be.w[3]) : ubm_u01_53(be.w[0], be.w[1]));
+    const unsigned k = (ke++) & 63u;
+    const uint64_t blk = base | (k >> 1);
+    if (blk != cbe || rep_eff != cre) { cbe = blk; cre = rep_eff; be = ubm_stream_block(seed, rep_eff, UBM_STREAM_E, blk); }
+    return -ubm_log((k & 1) ? ubm_u01_53(be.w[2], be.w[3]) : ubm_u01_53(be.w[0], be.w[1]));
   }
 };
 
@@ -328,17 +332,20 @@ template <bool TWO>
 __device__ inline void pg_gram(const PgDevice& M, const double* w1, const double* w2, double* A1, double* A2,
                                double* xs /* [PG_TILE][p] */, int tid) {
   const int n = M.n, p = M.p, ne = M.ne;
-  // up to 5 entries per thread (ne <= 2080 for p = 64, 512 threads -> 5)
+  // up to 5 entries per thread (ne <= 2080 for p = 64, 512 threads -> 5); slots are indexed statically so that
+  // they stay in registers
   int j1[5], j2[5];
   double a1[5], a2[5];
-  int cnt = 0;
-  for (int e = tid; e < ne && cnt < 5; e += PG_T) {
-    int a = 0, rem = e;
+  bool on[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    const int e = tid + c * PG_T;
+    on[c] = e < ne;
+    int a = 0, rem = on[c] ? e : 0;
     while (rem >= p - a) { rem -= p - a; ++a; }
-    j1[cnt] = a; j2[cnt] = a + rem;
-    a1[cnt] = M.invB[(size_t)(a + rem) * p + a];
-    a2[cnt] = a1[cnt];
-    ++cnt;
+    j1[c] = a; j2[c] = a + rem;
+    a1[c] = M.invB[(size_t)(a + rem) * p + a];
+    a2[c] = a1[c];
   }
   for (int i0 = 0; i0 < n; i0 += PG_TILE) {
     const int rows = (n - i0 < PG_TILE) ? (n - i0) : PG_TILE;
@@ -353,7 +360,7 @@ __device__ inline void pg_gram(const PgDevice& M, const double* w1, const double
       const double wb = TWO ? w2[i0 + ii] : 0.0;
 #pragma unroll
       for (int c = 0; c < 5; ++c) {
-        if (c < cnt) {
+        if (on[c]) {
           const double z = xs[ii * p + j1[c]] * xs[ii * p + j2[c]];
           a1[c] = ubm_fma(z, wa, a1[c]);
           if (TWO) a2[c] = ubm_fma(z, wb, a2[c]);
@@ -363,7 +370,7 @@ __device__ inline void pg_gram(const PgDevice& M, const double* w1, const double
   }
 #pragma unroll
   for (int c = 0; c < 5; ++c) {
-    if (c < cnt) {
+    if (on[c]) {
       A1[j1[c] * p + j2[c]] = a1[c]; A1[j2[c] * p + j1[c]] = a1[c];
       if (TWO) { A2[j1[c] * p + j2[c]] = a2[c]; A2[j2[c] * p + j1[c]] = a2[c]; }
     }
@@ -403,6 +410,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
   double* tmp = sp; sp += PG_MAXP;
   double* zz = sp; sp += PG_MAXP;
   double* acc = sp; sp += 4 * PG_MAXP;      // mcmc [2p], corr [2p]
+  int* plist = reinterpret_cast<int*>(sp); sp += (n + 1) / 2;   // observations whose first coupling test failed
   PgShared& sh = *reinterpret_cast<PgShared*>(sp);
   const int dimh = (P.h_kind == UBM_H_BOTH) ? 2 * p : p;
   const double denom = (double)(P.m - P.k + 1);
@@ -445,6 +453,12 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
     }
     long long time = 0, tau = 0;
     bool met = false;
+#ifdef UBM_PG_TIMING
+    long long tacc[4] = {0, 0, 0, 0}, tprev = clock64(), tsteps = 0, tcoupled = 0;
+#define PGMARK(i) do { long long now_ = clock64(); tacc[i] += now_ - tprev; tprev = now_; } while (0)
+#else
+#define PGMARK(i) do { } while (0)
+#endif
     // ---- time loop (generic drivers; CTA-uniform control flow)
     for (;;) {
       bool go;
@@ -459,8 +473,14 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
       const bool coupled_step = (time > P.lag) && !met;
       const unsigned long long sweep = (unsigned long long)time;
       __syncthreads();
-      // ---- 1. PG sweep (one thread per observation)
+#ifdef UBM_PG_TIMING
+      tprev = clock64(); tsteps++; if (coupled_step) tcoupled++;
+#endif
+      // ---- 1. PG sweep.  Phase 1: one thread per observation draws w1 (attempt 0 of the cell) and runs the first
+      // test of the max coupling (src/logisticregressioncoupling.cpp:87-98); failures go to a work list.
       int all_equal = 1;
+      if (tid == 0) sh.flag = 0;
+      __syncthreads();
       for (int i = tid; i < n; i += PG_T) {
         double xb1 = 0.0, xb2 = 0.0;
         for (int j = 0; j < p; ++j) {                                     // xbeta_ (logisticregressioncoupling.cpp:22-32)
@@ -472,30 +492,49 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
         const double z1 = fabs(xb1);
         const double a1 = pg_draw(z1, cell);
         w1[i] = a1;
-        if (coupled_step) {                                               // w_max_couplingC (:87-113)
+        if (coupled_step) {
           const double z2 = fabs(xb2);
-          double a2;
           const double u1 = cell.u();
           const double la1 = pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * a1 - (pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * a1);
-          if (ubm_log(u1) <= la1) a2 = a1;
-          else {
-            bool accept = false;
-            a2 = a1;
-            while (!accept) {
-              a2 = pg_draw(z2, cell);
-              const double u2 = cell.u();
-              const double la2 = pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * a2 - (pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * a2);
-              if (ubm_log(u2) > la2) accept = true;
+          if (ubm_log(u1) <= la1) w2[i] = a1;
+          else { all_equal = 0; plist[atomicAdd(&sh.flag, 1)] = i; }
+        }
+      }
+      __syncthreads();
+      // Phase 2: the rejection loop of the max coupling (:99-110), one warp per listed observation, 32 attempts at a
+      // time (attempt a draws from its own region of the cell, so the first accepted attempt is the sequential answer)
+      if (coupled_step) {
+        const int nlist = sh.flag;
+        for (int q = warp; q < nlist; q += PG_T / 32) {
+          const int i = plist[q];
+          double xb1 = 0.0, xb2 = 0.0;
+          for (int j = 0; j < p; ++j) {
+            const double xv = M.X[(size_t)j * n + i];
+            xb1 = ubm_fma(xv, beta1[j], xb1);
+            xb2 = ubm_fma(xv, beta2[j], xb2);
+          }
+          const double z1 = fabs(xb1), z2 = fabs(xb2);
+          PgCell cell(P.seed, grep, sweep * (unsigned long long)n + (unsigned long long)i);
+          for (unsigned long long base = 1;; base += 32) {
+            cell.set_attempt(base + lane);
+            const double a2 = pg_draw(z2, cell);
+            const double u2 = cell.u();
+            const double la2 = pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * a2 - (pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * a2);
+            const unsigned okm = __ballot_sync(0xffffffffu, ubm_log(u2) > la2);
+            if (okm) {
+              const double win = __shfl_sync(0xffffffffu, a2, __ffs(okm) - 1);
+              if (lane == 0) w2[i] = win;
+              break;
             }
           }
-          w2[i] = a2;
-          if (a1 != a2) all_equal = 0;
         }
       }
       all_equal = __syncthreads_and(all_equal);
+      PGMARK(0);
       // ---- 2. Gram build(s)
       if (coupled_step) pg_gram<true>(M, w1, w2, MA1, MA2, xs, tid);
       else pg_gram<false>(M, w1, w2, MA1, MA2, xs, tid);
+      PGMARK(1);
       // ---- 3. m, L, Linv per chain (warp 0: chain 1, warp 1: chain 2)
       if (warp == 0) pg_warp_m_sigma(M, MA1, MB1, m1, lane);
       else if (warp == 1 && coupled_step) pg_warp_m_sigma(M, MA2, MB2, m2, lane);
@@ -565,6 +604,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
         if (all_equal) { met = true; tau = time; }
       }
       __syncthreads();
+      PGMARK(2);
       // ---- estimator / trajectories
       if (tid < p) {
         const double xa = beta1[tid];
@@ -588,6 +628,11 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
       }
     }
     __syncthreads();
+#ifdef UBM_PG_TIMING
+    if (tid == 0 && blockIdx.x == 0)
+      printf("pg timing (cycles/step, block 0): steps %lld coupled %lld pg-sweep %.0f gram %.0f linalg+sample %.0f\n", tsteps,
+             tcoupled, (double)tacc[0] / tsteps, (double)tacc[1] / tsteps, (double)tacc[2] / tsteps);
+#endif
     // ---- results
     if (tid == 0) {
       double cost = dinf();
@@ -611,7 +656,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
 }
 
 inline size_t pg_smem_bytes(int n, int p) {
-  return (size_t)(2 * n + 4 * p * p + PG_TILE * p + 8 * PG_MAXP + 4 * PG_MAXP) * sizeof(double) + sizeof(PgShared) + 16;
+  return (size_t)(2 * n + 4 * p * p + PG_TILE * p + 8 * PG_MAXP + 4 * PG_MAXP + (n + 1) / 2) * sizeof(double) + sizeof(PgShared) + 16;
 }
 
 inline int pg_launch(const PgDevice& M, const RunParams& P, bool tape, int nsm, cudaStream_t st, int64_t* launches,
