@@ -90,6 +90,21 @@ def workload(name):
             coupled = 2.0 * (2.0 * n * p_ + gram + 2.0 * p_ ** 3 + 300.0 * n)
             return single * (sum_iter - (sum_tau - S[0])) + coupled * (sum_tau - S[0])
         return mdl, kw, 1184, desc, flops, "fp64"
+    if name == "c5":
+        mdl = cases.c5_model()
+        kw = dict(h_kind=A.UBM_H_IDENTITY, bins=None, k=7500, m=15000, lag=1)
+        desc = ("C5: variable selection n=500, p=1000, SNR 1, g=p^3, s0=100, kappa=2, flip/swap MH with coupled index "
+                "sampling, lag=1, CI-sized horizon k=7500, m=15000 (clusterscript.kappas.R uses k=75000, m=150000), "
+                "h = gamma (1000 inclusion indicators)")
+
+        def flops(S, nrep):
+            # per proposal ~ 4 s^2 flop (gather + factor + solve of the s x s block, s ~ 15 here we use the
+            # full Cholesky: s^3/3 + 2 s^2), 1 proposal per single step, 2 per coupled step
+            n_all, sum_tau, sum_iter = S[0] + S[1], S[2], S[5]
+            s = 15.0
+            per = s ** 3 / 3.0 + 2.0 * s * s
+            return per * (sum_iter + (sum_tau - S[0]))
+        return mdl, kw, 2960, desc, flops, "fp64"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -286,7 +301,7 @@ def main():
     roofline = {"bound": bound, "achieved": achieved, "peak": peak, "unit": "TFLOP/s" if bound == "fp64" else "Top/s",
                 "frac": achieved / peak, "traffic": None,
                 "kernel": {"c1": "mix_driver_kernel", "c2": "mvn_driver_kernel", "c3": "pg_driver_kernel",
-                           "c4": "ising_driver_kernel"}[args.workload],
+                           "c4": "ising_driver_kernel", "c5": "varsel_driver_kernel"}[args.workload],
                 "kernel_share_of_step": kernel_ms / dev_ms,
                 "peak_source": "measured live by ubm_measure_peaks (independent DFMA / IMAD chains, 2 ops each); "
                                "MEASURED_PEAKS.json holds no FP64 / INT32 figure; HBM is not the bound (state stays on "

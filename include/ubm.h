@@ -135,6 +135,22 @@ typedef struct {
   const double* B;        /* p x p prior covariance (column-major, symmetric positive definite) */
 } ubm_model_pg_logistic;
 
+/* C5: Bayesian variable selection, g-prior spike-and-slab, flip / swap Metropolis-Hastings on gamma in {0,1}^p,
+ * coupled as in R/variableselection.R:57-148 (shared flip coordinate, max-coupled swap indices
+ * R/coupled_pairs01.R:3-40, shared accept uniform).  Marginal likelihood: src/vs_mlikelihood.cpp:5-28, evaluated in
+ * FP64 from G = X'X and X'Y (formed once on the device) with a Cholesky factorisation of G[gamma, gamma].
+ * Prior: -kappa |gamma| log p, -Inf when |gamma| > s0 (R/variableselection.R:8-11).  The chain state exposed to
+ * h / trajectories is gamma as 0/1 doubles (dim = p): H estimates the posterior inclusion probabilities. */
+typedef struct {
+  int32_t n, p;                 /* p <= 1024 */
+  const double* X;              /* n x p column-major */
+  const double* Y;              /* [n] */
+  double g, kappa;
+  int32_t s0;                   /* <= 128 */
+  int32_t reserved;
+  double proportion_singleflip;
+} ubm_model_varsel;
+
 /* ---------------------------------------------------------------------------------------------
  * test functions h and histogram bins
  * ------------------------------------------------------------------------------------------- */

@@ -59,3 +59,22 @@ def c3_model(n=1000, p=49, seed=SEED):
     """germancredit.run.R:18-20: prior b = 0, B = 10 I."""
     Y, X = c3_data(n, p, seed)
     return R.PgLogistic(Y, X, np.zeros(p), 10.0 * np.eye(p))
+
+
+def c5_data(n=500, p=1000, snr=1.0, seed=SEED):
+    """inst/reproducevarselection/varselection.generatedata.run.R:7-18 (independent design, scaled X and Y)."""
+    rng = np.random.default_rng(seed)
+    beta = np.zeros(p)
+    sig = np.array([2, -3, 2, 2, -3, 3, -2, 3, -2, 3], dtype=np.float64)
+    beta[:min(10, p)] = snr * np.sqrt(np.log(p) / n) * sig[:min(10, p)]
+    X = rng.standard_normal((n, p))
+    X = (X - X.mean(0)) / X.std(0, ddof=1)
+    Y = X @ beta + rng.standard_normal(n)
+    Y = (Y - Y.mean()) / Y.std(ddof=1)
+    return Y, X
+
+
+def c5_model(n=500, p=1000, kappa=2.0, s0=100, snr=1.0, seed=SEED):
+    """varselection.differentp.R:22-26,40: g = p^3, s0 = 100, proportion_singleflip = 0.5."""
+    Y, X = c5_data(n, p, snr, seed)
+    return R.VariableSelection(Y, X, float(p) ** 3, kappa, min(s0, p), 0.5)

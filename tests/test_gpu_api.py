@@ -1,0 +1,57 @@
+"""GPU: the README workflow of the reference (README.Rmd:66-121) written against the mirrored R API
+(unbiasedmcmc_b200/api.py), with the README's own numbers as statistical anchors (README.md:146,171)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_readme_workflow():
+    from unbiasedmcmc_b200 import api
+    target = api.NormalMixtureTarget([0.5, 0.5], [-4.0, 4.0], [1.0, 1.0])        # README.Rmd:69-72
+    kernels = api.get_mh_kernels(target, 4)                                        # :74
+    single_kernel, coupled_kernel = kernels["single_kernel"], kernels["coupled_kernel"]
+    rinit = api.normal_rinit(3, 2)                                                 # :80-84
+    nrep = 500
+    mt = api.sample_meetingtime(single_kernel, coupled_kernel, rinit, nrep=nrep, seed=1)["meetingtime"]    # :89-92
+    assert mt.shape == (nrep,) and np.all(mt >= 2) and np.all(np.isfinite(mt))
+    chains = api.sample_coupled_chains(single_kernel, coupled_kernel, rinit, m=2000, lag=500, nrep=nrep, seed=1)  # :97-99
+    assert len(chains) == nrep
+    c0 = chains[0]
+    assert c0["samples1"].shape[0] == c0["iteration"] + 1 and c0["samples2"].shape[0] == c0["iteration"] - 500 + 1
+    cost = np.array([c["cost"] for c in chains])
+    assert abs(cost.mean() - 2072.788) < 5 * cost.std() / np.sqrt(nrep) + 6       # README.md:146
+    hist1 = api.histogram_c_chains(chains, 1, k=500, m=2000, nclass=100)           # README.Rmd:102
+    assert set(hist1) == {"mids", "breaks", "proportions", "sd", "width"}
+    assert abs(hist1["proportions"].sum() - 1.0) < 0.05
+    est = api.H_bar(chains, h="identity", k=500, m=2000)[:, 0]                     # README.Rmd:119
+    half = 1.96 * est.std(ddof=1) / np.sqrt(nrep)
+    assert abs(est.mean()) < 2 * half and 0.10 < half < 0.20                       # README.md:171: 0.0055 +/- 0.1459
+    # on-the-fly estimator: same numbers without storing the chains
+    u = api.sample_unbiasedestimator(single_kernel, coupled_kernel, rinit, k=500, m=2000, lag=500, nrep=nrep, seed=1)
+    np.testing.assert_allclose(u["uestimator"][:, 0], est, rtol=1e-11, atol=1e-11)
+    assert np.array_equal(u["meetingtime"], np.array([c["meetingtime"] for c in chains]))
+    # argument guards print and return None, as in R/unbiasedestimator.R:44-51
+    assert api.sample_unbiasedestimator(single_kernel, coupled_kernel, rinit, k=5, m=3) is None
+    # a plain closure cannot run on the device
+    with pytest.raises(TypeError):
+        api.get_mh_kernels(lambda x: -0.5 * x * x, 1.0)
+
+
+def test_registry_models_through_the_api():
+    from tests import cases
+    from unbiasedmcmc_b200 import api
+    ks = api.ising_pt_kernels(np.linspace(0.3, 0.4, 4), 0.05)
+    r = api.sample_unbiasedestimator(ks["single_kernel"], ks["coupled_kernel"], ks["rinit"], k=10, m=60, nrep=8, seed=3)
+    assert r["uestimator"].shape == (8, 4) and np.isfinite(r["meetingtime"]).all()
+    Y, X = cases.c3_data(150, 6, seed=2)
+    ks = api.logisticregression_kernels(Y, X, np.zeros(6), 10 * np.eye(6))
+    r = api.sample_meetingtime(ks["single_kernel"], ks["coupled_kernel"], ks["rinit"], nrep=16, seed=2)
+    assert np.isfinite(r["meetingtime"]).all()
+    Y, X = cases.c5_data(100, 30, snr=2.0)
+    ks = api.get_variableselection(Y, X, 30.0 ** 3, 0.1, 10, 0.5)
+    r = api.sample_unbiasedestimator(ks["single_kernel"], ks["coupled_kernel"], ks["rinit"], k=300, m=1500, nrep=64, seed=1)
+    incl = r["uestimator"].mean(0)       # unbiased but noisy with 64 replicates: compare groups, not coordinates
+    assert r["uestimator"].shape == (64, 30) and incl[:10].mean() > 0.8 and abs(incl[10:].mean()) < 0.2
+    c = api.rnorm_max_coupling(0.0, 1.0, 1.0, 1.0, n=1000, seed=2)
+    assert c["xy"].shape == (1000, 2) and c["identical"].dtype == bool

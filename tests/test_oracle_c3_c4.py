@@ -49,3 +49,19 @@ def test_c4_natural_statistic_and_meeting(oracle):
     # estimator == H_bar of the stored natural statistics
     ch = oracle.sample_coupled_chains(mdl, R.Draws(seed=2), m=200, lag=1, stride=4000, nrep=8)
     np.testing.assert_allclose(oracle.h_bar(ch, A.UBM_H_IDENTITY, k=50, m=200), u[:8], rtol=1e-12)
+
+
+def test_c5_marginal_likelihood_and_inclusion_probabilities(oracle):
+    """inst/check/check_vs_mlikelihood.R:79-95 (agreement of marginal-likelihood formulas) and a long-chain check."""
+    import ctypes as C
+    mdl = cases.c5_model(100, 30, kappa=0.1, s0=10, snr=2.0)
+    e = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=1), k=300, m=1500, lag=1, nrep=600, nthreads=8)
+    assert np.isfinite(e["meetingtime"]).all()
+    u = e["uestimator"]
+    ch = oracle.sample_coupled_chains(mdl, R.Draws(seed=7), m=100000, lag=1, stride=100100, nrep=1)
+    s = ch["samples1"][0, 2000:100001]
+    se = u.std(0) / np.sqrt(len(u)) + 0.02
+    assert np.all(np.abs(u.mean(0) - s.mean(0)) < 5 * se)
+    assert np.all(s.mean(0)[:10] > 0.9) and np.all(s.mean(0)[10:] < 0.2)      # the 10 true signals are found
+    # states are 0/1 vectors with at most s0 ones
+    assert set(np.unique(s)) <= {0.0, 1.0} and s.sum(1).max() <= 10

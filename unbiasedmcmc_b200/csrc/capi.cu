@@ -14,6 +14,7 @@
 #include "ubm_mvn.cuh"
 #include "ubm_ising.cuh"
 #include "ubm_pg.cuh"
+#include "ubm_varsel.cuh"
 #include "ubm_summary.cuh"
 #include "ubm_post.cuh"
 #include "ubm_peaks.cuh"
@@ -63,6 +64,7 @@ struct ubm_plan {
   MvnDevice mvn{};
   IsingDevice ising{};
   PgDevice pg{};
+  VarselDevice varsel{};
   DevBuf model_blob;
   // results
   DevBuf uest, mcmc, corr, tau, cost, iter, bins_out, bin_acc, breaks, summary, counter, status, scratch;
@@ -88,6 +90,7 @@ static int model_dims(int32_t kind, const void* model, int* dim) {
     case UBM_MODEL_MVN: *dim = ((const ubm_model_mvn*)model)->d; return UBM_OK;
     case UBM_MODEL_ISING_PT: *dim = ((const ubm_model_ising_pt*)model)->nchains; return UBM_OK;
     case UBM_MODEL_PG_LOGISTIC: *dim = ((const ubm_model_pg_logistic*)model)->p; return UBM_OK;
+    case UBM_MODEL_VARSEL: *dim = ((const ubm_model_varsel*)model)->p; return UBM_OK;
     default: return UBM_ERR_UNSUPPORTED;
   }
 }
@@ -144,6 +147,32 @@ static int register_model(ubm_plan* p, int32_t kind, const void* model) {
     CU(cudaMemcpyAsync(p->model_blob.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     pg_bind_device(&p->pg, p->model_blob.as<double>());
+    return UBM_OK;
+  }
+  if (kind == UBM_MODEL_VARSEL) {
+    const ubm_model_varsel* s = (const ubm_model_varsel*)model;
+    if (s->p < 2 || s->p > 1024 || s->n < 1 || s->s0 < 1 || s->s0 > 128) return fail(h, UBM_ERR_INVALID, "variable selection: 2 <= p <= 1024, 1 <= s0 <= 128");
+    if (!s->X || !s->Y) return fail(h, UBM_ERR_INVALID, "variable selection: null data");
+    if (!(s->proportion_singleflip >= 0.0 && s->proportion_singleflip <= 1.0)) return fail(h, UBM_ERR_INVALID, "variable selection: proportion_singleflip in [0,1]");
+    VarselDevice& V = p->varsel;
+    V.n = s->n; V.p = s->p; V.s0 = s->s0 < s->p ? s->s0 : s->p; V.nwords = (s->p + 31) / 32;
+    V.g = s->g; V.kappa = s->kappa; V.prop_flip = s->proportion_singleflip;
+    double y2 = 0.0;
+    for (int i = 0; i < s->n; ++i) y2 = ubm_fma(s->Y[i], s->Y[i], y2);          // R/variableselection.R:6
+    V.Y2 = y2; V.lg1 = ubm_log(s->g + 1.); V.gg = s->g / (s->g + 1.); V.logp = ubm_log((double)s->p);
+    p->dim = s->p;
+    DevBuf dX, dY;
+    const size_t np_ = (size_t)s->n * s->p, pp_ = (size_t)s->p * s->p;
+    CU(dX.alloc(np_ * 8)); CU(dY.alloc((size_t)s->n * 8));
+    CU(p->model_blob.alloc((pp_ + s->p) * 8));
+    CU(cudaMemcpyAsync(dX.p, s->X, np_ * 8, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dY.p, s->Y, (size_t)s->n * 8, cudaMemcpyHostToDevice, h->stream));
+    double* G = p->model_blob.as<double>();
+    varsel_gram_kernel<<<(unsigned)((pp_ + 255) / 256), 256, 0, h->stream>>>(dX.as<double>(), dY.as<double>(), s->n, s->p, G, G + pp_);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    V.G = G; V.v = G + pp_;
     return UBM_OK;
   }
   return fail(h, UBM_ERR_UNSUPPORTED, "model kind not in the device registry (no CPU fallback)");
@@ -269,6 +298,9 @@ static int plan_run(ubm_plan* p, int draws_mode, uint64_t seed, int64_t nrep, in
     h->launches += 1;
   } else if (p->model_kind == UBM_MODEL_MVN) {
     int stl = mvn_launch(p->mvn, P, tape, nsm, st, p->scratch, &h->launches, &h->err);
+    if (stl != UBM_OK) return stl;
+  } else if (p->model_kind == UBM_MODEL_VARSEL) {
+    int stl = varsel_launch(p->varsel, P, tape, nsm, st, p->scratch, &h->launches, &h->err);
     if (stl != UBM_OK) return stl;
   } else if (p->model_kind == UBM_MODEL_PG_LOGISTIC) {
     int stl = pg_launch(p->pg, P, tape, nsm, st, &h->launches, &h->err);

@@ -166,3 +166,23 @@ class PgLogistic(ModelSpec):
 
     def struct(self):
         return A.ubm_model_pg_logistic(self.n, self.p, A.dptr(self.X), A.dptr(self.Y), A.dptr(self.b), A.dptr(self.B))
+
+
+class VariableSelection(ModelSpec):
+    """C5 — get_variableselection(Y, X, g, kappa, s0, proportion_singleflip) (R/variableselection.R:3)."""
+    kind = A.UBM_MODEL_VARSEL
+
+    def __init__(self, Y, X, g, kappa, s0, proportion_singleflip):
+        X = np.asarray(X, dtype=np.float64)
+        self.n, self.p = X.shape
+        if not (2 <= self.p <= 1024 and 1 <= int(s0) <= 128):
+            raise ValueError("variable selection: 2 <= p <= 1024, 1 <= s0 <= 128")
+        self.dim = self.p
+        self.X = _colmajor(X)
+        self.Y = _f64(Y).reshape(-1)
+        self.g, self.kappa, self.s0 = float(g), float(kappa), int(s0)
+        self.proportion_singleflip = float(proportion_singleflip)
+
+    def struct(self):
+        return A.ubm_model_varsel(self.n, self.p, A.dptr(self.X), A.dptr(self.Y), self.g, self.kappa, self.s0, 0,
+                                  self.proportion_singleflip)
