@@ -307,6 +307,12 @@ def main():
                                "MEASURED_PEAKS.json holds no FP64 / INT32 figure; HBM is not the bound (state stays on "
                                "chip, dram traffic of the driver kernel is a few KB per launch, see profiles/)",
                 "fp64_tflops_measured": peaks["fp64_tflops"], "int32_tops_measured": peaks["int32_tops"]}
+    tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tj):
+        tr = json.load(open(tj)).get(roofline["kernel"])
+        if tr:   # DRAM bytes per launch, scaled from the committed ncu capture (bytes per replicate x replicates)
+            roofline["traffic"] = tr["dram_bytes_per_replicate"] * nrep
+            roofline["traffic_source"] = tr["source"]
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(mp):
         roofline["hbm_gbs_measured_peak"] = json.load(open(mp)).get("hbm_gbs")
