@@ -211,28 +211,29 @@ UBM_HD double ubm_log1p(double x) {
  * qnorm: Wichura (1988) algorithm AS241, PPND16 — the routine behind R's qnorm5 and therefore behind
  * R's default ("Inversion") norm_rand.  One uniform in, one standard normal out.
  * ---------------------------------------------------------------------------------------------- */
-UBM_HD double ubm_qnorm(double p) {
-  double q = p - 0.5;
-  if (fabs(q) <= 0.425) {
-    double r = 0.180625 - q * q;
-    double num = 2509.0809287301226727;
-    num = ubm_fma(num, r, 33430.575583588128105);
-    num = ubm_fma(num, r, 67265.770927008700853);
-    num = ubm_fma(num, r, 45921.953931549871457);
-    num = ubm_fma(num, r, 13731.693765509461125);
-    num = ubm_fma(num, r, 1971.5909503065514427);
-    num = ubm_fma(num, r, 133.14166789178437745);
-    num = ubm_fma(num, r, 3.387132872796366608);
-    double den = 5226.495278852545925;
-    den = ubm_fma(den, r, 28729.085735721942674);
-    den = ubm_fma(den, r, 39307.89580009271061);
-    den = ubm_fma(den, r, 21213.794301586595867);
-    den = ubm_fma(den, r, 5394.1960214247511077);
-    den = ubm_fma(den, r, 687.1870074920579083);
-    den = ubm_fma(den, r, 42.313330701600911252);
-    den = ubm_fma(den, r, 1.0);
-    return q * num / den;
-  }
+/* central branch: |q| <= 0.425, q = p - 1/2 */
+UBM_HD double ubm_qnorm_central(double q) {
+  double r = 0.180625 - q * q;
+  double num = 2509.0809287301226727;
+  num = ubm_fma(num, r, 33430.575583588128105);
+  num = ubm_fma(num, r, 67265.770927008700853);
+  num = ubm_fma(num, r, 45921.953931549871457);
+  num = ubm_fma(num, r, 13731.693765509461125);
+  num = ubm_fma(num, r, 1971.5909503065514427);
+  num = ubm_fma(num, r, 133.14166789178437745);
+  num = ubm_fma(num, r, 3.387132872796366608);
+  double den = 5226.495278852545925;
+  den = ubm_fma(den, r, 28729.085735721942674);
+  den = ubm_fma(den, r, 39307.89580009271061);
+  den = ubm_fma(den, r, 21213.794301586595867);
+  den = ubm_fma(den, r, 5394.1960214247511077);
+  den = ubm_fma(den, r, 687.1870074920579083);
+  den = ubm_fma(den, r, 42.313330701600911252);
+  den = ubm_fma(den, r, 1.0);
+  return q * num / den;
+}
+/* tail branches: |q| > 0.425 */
+UBM_HD double ubm_qnorm_tail(double p, double q) {
   double pp = (q < 0.0) ? p : (1.0 - p);
   double r = sqrt(-ubm_log(pp));
   double val;
@@ -276,6 +277,11 @@ UBM_HD double ubm_qnorm(double p) {
     val = num / den;
   }
   return (q < 0.0) ? -val : val;
+}
+UBM_HD double ubm_qnorm(double p) {
+  double q = p - 0.5;
+  if (fabs(q) <= 0.425) return ubm_qnorm_central(q);
+  return ubm_qnorm_tail(p, q);
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -19,9 +19,13 @@
 // finishes (work stealing).  Reductions over a d-vector use the canonical order "fma chain inside each
 // 4-column group, xor-butterfly over the <= 32 groups" (oracle: sum_g4_*).
 //
-// Thread roles (256 threads): warps 0-3 (one per SM sub-partition) run the GEMM phases with software-pipelined
-// operand loads; all 8 warps share the per-slot work (draws, coupling algebra, accept/reject, state and estimator
-// updates), one warp per slot at a time, so that step needs no CTA-wide barrier.
+// Thread roles (256 threads, warp-specialised): warps 0-3 (one per SM sub-partition) are CONSUMERS: they run the GEMM
+// phases with software-pipelined operand loads and the coupling algebra, synchronising among themselves on a named
+// barrier; warps 4-7 are PRODUCERS: while step t is computed they generate every draw of step t+1 (the d normals
+// per slot through Philox + AS241 with the rare tail branch handled in a separate lane-local pass, and the
+// log-uniforms, into a small ring), so no random-number work sits on the critical path.  All 8 warps share the short
+// per-slot section at the step boundary (accept/reject, state and estimator update, slot state machine), one warp
+// per slot.  Two CTA-wide barriers per step.
 //
 // Shared-memory layout notes (ncu, profiles/r01_mvn_*.md: the first version had 12.5e9 bank conflicts):
 //   - packed group g starts at 8 g (g+1) + 2 (g mod 8) + 14 (g div 8) doubles: the 16-byte pads spread the
@@ -84,49 +88,62 @@ inline void mvn_bind_device(MvnDevice* M, const double* dev) {
   M->packA = dev + M->offs[2]; M->packB = dev + M->offs[3]; M->packC = dev + M->offs[4]; M->packI = dev + M->offs[5];
 }
 
-enum { SL_IDLE = 0, SL_INIT = 1, SL_SINGLE = 2, SL_COUPLED = 3 };
+enum { SL_IDLE = 0, SL_WAIT = 1, SL_INIT = 2, SL_SINGLE = 3, SL_COUPLED = 4 };
 #define MVN_MAXR 16
 #define MVN_T 256      // threads per CTA
-#define MVN_GT 128     // GEMM threads (warps 0-3)
+#define MVN_GT 128     // consumer (GEMM) threads: warps 0-3; warps 4-7 produce the draws of the next step
 
 struct MvnSlots {   // per-slot scalars, in shared memory
   long long rep[MVN_MAXR], time[MVN_MAXR], tau[MVN_MAXR];
-  unsigned long long iu[MVN_MAXR], in[MVN_MAXR];
+  unsigned long long iu[MVN_MAXR], in[MVN_MAXR], pu[MVN_MAXR];
   double pdf1[MVN_MAXR], pdf2[MVN_MAXR];
   int phase[MVN_MAXR], met[MVN_MAXR], ident[MVN_MAXR], bad[MVN_MAXR];
+  int rowsA[MVN_MAXR], rowsB[2 * MVN_MAXR], rowsI[2 * MVN_MAXR], rowsC[2 * MVN_MAXR];
+  int nA, nB, nI, nC;
   int exhausted;
 };
+
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // One GEMM unit: RT input rows (smem, 16-byte aligned) against column group g of a packed matrix:
 // acc[r][c] = sum_{k <= 4g+3} in_r[k] M[k][4g+c], sequential in k.  Operands for k+2, k+3 are loaded while
 // k, k+1 are computed (reads run at most 32 bytes past the group / row, inside the padding).
-template <int RT, bool SUBMEAN>
+// MODE 0: plain input; 1: input minus `aux` vector (the target mean); 2: input = in2_r[k] - in_r[k] (x2 - x1).
+template <int RT, int MODE>
 __device__ __forceinline__ void mvn_unit(const double* __restrict__ pack, int g, const double* const* in,
-                                         const double* __restrict__ mean, double (&acc)[RT][4]) {
+                                         const double* const* in2, const double* __restrict__ aux,
+                                         double (&acc)[RT][4]) {
   const int K = 4 * g + 4;
   const double* mp = pack + mvn_group_off(g);
   double2 m0 = *reinterpret_cast<const double2*>(mp), m1 = *reinterpret_cast<const double2*>(mp + 2);
   double2 m2 = *reinterpret_cast<const double2*>(mp + 4), m3 = *reinterpret_cast<const double2*>(mp + 6);
-  double2 v[RT];
+  double2 v[RT], w[RT];
 #pragma unroll
-  for (int r = 0; r < RT; ++r) v[r] = *reinterpret_cast<const double2*>(in[r]);
+  for (int r = 0; r < RT; ++r) {
+    v[r] = *reinterpret_cast<const double2*>(in[r]);
+    if (MODE == 2) w[r] = *reinterpret_cast<const double2*>(in2[r]);
+  }
   double2 mu = make_double2(0.0, 0.0);
-  if (SUBMEAN) mu = *reinterpret_cast<const double2*>(mean);
+  if (MODE == 1) mu = *reinterpret_cast<const double2*>(aux);
 #pragma unroll 2
   for (int k = 0; k < K; k += 2) {
     const double2 n0 = *reinterpret_cast<const double2*>(mp + 4 * k + 8);
     const double2 n1 = *reinterpret_cast<const double2*>(mp + 4 * k + 10);
     const double2 n2 = *reinterpret_cast<const double2*>(mp + 4 * k + 12);
     const double2 n3 = *reinterpret_cast<const double2*>(mp + 4 * k + 14);
-    double2 vn[RT];
+    double2 vn[RT], wn[RT];
 #pragma unroll
-    for (int r = 0; r < RT; ++r) vn[r] = *reinterpret_cast<const double2*>(in[r] + k + 2);
+    for (int r = 0; r < RT; ++r) {
+      vn[r] = *reinterpret_cast<const double2*>(in[r] + k + 2);
+      if (MODE == 2) wn[r] = *reinterpret_cast<const double2*>(in2[r] + k + 2);
+    }
     double2 mun = make_double2(0.0, 0.0);
-    if (SUBMEAN) mun = *reinterpret_cast<const double2*>(mean + k + 2);
+    if (MODE == 1) mun = *reinterpret_cast<const double2*>(aux + k + 2);
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       double2 x = v[r];
-      if (SUBMEAN) { x.x = x.x - mu.x; x.y = x.y - mu.y; }
+      if (MODE == 1) { x.x = x.x - mu.x; x.y = x.y - mu.y; }
+      if (MODE == 2) { x.x = w[r].x - x.x; x.y = w[r].y - x.y; }
       acc[r][0] = ubm_fma(x.x, m0.x, acc[r][0]);
       acc[r][1] = ubm_fma(x.x, m0.y, acc[r][1]);
       acc[r][2] = ubm_fma(x.x, m1.x, acc[r][2]);
@@ -138,7 +155,7 @@ __device__ __forceinline__ void mvn_unit(const double* __restrict__ pack, int g,
     }
     m0 = n0; m1 = n1; m2 = n2; m3 = n3; mu = mun;
 #pragma unroll
-    for (int r = 0; r < RT; ++r) v[r] = vn[r];
+    for (int r = 0; r < RT; ++r) { v[r] = vn[r]; if (MODE == 2) w[r] = wn[r]; }
   }
 }
 
@@ -148,72 +165,95 @@ __device__ __forceinline__ double warp_butterfly(double v) {
   return v;
 }
 
-// four consecutive standard normals of a replicate's N stream starting at index i0 (two Philox blocks when
-// i0 is even, three otherwise)
+// Four consecutive standard normals of a replicate's N stream starting at index i0, executed by a whole warp
+// (lanes with nvalid <= 0 idle).  AS241's central branch is evaluated for all draws first; the ~15 % of draws in the
+// tails are finished in a separate lane-local loop so that the warp does not run both branches for every draw.
 template <bool TAPE>
-__device__ __forceinline__ void draw_n4(const RunParams& P, long long rep, unsigned long long i0, int nvalid,
-                                        double* out, bool* bad) {
+__device__ __forceinline__ void draw_n4_warp(const RunParams& P, long long rep, unsigned long long i0, int nvalid,
+                                             double (&out)[4], bool* bad) {
   if (TAPE) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) out[c] = (c < nvalid) ? draw_n_at<true>(P, rep, i0 + c, bad) : 0.0;
     return;
   }
   const uint64_t grep = (uint64_t)(P.rep_offset + rep);
-  unsigned long long cur = ~0ull;
-  ubm_u32x4 blk;
-  blk.w[0] = blk.w[1] = blk.w[2] = blk.w[3] = 0;
+  double pr[4] = {0.5, 0.5, 0.5, 0.5};
+  if (nvalid > 0) {
+    const unsigned long long b0 = i0 >> 1;
+    const ubm_u32x4 A0 = ubm_stream_block(P.seed, grep, UBM_STREAM_N, b0);
+    const ubm_u32x4 A1 = ubm_stream_block(P.seed, grep, UBM_STREAM_N, b0 + 1);
+    if (i0 & 1) {
+      const ubm_u32x4 A2 = ubm_stream_block(P.seed, grep, UBM_STREAM_N, b0 + 2);
+      pr[0] = ubm_u01_53(A0.w[2], A0.w[3]); pr[1] = ubm_u01_53(A1.w[0], A1.w[1]);
+      pr[2] = ubm_u01_53(A1.w[2], A1.w[3]); pr[3] = ubm_u01_53(A2.w[0], A2.w[1]);
+    } else {
+      pr[0] = ubm_u01_53(A0.w[0], A0.w[1]); pr[1] = ubm_u01_53(A0.w[2], A0.w[3]);
+      pr[2] = ubm_u01_53(A1.w[0], A1.w[1]); pr[3] = ubm_u01_53(A1.w[2], A1.w[3]);
+    }
+  }
+  unsigned pending = 0;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
+    const double q = pr[c] - 0.5;
+    out[c] = 0.0;
     if (c < nvalid) {
-      const unsigned long long idx = i0 + c, b = idx >> 1;
-      if (b != cur) { blk = ubm_stream_block(P.seed, grep, UBM_STREAM_N, b); cur = b; }
-      const double p = (idx & 1) ? ubm_u01_53(blk.w[2], blk.w[3]) : ubm_u01_53(blk.w[0], blk.w[1]);
-      out[c] = ubm_qnorm(p);
-    } else out[c] = 0.0;
+      if (fabs(q) <= 0.425) out[c] = ubm_qnorm_central(q);
+      else pending |= 1u << c;
+    }
+  }
+  while (__any_sync(0xffffffffu, pending != 0)) {
+    if (pending) {
+      const int c = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const double pc = (c == 0) ? pr[0] : (c == 1) ? pr[1] : (c == 2) ? pr[2] : pr[3];
+      const double val = ubm_qnorm_tail(pc, pc - 0.5);
+      if (c == 0) out[0] = val; else if (c == 1) out[1] = val; else if (c == 2) out[2] = val; else out[3] = val;
+    }
   }
 }
 
 struct MvnSmem {
   double *packA, *packB, *packC, *MEAN;
-  double *X1, *X2, *V1, *V2;      // [R][DPS]   V1: chain-1 row (diff -> xi -> proposal 1), V2: chain-2 row
-  double *ACC;                    // [R][2][dimh]  mcmc sums, correction sums (estimator mode)
-  double* TG;                     // [2R][32]
-  double* ZERO;                   // [DPS]
+  double *X1, *X2;                // [R][DPS]
+  double *XI;                     // [2][R][DPS]  double-buffered chain-1 row: normals of this step -> proposal 1 (in place)
+  double *V2;                     // [R][DPS]     chain-2 row: z -> e -> eta -> proposal 2 (in place)
+  double *ACC;                    // [R][2][dimh] mcmc sums, correction sums (estimator mode)
+  double *TG;                     // [2R][32]
+  double *ZERO;                   // [DPS]
+  double *LU;                     // [R][8] ring of log-uniforms produced ahead
   MvnSlots* S;
 };
 
 __host__ __device__ inline size_t mvn_smem_bytes(int packLen, int DPS, int R, int acc_per_slot) {
-  return (size_t)(3 * packLen + DPS + 4 * R * DPS + R * acc_per_slot + 2 * R * 32 + DPS) * sizeof(double) +
+  return (size_t)(3 * packLen + DPS + 5 * R * DPS + R * acc_per_slot + 2 * R * 32 + DPS + 8 * R) * sizeof(double) +
          sizeof(MvnSlots) + 16;
 }
 
-// idx-th row of the compact row list "all set bits of m1 as chain-1 rows, then all set bits of m2 as chain-2
-// rows"; returns slot * 2 + which, or -1
-__device__ __forceinline__ int mvn_row_code(unsigned m1, unsigned m2, int idx) {
-  const int n1 = __popc(m1);
-  if (idx < n1) return 2 * (int)__fns(m1, 0, idx + 1);
-  idx -= n1;
-  if (idx < __popc(m2)) return 2 * (int)__fns(m2, 0, idx + 1) + 1;
-  return -1;
-}
-
-// GEMM phase over a compact row list.  Input vector of row code c = (c & 1 ? V2 : V1)[c >> 1].  Thread u owns
-// unit u = pr * nRG + rg (row group fastest).  Every thread owns at most ONE unit, so outputs can be parked in
-// registers across the barrier that protects in-place overwriting of the inputs.
-template <int RT, bool SUBMEAN>
-__device__ __forceinline__ void mvn_phase_compute(const double* __restrict__ pack, const MvnSmem& sm, unsigned m1,
-                                                  unsigned m2, int nrows, int DPS, int nCG, int nPairs,
-                                                  const double* mean, int u, int (&code)[RT], int (&gs)[2], int& ng,
+// GEMM phase over a compact row list (row code = slot * 2 + which).  Thread u owns unit u = pr * nRG + rg (row group
+// fastest, so that a warp touches few column groups).  Every thread owns at most ONE unit, so outputs can be parked
+// in registers across the barrier that protects in-place overwriting of the inputs.
+template <int RT, int MODE>
+__device__ __forceinline__ void mvn_phase_compute(const double* __restrict__ pack, const MvnSmem& sm, const double* V1,
+                                                  const int* rows, int nrows, int DPS, int nCG, int nPairs,
+                                                  const double* aux, int u, int (&code)[RT], int (&gs)[2], int& ng,
                                                   double (&acc)[2][RT][4]) {
   const int nRG = (nrows + RT - 1) / RT;
   ng = 0;
   if (u >= nRG * nPairs) return;
   const int pr = u / nRG, rg = u - pr * nRG;
   const double* in[RT];
+  const double* in2[RT];
 #pragma unroll
   for (int r = 0; r < RT; ++r) {
-    code[r] = mvn_row_code(m1, m2, RT * rg + r);
-    in[r] = (code[r] < 0) ? sm.ZERO : ((code[r] & 1) ? sm.V2 : sm.V1) + (code[r] >> 1) * DPS;
+    const int idx = RT * rg + r;
+    code[r] = (idx < nrows) ? rows[idx] : -1;
+    if (MODE == 2) {
+      in[r] = (code[r] < 0) ? sm.ZERO : sm.X1 + (code[r] >> 1) * DPS;
+      in2[r] = (code[r] < 0) ? sm.ZERO : sm.X2 + (code[r] >> 1) * DPS;
+    } else {
+      in[r] = (code[r] < 0) ? sm.ZERO : ((code[r] & 1) ? sm.V2 : V1) + (code[r] >> 1) * DPS;
+      in2[r] = in[r];
+    }
   }
   gs[0] = pr; gs[1] = nCG - 1 - pr;
   ng = (gs[0] == gs[1]) ? 1 : 2;
@@ -221,7 +261,7 @@ __device__ __forceinline__ void mvn_phase_compute(const double* __restrict__ pac
   for (int q = 0; q < 2; ++q) {
 #pragma unroll
     for (int r = 0; r < RT; ++r) { acc[q][r][0] = acc[q][r][1] = acc[q][r][2] = acc[q][r][3] = 0.0; }
-    if (q < ng) mvn_unit<RT, SUBMEAN>(pack, gs[q], in, mean, acc[q]);
+    if (q < ng) mvn_unit<RT, MODE>(pack, gs[q], in, in2, aux, acc[q]);
   }
 }
 
@@ -236,26 +276,28 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
     double* p = reinterpret_cast<double*>(smem_raw);
     sm.packA = p; p += M.packLen; sm.packB = p; p += M.packLen; sm.packC = p; p += M.packLen;
     sm.MEAN = p; p += DPS;
-    sm.X1 = p; p += R * DPS; sm.X2 = p; p += R * DPS; sm.V1 = p; p += R * DPS; sm.V2 = p; p += R * DPS;
+    sm.X1 = p; p += R * DPS; sm.X2 = p; p += R * DPS; sm.XI = p; p += 2 * R * DPS; sm.V2 = p; p += R * DPS;
     sm.ACC = p; p += R * acc_per_slot;
     sm.TG = p; p += 2 * R * 32;
     sm.ZERO = p; p += DPS;
+    sm.LU = p; p += 8 * R;
     sm.S = reinterpret_cast<MvnSlots*>(p);
   }
   MvnSlots& S = *sm.S;
   for (int i = tid; i < M.packLen; i += T) { sm.packA[i] = M.packA[i]; sm.packB[i] = M.packB[i]; sm.packC[i] = M.packC[i]; }
   for (int i = tid; i < DPS; i += T) sm.MEAN[i] = M.mean_pi[i];
-  for (int i = tid; i < 4 * R * DPS + R * acc_per_slot + 2 * R * 32 + DPS; i += T) sm.X1[i] = 0.0;
+  for (int i = tid; i < 5 * R * DPS + R * acc_per_slot + 2 * R * 32 + DPS + 8 * R; i += T) sm.X1[i] = 0.0;
   if (tid < MVN_MAXR) {
     S.rep[tid] = -1; S.phase[tid] = SL_IDLE; S.time[tid] = 0; S.tau[tid] = 0; S.met[tid] = 0;
-    S.iu[tid] = 0; S.in[tid] = 0; S.bad[tid] = 0; S.ident[tid] = 0;
+    S.iu[tid] = 0; S.in[tid] = 0; S.pu[tid] = 0; S.bad[tid] = 0; S.ident[tid] = 0;
   }
-  if (tid == 0) S.exhausted = 0;
+  if (tid == 0) { S.exhausted = 0; S.nA = S.nB = S.nI = S.nC = 0; }
   __syncthreads();
 
   const int dimh = (P.h_kind == UBM_H_BOTH) ? 2 * d : d;
   const double denom = (double)(P.m - P.k + 1);
   const unsigned FULL = 0xffffffffu;
+  int cur = 0;
 
 #ifdef UBM_MVN_TIMING
   long long tacc[5] = {0, 0, 0, 0, 0}, tsteps = 0;
@@ -267,16 +309,18 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
 #ifdef UBM_MVN_TIMING
     long long tprev = clock64(); tsteps++;
 #endif
-    // ================================================================ per-slot section (one warp per slot)
-    // finishes the step just computed (densities -> accept/reject -> state/estimator update), runs the slot state
-    // machine (finish / write-out / fetch the next replicate), and prepares the inputs of the next step.
-    int my_active = 0, my_coupled = 0;
+    double* XIc = sm.XI + cur * R * DPS;          // this step's chain-1 rows (normals -> proposals)
+    double* XIn = sm.XI + (cur ^ 1) * R * DPS;    // filled by the producers for the next step
+    // ================================================================ per-slot section (all 8 warps, one warp per slot)
+    // finishes the step just computed (densities -> accept/reject -> state/estimator update) and runs the slot state
+    // machine (finish / write-out / fetch the next replicate).  No random-number work: uniforms come from the ring.
+    int my_active = 0;
     for (int s = warp; s < R; s += nwarp) {
       int ph = S.phase[s];
       long long rep = S.rep[s];
       long long time = S.time[s];
       int met = S.met[s];
-      if (ph != SL_IDLE) {
+      if (ph >= SL_INIT) {
         // ---- log-densities of the proposals (src/mvnorm.cpp:81-84) and the MH accept step
         const double ss1 = warp_butterfly(sm.TG[(2 * s) * 32 + lane]);
         const double ss2 = warp_butterfly(sm.TG[(2 * s + 1) * 32 + lane]);
@@ -289,14 +333,7 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
           a1 = 1; a2 = 1;
           if (lane == 0) { S.pdf1[s] = pp1; S.pdf2[s] = pp2; }
         } else {
-          double logu = 0.0;
-          if (lane == 0) {
-            bool bad = false;
-            logu = ubm_log(draw_u_at<TAPE>(P, rep, S.iu[s], &bad));   // R/get_mh_kernels.R:34,57
-            S.iu[s] += 1;
-            if (bad) S.bad[s] = 1;
-          }
-          logu = __shfl_sync(FULL, logu, 0);
+          const double logu = sm.LU[s * 8 + (int)(S.iu[s] & 7ull)];      // log(runif(1)), R/get_mh_kernels.R:34,57
           const double pdf1 = S.pdf1[s], pdf2 = S.pdf2[s];
           if (ph == SL_SINGLE) {
             a1 = (logu < pp1 - pdf1) ? 1 : 0;
@@ -306,7 +343,9 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
             if (ident && a1 && a2) met = 1;
           }
           time += 1;
+          __syncwarp();
           if (lane == 0) {
+            S.iu[s] += 1;
             if (a1) S.pdf1[s] = pp1;
             if (a2) S.pdf2[s] = pp2;
             S.time[s] = time;
@@ -321,8 +360,8 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
         const bool coupled_step = (ph == SL_COUPLED);
         for (int j = lane; j < d; j += 32) {
           const int o = s * DPS + j;
-          if (a1) sm.X1[o] = sm.V1[o];
-          if (a2) sm.X2[o] = (coupled_step && ident) ? sm.V1[o] : sm.V2[o];
+          if (a1) sm.X1[o] = XIc[o];
+          if (a2) sm.X2[o] = (coupled_step && ident) ? XIc[o] : sm.V2[o];
           const double x1 = sm.X1[o];
           const double x2 = sm.X2[o];
           if (P.mode == MODE_ESTIMATOR) {
@@ -364,6 +403,7 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
           finished = (met && time >= horizon) || (time >= P.lag && capped);
         }
         if (ph == SL_INIT) finished = false;
+        if (lane == 0) S.in[s] += (ph == SL_INIT) ? 2 * d : d;          // normals consumed by the step just finished
         if (finished) {
           if (lane == 0) {
             const long long tt = S.tau[s];
@@ -393,6 +433,8 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
           ph = SL_IDLE;
         } else if (time < P.lag) ph = SL_SINGLE;
         else ph = met ? SL_SINGLE : SL_COUPLED;
+      } else if (ph == SL_WAIT) {
+        ph = SL_INIT;       // the producers generated the 2d rinit normals during the step that just ended
       }
       if (ph == SL_IDLE) {
         long long r = -1;
@@ -403,140 +445,127 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
         }
         r = __shfl_sync(FULL, r, 0);
         if (r >= 0) {
-          rep = r; time = 0; met = 0; ph = SL_INIT;
-          if (lane == 0) { S.rep[s] = r; S.time[s] = 0; S.tau[s] = 0; S.met[s] = 0; S.iu[s] = 0; S.in[s] = 0; S.bad[s] = 0; }
+          ph = SL_WAIT;
+          if (lane == 0) {
+            S.rep[s] = r; S.time[s] = 0; S.tau[s] = 0; S.met[s] = 0; S.iu[s] = 0; S.in[s] = 0; S.pu[s] = 0; S.bad[s] = 0;
+          }
         } else if (lane == 0) S.rep[s] = -1;
       }
       __syncwarp();
       if (lane == 0) { S.phase[s] = ph; S.ident[s] = 0; }
-      // ---- inputs of the next step: draws (non-coupled slots) or x2 - x1 (coupled slots)
-      if (ph != SL_IDLE) {
-        my_active = 1;
-        const unsigned long long in0 = S.in[s];
-        if (ph == SL_COUPLED) {
-          my_coupled = 1;
-          for (int j = lane; j < d; j += 32) sm.V1[s * DPS + j] = sm.X2[s * DPS + j] - sm.X1[s * DPS + j];   // mu2 - mu1 (:191)
-        } else if (lane < nCG) {
-          const int g = lane;
-          bool bad = false;
-          double z[4];
-          draw_n4<TAPE>(P, rep, in0 + 4 * g, d - 4 * g, z, &bad);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) sm.V1[s * DPS + 4 * g + c] = z[c];
-          if (ph == SL_INIT) {
-            draw_n4<TAPE>(P, rep, in0 + d + 4 * g, d - 4 * g, z, &bad);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) sm.V2[s * DPS + 4 * g + c] = z[c];
-          }
-          if (bad) S.bad[s] = 1;
-        }
-        __syncwarp();
-        if (lane == 0 && ph != SL_COUPLED) S.in[s] = in0 + ((ph == SL_INIT) ? 2 * d : d);
-      }
+      if (ph != SL_IDLE) my_active = 1;
     }
-    const int any_active = __syncthreads_or(my_active);
+    const int any_active = __syncthreads_or(my_active);      // CTA barrier 1: phases of this step are published
     if (!any_active) break;
-    const int any_coupled = __syncthreads_or(my_coupled);
     TMARK(0);
 
-    // row masks of this step (every warp computes them from the slot phases)
-    unsigned mA, mI, mS;
-    {
-      const int ph = (lane < R) ? S.phase[lane] : SL_IDLE;
-      mA = __ballot_sync(FULL, ph == SL_COUPLED);
-      mI = __ballot_sync(FULL, ph == SL_INIT);
-      mS = __ballot_sync(FULL, ph == SL_SINGLE);
-    }
-    // ================================================================ phase A: z = -(diff^T Cinv_prop) -> V2, |z|^2
-    if (any_coupled) {
-      if (tid < MVN_GT) {
-        int code[2], gs[2], ng;
-        double acc[2][2][4];
-        mvn_phase_compute<2, false>(sm.packA, sm, mA, 0u, __popc(mA), DPS, nCG, nPairs, nullptr, tid, code, gs, ng, acc);
-        for (int q = 0; q < ng; ++q) {
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            if (code[r] < 0) continue;
-            const int s = code[r] >> 1;
-            double t = 0.0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const double z = -acc[q][r][c];                        // :198
-              sm.V2[s * DPS + 4 * gs[q] + c] = z;
-              t = ubm_fma(z, z, t);
-            }
-            sm.TG[(2 * s) * 32 + gs[q]] = t;
-          }
+    if (warp < 4) {
+      // ================================================================ CONSUMERS (warps 0-3)
+      if (warp == 0) {      // row tables from ballots
+        const int ph = (lane < R) ? S.phase[lane] : SL_IDLE;
+        const unsigned mA = __ballot_sync(FULL, ph == SL_COUPLED), mS = __ballot_sync(FULL, ph == SL_SINGLE);
+        const unsigned mI = __ballot_sync(FULL, ph == SL_INIT);
+        const unsigned below = (1u << lane) - 1u;
+        if (ph == SL_COUPLED) S.rowsA[__popc(mA & below)] = 2 * lane;
+        if (ph == SL_INIT) { const int q = 2 * __popc(mI & below); S.rowsI[q] = 2 * lane; S.rowsI[q + 1] = 2 * lane + 1; }
+        if (lane == 0) { S.nA = __popc(mA); S.nI = 2 * __popc(mI); }
+        if (mA == 0) {      // no coupled slot: the B / C lists are known already
+          const unsigned mBS = mS;
+          if (ph == SL_SINGLE) { const int q = __popc(mBS & below); S.rowsB[q] = 2 * lane; S.rowsC[q] = 2 * lane; }
+          const int nb = __popc(mBS);
+          if (ph == SL_INIT) { const int q = nb + 2 * __popc(mI & below); S.rowsC[q] = 2 * lane; S.rowsC[q + 1] = 2 * lane + 1; }
+          if (lane == 0) { S.nB = nb; S.nC = nb + 2 * __popc(mI); }
         }
       }
-      __syncthreads();
-      // -------------------------------------------------------------- coupling algebra, one warp per coupled slot
-      for (int s = warp; s < R; s += nwarp) {
-        if (!((mA >> s) & 1u)) continue;
-        const long long rep = S.rep[s];
-        const double nz = sqrt(warp_butterfly(sm.TG[(2 * s) * 32 + lane]));   // :199
-        const unsigned long long in0 = S.in[s];
-        double z[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
-        double t = 0.0;
-        bool bad = false;
-        if (lane < nCG) {
-          draw_n4<TAPE>(P, rep, in0 + 4 * lane, d - 4 * lane, z, &bad);        // :193-195
-          if (!(nz < 1e-15)) {
+      consumer_bar();
+      const int nA = S.nA;
+      // ---------------------------------------------------------------- phase A: z = -((x2 - x1)^T Cinv_prop) -> V2, |z|^2
+      if (nA > 0) {
+        {
+          int code[2], gs[2], ng;
+          double acc[2][2][4];
+          mvn_phase_compute<2, 2>(sm.packA, sm, XIc, S.rowsA, nA, DPS, nCG, nPairs, nullptr, tid, code, gs, ng, acc);
+          for (int q = 0; q < ng; ++q) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              e[c] = sm.V2[s * DPS + 4 * lane + c] / nz;                       // :212
-              t = ubm_fma(e[c], z[c], t);                                      // :216
+            for (int r = 0; r < 2; ++r) {
+              if (code[r] < 0) continue;
+              const int s = code[r] >> 1;
+              double t = 0.0;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const double z = -acc[q][r][c];                        // :198
+                sm.V2[s * DPS + 4 * gs[q] + c] = z;
+                t = ubm_fma(z, z, t);
+              }
+              sm.TG[(2 * s) * 32 + gs[q]] = t;
             }
           }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) sm.V1[s * DPS + 4 * lane + c] = z[c];
         }
-        const double edx = warp_butterfly(t);
-        int ident = 0;
-        if (lane == 0) {
-          if (nz < 1e-15) ident = 1;                                           // :200-210, no uniform drawn
+        consumer_bar();
+        // -------------------------------------------------------------- coupling algebra, one warp per coupled slot
+        for (int i = warp; i < nA; i += 4) {
+          const int s = S.rowsA[i] >> 1;
+          const double nz = sqrt(warp_butterfly(sm.TG[(2 * s) * 32 + lane]));   // :199
+          double z[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
+          double t = 0.0;
+          if (lane < nCG) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) z[c] = XIc[s * DPS + 4 * lane + c];      // xi, drawn ahead (:193-195)
+            if (!(nz < 1e-15)) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                e[c] = sm.V2[s * DPS + 4 * lane + c] / nz;                       // :212
+                t = ubm_fma(e[c], z[c], t);                                      // :216
+              }
+            }
+          }
+          const double edx = warp_butterfly(t);
+          int ident = 0;
+          if (nz < 1e-15) ident = 1;                                             // :200-210, no uniform consumed
           else {
-            const double ut = draw_u_at<TAPE>(P, rep, S.iu[s], &bad);          // :213-215
-            S.iu[s] += 1;
+            const double lut = sm.LU[s * 8 + (int)(S.iu[s] & 7ull)];             // log(utilde), :213-215
             const double a = edx + nz;
-            ident = (ubm_log(ut) < (-0.5 * a * a + 0.5 * edx * edx)) ? 1 : 0;  // :217
+            ident = (lut < (-0.5 * a * a + 0.5 * edx * edx)) ? 1 : 0;            // :217
           }
-          S.ident[s] = ident;
-          S.in[s] = in0 + d;
-        }
-        if (bad) S.bad[s] = 1;
-        ident = __shfl_sync(FULL, ident, 0);
-        if (!ident && lane < nCG) {
-          const double two_edx = 2. * edx;
+          __syncwarp();
+          if (lane == 0) { S.ident[s] = ident; if (!(nz < 1e-15)) S.iu[s] += 1; }
+          if (!ident && lane < nCG) {
+            const double two_edx = 2. * edx;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) sm.V2[s * DPS + 4 * lane + c] = z[c] - two_edx * e[c];   // :221
+            for (int c = 0; c < 4; ++c) sm.V2[s * DPS + 4 * lane + c] = z[c] - two_edx * e[c];   // :221
+          }
         }
+        consumer_bar();
+        if (warp == 0) {      // B / C row lists: chain-1 rows of all stepping slots, chain-2 rows where proposals differ
+          const int ph = (lane < R) ? S.phase[lane] : SL_IDLE;
+          const int differ = (ph == SL_COUPLED) && !S.ident[lane < R ? lane : 0];
+          const unsigned m1 = __ballot_sync(FULL, ph == SL_COUPLED || ph == SL_SINGLE);
+          const unsigned m2 = __ballot_sync(FULL, differ);
+          const unsigned mI = __ballot_sync(FULL, ph == SL_INIT);
+          const unsigned below = (1u << lane) - 1u;
+          const int n1 = __popc(m1), n2 = __popc(m2);
+          if (ph == SL_COUPLED || ph == SL_SINGLE) { const int q = __popc(m1 & below); S.rowsB[q] = 2 * lane; S.rowsC[q] = 2 * lane; }
+          if (differ) { const int q = n1 + __popc(m2 & below); S.rowsB[q] = 2 * lane + 1; S.rowsC[q] = 2 * lane + 1; }
+          if (ph == SL_INIT) { const int q = n1 + n2 + 2 * __popc(mI & below); S.rowsC[q] = 2 * lane; S.rowsC[q + 1] = 2 * lane + 1; }
+          if (lane == 0) { S.nB = n1 + n2; S.nC = n1 + n2 + 2 * __popc(mI); }
+        }
+        consumer_bar();
       }
-      __syncthreads();
-    }
-    TMARK(1);
-    // chain-2 rows of the coupled slots whose proposals differ
-    unsigned mD;
-    {
-      const int differ = (lane < R) ? (((mA >> lane) & 1u) && !S.ident[lane]) : 0;
-      mD = __ballot_sync(FULL, differ);
-    }
-    // ================================================================ phase B: proposals = x + in^T C_prop (in place)
-    // and, for freshly fetched slots, x0 = init_mean + in^T init_chol (matrix read from global memory / L2)
-    for (int pass = 0; pass < 2; ++pass) {
-      const unsigned m1 = pass ? mI : (mA | mS);
-      const unsigned m2 = pass ? mI : mD;
-      const int nrows = __popc(m1) + __popc(m2);
-      if (nrows == 0) continue;   // block-uniform
-      int code[4] = {-1, -1, -1, -1}, gs[2] = {0, 0}, ng = 0, rt = 4;
-      double acc[2][4][4];
-      if (tid < MVN_GT) {
+      TMARK(1);
+      // ---------------------------------------------------------------- phase B: proposals = x + in^T C_prop (in place)
+      // and, for freshly fetched slots, x0 = init_mean + in^T init_chol (matrix read from global memory / L2)
+      for (int pass = 0; pass < 2; ++pass) {
+        const int nrows = pass ? S.nI : S.nB;
+        if (nrows == 0) continue;   // uniform over the consumer group
+        const int* rows = pass ? S.rowsI : S.rowsB;
+        int code[4] = {-1, -1, -1, -1}, gs[2] = {0, 0}, ng = 0, rt = 4;
+        double acc[2][4][4];
         if (((nrows + 1) / 2) * nPairs <= MVN_GT) {
           rt = 2;
           int code2[2];
           double acc2[2][2][4];
-          if (pass) mvn_phase_compute<2, false>(M.packI, sm, m1, m2, nrows, DPS, nCG, nPairs, nullptr, tid, code2, gs, ng, acc2);
-          else mvn_phase_compute<2, false>(sm.packB, sm, m1, m2, nrows, DPS, nCG, nPairs, nullptr, tid, code2, gs, ng, acc2);
+          if (pass) mvn_phase_compute<2, 0>(M.packI, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code2, gs, ng, acc2);
+          else mvn_phase_compute<2, 0>(sm.packB, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code2, gs, ng, acc2);
 #pragma unroll
           for (int q = 0; q < 2; ++q)
 #pragma unroll
@@ -546,59 +575,89 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
               for (int c = 0; c < 4; ++c) acc[q][r][c] = acc2[q][r][c];
             }
         } else {
-          if (pass) mvn_phase_compute<4, false>(M.packI, sm, m1, m2, nrows, DPS, nCG, nPairs, nullptr, tid, code, gs, ng, acc);
-          else mvn_phase_compute<4, false>(sm.packB, sm, m1, m2, nrows, DPS, nCG, nPairs, nullptr, tid, code, gs, ng, acc);
+          if (pass) mvn_phase_compute<4, 0>(M.packI, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code, gs, ng, acc);
+          else mvn_phase_compute<4, 0>(sm.packB, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code, gs, ng, acc);
         }
-      }
-      __syncthreads();   // every read of V1 / V2 of this pass is done: overwrite inputs with outputs
-      for (int q = 0; q < ng; ++q) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          if (r >= rt || code[r] < 0) continue;
-          const int s = code[r] >> 1, which = code[r] & 1;
-          const double* base = pass ? (M.init_mean + 4 * gs[q]) : ((which ? sm.X2 : sm.X1) + s * DPS + 4 * gs[q]);
-          double* out = (which ? sm.V2 : sm.V1) + s * DPS + 4 * gs[q];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) out[c] = (4 * gs[q] + c < d) ? (base[c] + acc[q][r][c]) : 0.0;   // :40-44, :224-225
-        }
-      }
-    }
-    __syncthreads();
-    TMARK(2);
-    // ================================================================ phase C: w = Cinv_pi^T (prop - mean), |w|^2
-    if (tid < MVN_GT) {
-      const unsigned m1 = mA | mS | mI, m2 = mD | mI;
-      const int nrows = __popc(m1) + __popc(m2);
-      if (((nrows + 1) / 2) * nPairs <= MVN_GT) {
-        int code[2], gs[2], ng;
-        double acc[2][2][4];
-        mvn_phase_compute<2, !ZERO_MEAN>(sm.packC, sm, m1, m2, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, gs, ng, acc);
-        for (int q = 0; q < ng; ++q)
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            if (code[r] < 0) continue;
-            double t = 0.0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) t = ubm_fma(acc[q][r][c], acc[q][r][c], t);
-            sm.TG[code[r] * 32 + gs[q]] = t;
-          }
-      } else {
-        int code[4], gs[2], ng;
-        double acc[2][4][4];
-        mvn_phase_compute<4, !ZERO_MEAN>(sm.packC, sm, m1, m2, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, gs, ng, acc);
-        for (int q = 0; q < ng; ++q)
+        consumer_bar();   // every read of this pass's inputs is done: overwrite them with the outputs
+        for (int q = 0; q < ng; ++q) {
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            if (code[r] < 0) continue;
-            double t = 0.0;
+            if (r >= rt || code[r] < 0) continue;
+            const int s = code[r] >> 1, which = code[r] & 1;
+            const double* base = pass ? (M.init_mean + 4 * gs[q]) : ((which ? sm.X2 : sm.X1) + s * DPS + 4 * gs[q]);
+            double* out = (which ? sm.V2 : XIc) + s * DPS + 4 * gs[q];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) t = ubm_fma(acc[q][r][c], acc[q][r][c], t);
-            sm.TG[code[r] * 32 + gs[q]] = t;
+            for (int c = 0; c < 4; ++c) out[c] = (4 * gs[q] + c < d) ? (base[c] + acc[q][r][c]) : 0.0;   // :40-44, :224-225
           }
+        }
+      }
+      consumer_bar();
+      TMARK(2);
+      // ---------------------------------------------------------------- phase C: w = Cinv_pi^T (prop - mean), |w|^2
+      {
+        const int nrows = S.nC;
+        if (((nrows + 1) / 2) * nPairs <= MVN_GT) {
+          int code[2], gs[2], ng;
+          double acc[2][2][4];
+          mvn_phase_compute<2, ZERO_MEAN ? 0 : 1>(sm.packC, sm, XIc, S.rowsC, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, gs, ng, acc);
+          for (int q = 0; q < ng; ++q)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              if (code[r] < 0) continue;
+              double t = 0.0;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) t = ubm_fma(acc[q][r][c], acc[q][r][c], t);
+              sm.TG[code[r] * 32 + gs[q]] = t;
+            }
+        } else {
+          int code[4], gs[2], ng;
+          double acc[2][4][4];
+          mvn_phase_compute<4, ZERO_MEAN ? 0 : 1>(sm.packC, sm, XIc, S.rowsC, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, gs, ng, acc);
+          for (int q = 0; q < ng; ++q)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              if (code[r] < 0) continue;
+              double t = 0.0;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) t = ubm_fma(acc[q][r][c], acc[q][r][c], t);
+              sm.TG[code[r] * 32 + gs[q]] = t;
+            }
+        }
+      }
+      TMARK(3);
+    } else {
+      // ================================================================ PRODUCERS (warps 4-7): draws of the NEXT step
+      for (int s = warp - 4; s < R; s += 4) {
+        const int ph = S.phase[s];
+        if (ph == SL_IDLE) continue;
+        const long long rep = S.rep[s];
+        const unsigned long long base = (ph == SL_WAIT) ? 0ull : ((ph == SL_INIT) ? (unsigned long long)(2 * d) : S.in[s] + d);
+        bool bad = false;
+        double z[4];
+        const int nvalid = (lane < nCG) ? d - 4 * lane : 0;
+        draw_n4_warp<TAPE>(P, rep, base + 4 * lane, nvalid, z, &bad);
+        if (lane < nCG) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) XIn[s * DPS + 4 * lane + c] = z[c];
+        }
+        if (ph == SL_WAIT) {      // rinit of chain 2 (draw order: chain 1's d normals, then chain 2's)
+          draw_n4_warp<TAPE>(P, rep, base + d + 4 * lane, nvalid, z, &bad);
+          if (lane < nCG) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sm.V2[s * DPS + 4 * lane + c] = z[c];
+          }
+        }
+        // log-uniform ring: keep it at least 4 draws ahead of the consumers (they use at most 2 per step)
+        const unsigned long long pu = S.pu[s], target = S.iu[s] + 6;
+        const unsigned long long idx = pu + lane;
+        if (lane < 8 && idx < target) sm.LU[s * 8 + (int)(idx & 7ull)] = ubm_log(draw_u_at<TAPE>(P, rep, idx, &bad));
+        __syncwarp();
+        if (lane == 0 && target > pu) S.pu[s] = target;
+        if (bad) S.bad[s] = 1;
       }
     }
-    __syncthreads();
-    TMARK(3);
+    __syncthreads();      // CTA barrier 2: step computed, draws of the next step in place
+    cur ^= 1;
   }
 #ifdef UBM_MVN_TIMING
   if (tid == 0 && blockIdx.x == 0)
