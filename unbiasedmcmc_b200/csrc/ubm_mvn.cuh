@@ -19,16 +19,16 @@
 // finishes (work stealing).  Reductions over a d-vector use the canonical order "fma chain inside each
 // 4-column group, xor-butterfly over the <= 32 groups" (oracle: sum_g4_*).
 //
-// Thread roles (256 threads, warp-specialised): warps 0-3 (one per SM sub-partition) are CONSUMERS: they run the GEMM
-// phases with software-pipelined operand loads and the coupling algebra, synchronising among themselves on a named
-// barrier; warps 4-7 are PRODUCERS: while step t is computed they generate every draw of step t+1 (the d normals
+// Thread roles (384 threads, warp-specialised): warps 0-7 (two per SM sub-partition, so that one hides the other's
+// shared-memory latency) are CONSUMERS: they run the GEMM phases and the coupling algebra, synchronising among
+// themselves on a named barrier; warps 8-11 are PRODUCERS: while step t is computed they generate every draw of step t+1 (the d normals
 // per slot through Philox + AS241 with the rare tail branch handled in a separate lane-local pass, and the
 // log-uniforms, into a small ring), so no random-number work sits on the critical path.  All 8 warps share the short
 // per-slot section at the step boundary (accept/reject, state and estimator update, slot state machine), one warp
-// per slot.  Two CTA-wide barriers per step.
+// per slot.  Tiles are 1 row x 4+4 columns when a phase has at most 16 rows, 2 rows otherwise: one unit per thread.  Two CTA-wide barriers per step.
 //
 // Shared-memory layout notes (ncu, profiles/r01_mvn_*.md: the first version had 12.5e9 bank conflicts):
-//   - packed group g starts at 8 g (g+1) + 2 (g mod 8) + 14 (g div 8) doubles: the 16-byte pads spread the
+//   - packed group g starts at 8 g (g+1) + 2 g doubles: the 16-byte pad per group spreads the
 //     per-thread LDS.128 of different groups over different banks (unpadded, every group starts on bank 0);
 //   - vectors use a row stride of DP + 2 doubles (== 2 mod 4), so rows of different slots read at the same k
 //     fall into different banks while staying 16-byte aligned;
@@ -50,7 +50,7 @@ struct MvnDevice {
 };
 
 // column group g holds rows k = 0 .. 4g+3 (rows >= d and entries below the diagonal are zero), 4 doubles per row
-__host__ __device__ __forceinline__ int mvn_group_off(int g) { return 8 * g * (g + 1) + 2 * (g & 7) + 14 * (g >> 3); }
+__host__ __device__ __forceinline__ int mvn_group_off(int g) { return 8 * g * (g + 1) + 2 * g; }
 __host__ __device__ __forceinline__ int mvn_pack_len(int nCG) { return mvn_group_off(nCG - 1) + 16 * nCG + 16; }
 
 inline void mvn_pack_matrix(const double* Ucm, int d, int nCG, std::vector<double>* blob) {
@@ -90,8 +90,10 @@ inline void mvn_bind_device(MvnDevice* M, const double* dev) {
 
 enum { SL_IDLE = 0, SL_WAIT = 1, SL_INIT = 2, SL_SINGLE = 3, SL_COUPLED = 4 };
 #define MVN_MAXR 16
-#define MVN_T 256      // threads per CTA
-#define MVN_GT 128     // consumer (GEMM) threads: warps 0-3; warps 4-7 produce the draws of the next step
+#define MVN_T 384      // threads per CTA
+#define MVN_GT 256     // consumer (GEMM) threads: warps 0-7 (two per SM sub-partition); warps 8-11 produce the draws of the next step
+#define MVN_CW 8       // consumer warps
+#define MVN_PW 4       // producer warps
 
 struct MvnSlots {   // per-slot scalars, in shared memory
   long long rep[MVN_MAXR], time[MVN_MAXR], tau[MVN_MAXR];
@@ -103,34 +105,34 @@ struct MvnSlots {   // per-slot scalars, in shared memory
   int exhausted;
 };
 
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// One GEMM unit: RT input rows (smem, 16-byte aligned) against column group g of a packed matrix:
-// acc[r][c] = sum_{k <= 4g+3} in_r[k] M[k][4g+c], sequential in k.  Operands for k+2, k+3 are loaded while
-// k, k+1 are computed (reads run at most 32 bytes past the group / row, inside the padding).
+// One GEMM stream: RT input rows (smem, 16-byte aligned) against rows [k0, k1) of column group g of a packed matrix:
+// acc[r][c] += sum_{k0 <= k < k1} in_r[k] M[k][4g+c], sequential in k (k0, k1 even).  Operands for k+2, k+3 are
+// requested while k, k+1 are computed (reads run at most 32 bytes past the group / row, inside the padding).
 // MODE 0: plain input; 1: input minus `aux` vector (the target mean); 2: input = in2_r[k] - in_r[k] (x2 - x1).
 template <int RT, int MODE>
-__device__ __forceinline__ void mvn_unit(const double* __restrict__ pack, int g, const double* const* in,
-                                         const double* const* in2, const double* __restrict__ aux,
-                                         double (&acc)[RT][4]) {
-  const int K = 4 * g + 4;
-  const double* mp = pack + mvn_group_off(g);
+__device__ __forceinline__ void mvn_range(const double* __restrict__ pack, int g, int k0, int k1,
+                                          const double* const* in, const double* const* in2,
+                                          const double* __restrict__ aux, double (&acc)[RT][4]) {
+  const double* mp = pack + mvn_group_off(g) + 4 * k0;
   double2 m0 = *reinterpret_cast<const double2*>(mp), m1 = *reinterpret_cast<const double2*>(mp + 2);
   double2 m2 = *reinterpret_cast<const double2*>(mp + 4), m3 = *reinterpret_cast<const double2*>(mp + 6);
   double2 v[RT], w[RT];
 #pragma unroll
   for (int r = 0; r < RT; ++r) {
-    v[r] = *reinterpret_cast<const double2*>(in[r]);
-    if (MODE == 2) w[r] = *reinterpret_cast<const double2*>(in2[r]);
+    v[r] = *reinterpret_cast<const double2*>(in[r] + k0);
+    if (MODE == 2) w[r] = *reinterpret_cast<const double2*>(in2[r] + k0);
   }
   double2 mu = make_double2(0.0, 0.0);
-  if (MODE == 1) mu = *reinterpret_cast<const double2*>(aux);
+  if (MODE == 1) mu = *reinterpret_cast<const double2*>(aux + k0);
 #pragma unroll 2
-  for (int k = 0; k < K; k += 2) {
-    const double2 n0 = *reinterpret_cast<const double2*>(mp + 4 * k + 8);
-    const double2 n1 = *reinterpret_cast<const double2*>(mp + 4 * k + 10);
-    const double2 n2 = *reinterpret_cast<const double2*>(mp + 4 * k + 12);
-    const double2 n3 = *reinterpret_cast<const double2*>(mp + 4 * k + 14);
+  for (int k = k0; k < k1; k += 2) {
+    mp += 8;
+    const double2 n0 = *reinterpret_cast<const double2*>(mp);
+    const double2 n1 = *reinterpret_cast<const double2*>(mp + 2);
+    const double2 n2 = *reinterpret_cast<const double2*>(mp + 4);
+    const double2 n3 = *reinterpret_cast<const double2*>(mp + 6);
     double2 vn[RT], wn[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
@@ -229,24 +231,32 @@ __host__ __device__ inline size_t mvn_smem_bytes(int packLen, int DPS, int R, in
          sizeof(MvnSlots) + 16;
 }
 
-// GEMM phase over a compact row list (row code = slot * 2 + which).  Thread u owns unit u = pr * nRG + rg (row group
-// fastest, so that a warp touches few column groups).  Every thread owns at most ONE unit, so outputs can be parked
-// in registers across the barrier that protects in-place overwriting of the inputs.
+// GEMM phase over a compact row list (row code = slot * 2 + which).  Work is cut into BALANCED HALF-UNITS: column
+// group gA = pr (K_A = 4 pr + 4 rows) is paired with gB = nCG-1-pr (K_B rows, K_A + K_B = 2 half), and the long
+// column group is summed in two segments [0, K_B - half) and [K_B - half, K_B) — the engine's canonical order
+// (oracle: vec_times_upper).  Lane 2i (h = 0) computes gA completely plus the first segment of gB, lane 2i+1 (h = 1)
+// the second segment of gB: both stream exactly `half` matrix rows.  The partner's first-segment sums arrive by
+// shuffle, so h = 0 owns the outputs of gA and h = 1 those of gB.  Unit index u = ((pr * nRG) + rg) * 2 + h.
+// Must be called by all 32 lanes of every consumer warp (shuffles); every thread owns at most one output group.
 template <int RT, int MODE>
 __device__ __forceinline__ void mvn_phase_compute(const double* __restrict__ pack, const MvnSmem& sm, const double* V1,
                                                   const int* rows, int nrows, int DPS, int nCG, int nPairs,
-                                                  const double* aux, int u, int (&code)[RT], int (&gs)[2], int& ng,
-                                                  double (&acc)[2][RT][4]) {
+                                                  const double* aux, int u, int (&code)[RT], int& g_out, bool& has_out,
+                                                  double (&out)[RT][4]) {
   const int nRG = (nrows + RT - 1) / RT;
-  ng = 0;
-  if (u >= nRG * nPairs) return;
-  const int pr = u / nRG, rg = u - pr * nRG;
+  const bool active = u < nRG * nPairs * 2;
+  const int h = u & 1, ur = u >> 1;
+  const int pr = active ? ur / nRG : 0, rg = active ? ur - pr * nRG : 0;
+  const int gA = pr, gB = nCG - 1 - pr;
+  const int KA = 4 * gA + 4, KB = 4 * gB + 4, half = 2 * (nCG + 1);
+  const bool middle = (gA == gB);
+  const int ks = (KB > half) ? KB - half : 0;
   const double* in[RT];
   const double* in2[RT];
 #pragma unroll
   for (int r = 0; r < RT; ++r) {
     const int idx = RT * rg + r;
-    code[r] = (idx < nrows) ? rows[idx] : -1;
+    code[r] = (active && idx < nrows) ? rows[idx] : -1;
     if (MODE == 2) {
       in[r] = (code[r] < 0) ? sm.ZERO : sm.X1 + (code[r] >> 1) * DPS;
       in2[r] = (code[r] < 0) ? sm.ZERO : sm.X2 + (code[r] >> 1) * DPS;
@@ -255,14 +265,27 @@ __device__ __forceinline__ void mvn_phase_compute(const double* __restrict__ pac
       in2[r] = in[r];
     }
   }
-  gs[0] = pr; gs[1] = nCG - 1 - pr;
-  ng = (gs[0] == gs[1]) ? 1 : 2;
+  double accA[RT][4], accB[RT][4];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-#pragma unroll
-    for (int r = 0; r < RT; ++r) { acc[q][r][0] = acc[q][r][1] = acc[q][r][2] = acc[q][r][3] = 0.0; }
-    if (q < ng) mvn_unit<RT, MODE>(pack, gs[q], in, in2, aux, acc[q]);
+  for (int r = 0; r < RT; ++r) { accA[r][0] = accA[r][1] = accA[r][2] = accA[r][3] = 0.0; accB[r][0] = accB[r][1] = accB[r][2] = accB[r][3] = 0.0; }
+  if (active) {
+    if (h == 0) {
+      if (!middle) mvn_range<RT, MODE>(pack, gA, 0, KA, in, in2, aux, accA);
+      if (ks > 0) mvn_range<RT, MODE>(pack, gB, 0, ks, in, in2, aux, accB);
+    } else {
+      mvn_range<RT, MODE>(pack, gB, ks, KB, in, in2, aux, accB);
+    }
   }
+#pragma unroll
+  for (int r = 0; r < RT; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double lo = __shfl_xor_sync(0xffffffffu, accB[r][c], 1);
+      if (h == 1 && ks > 0) accB[r][c] = lo + accB[r][c];
+      out[r][c] = h ? accB[r][c] : accA[r][c];
+    }
+  g_out = h ? gB : gA;
+  has_out = active && !(h == 0 && middle);
 }
 
 template <bool TAPE, bool ZERO_MEAN>
@@ -300,7 +323,7 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
   int cur = 0;
 
 #ifdef UBM_MVN_TIMING
-  long long tacc[5] = {0, 0, 0, 0, 0}, tsteps = 0;
+  long long tacc[5] = {0, 0, 0, 0, 0}, tsteps = 0, tb[4] = {0, 0, 0, 0};
 #define TMARK(i) do { long long now_ = clock64(); tacc[i] += now_ - tprev; tprev = now_; } while (0)
 #else
 #define TMARK(i) do { } while (0)
@@ -310,7 +333,8 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
     long long tprev = clock64(); tsteps++;
 #endif
     double* XIc = sm.XI + cur * R * DPS;          // this step's chain-1 rows (normals -> proposals)
-    double* XIn = sm.XI + (cur ^ 1) * R * DPS;    // filled by the producers for the next step
+    double* XIn = sm.XI + (cur ^ 1) * R * DPS;    // filled by the producers for the next step ...
+    const double* XIp = XIn;                      // ... and, until barrier 1, still holding the proposals of the step just computed
     // ================================================================ per-slot section (all 8 warps, one warp per slot)
     // finishes the step just computed (densities -> accept/reject -> state/estimator update) and runs the slot state
     // machine (finish / write-out / fetch the next replicate).  No random-number work: uniforms come from the ring.
@@ -360,8 +384,8 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
         const bool coupled_step = (ph == SL_COUPLED);
         for (int j = lane; j < d; j += 32) {
           const int o = s * DPS + j;
-          if (a1) sm.X1[o] = XIc[o];
-          if (a2) sm.X2[o] = (coupled_step && ident) ? XIc[o] : sm.V2[o];
+          if (a1) sm.X1[o] = XIp[o];
+          if (a2) sm.X2[o] = (coupled_step && ident) ? XIp[o] : sm.V2[o];
           const double x1 = sm.X1[o];
           const double x2 = sm.X2[o];
           if (P.mode == MODE_ESTIMATOR) {
@@ -459,8 +483,8 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
     if (!any_active) break;
     TMARK(0);
 
-    if (warp < 4) {
-      // ================================================================ CONSUMERS (warps 0-3)
+    if (warp < MVN_CW) {
+      // ================================================================ CONSUMERS (warps 0-7)
       if (warp == 0) {      // row tables from ballots
         const int ph = (lane < R) ? S.phase[lane] : SL_IDLE;
         const unsigned mA = __ballot_sync(FULL, ph == SL_COUPLED), mS = __ballot_sync(FULL, ph == SL_SINGLE);
@@ -482,10 +506,11 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
       // ---------------------------------------------------------------- phase A: z = -((x2 - x1)^T Cinv_prop) -> V2, |z|^2
       if (nA > 0) {
         {
-          int code[2], gs[2], ng;
-          double acc[2][2][4];
-          mvn_phase_compute<2, 2>(sm.packA, sm, XIc, S.rowsA, nA, DPS, nCG, nPairs, nullptr, tid, code, gs, ng, acc);
-          for (int q = 0; q < ng; ++q) {
+          int code[2], g;
+          bool has;
+          double acc[2][4];
+          mvn_phase_compute<2, 2>(sm.packA, sm, XIc, S.rowsA, nA, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
+          if (has) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
               if (code[r] < 0) continue;
@@ -493,17 +518,17 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
               double t = 0.0;
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const double z = -acc[q][r][c];                        // :198
-                sm.V2[s * DPS + 4 * gs[q] + c] = z;
+                const double z = -acc[r][c];                           // :198
+                sm.V2[s * DPS + 4 * g + c] = z;
                 t = ubm_fma(z, z, t);
               }
-              sm.TG[(2 * s) * 32 + gs[q]] = t;
+              sm.TG[(2 * s) * 32 + g] = t;
             }
           }
         }
         consumer_bar();
         // -------------------------------------------------------------- coupling algebra, one warp per coupled slot
-        for (int i = warp; i < nA; i += 4) {
+        for (int i = warp; i < nA; i += MVN_CW) {
           const int s = S.rowsA[i] >> 1;
           const double nz = sqrt(warp_butterfly(sm.TG[(2 * s) * 32 + lane]));   // :199
           double z[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
@@ -558,76 +583,91 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
         const int nrows = pass ? S.nI : S.nB;
         if (nrows == 0) continue;   // uniform over the consumer group
         const int* rows = pass ? S.rowsI : S.rowsB;
-        int code[4] = {-1, -1, -1, -1}, gs[2] = {0, 0}, ng = 0, rt = 4;
-        double acc[2][4][4];
-        if (((nrows + 1) / 2) * nPairs <= MVN_GT) {
+        int code[4] = {-1, -1, -1, -1}, g = 0, rt = 4;
+        bool has = false;
+        double acc[4][4];
+        if (((nrows + 1) / 2) * nPairs * 2 <= MVN_GT) {
           rt = 2;
           int code2[2];
-          double acc2[2][2][4];
-          if (pass) mvn_phase_compute<2, 0>(M.packI, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code2, gs, ng, acc2);
-          else mvn_phase_compute<2, 0>(sm.packB, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code2, gs, ng, acc2);
+          double acc2[2][4];
+          if (pass) mvn_phase_compute<2, 0>(M.packI, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code2, g, has, acc2);
+          else mvn_phase_compute<2, 0>(sm.packB, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code2, g, has, acc2);
 #pragma unroll
-          for (int q = 0; q < 2; ++q)
+          for (int r = 0; r < 2; ++r) {
+            code[r] = code2[r];
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              code[r] = code2[r];
-#pragma unroll
-              for (int c = 0; c < 4; ++c) acc[q][r][c] = acc2[q][r][c];
-            }
+            for (int c = 0; c < 4; ++c) acc[r][c] = acc2[r][c];
+          }
         } else {
-          if (pass) mvn_phase_compute<4, 0>(M.packI, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code, gs, ng, acc);
-          else mvn_phase_compute<4, 0>(sm.packB, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code, gs, ng, acc);
+          if (pass) mvn_phase_compute<4, 0>(M.packI, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
+          else mvn_phase_compute<4, 0>(sm.packB, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
         }
+#ifdef UBM_MVN_TIMING
+        long long tq0 = clock64();
+#endif
         consumer_bar();   // every read of this pass's inputs is done: overwrite them with the outputs
-        for (int q = 0; q < ng; ++q) {
+#ifdef UBM_MVN_TIMING
+        long long tq1 = clock64(); tb[0] += tq0 - tprev; tb[1] += tq1 - tq0;
+#endif
+        if (has) {
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             if (r >= rt || code[r] < 0) continue;
             const int s = code[r] >> 1, which = code[r] & 1;
-            const double* base = pass ? (M.init_mean + 4 * gs[q]) : ((which ? sm.X2 : sm.X1) + s * DPS + 4 * gs[q]);
-            double* out = (which ? sm.V2 : XIc) + s * DPS + 4 * gs[q];
+            const double* base = pass ? (M.init_mean + 4 * g) : ((which ? sm.X2 : sm.X1) + s * DPS + 4 * g);
+            double* outp = (which ? sm.V2 : XIc) + s * DPS + 4 * g;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) out[c] = (4 * gs[q] + c < d) ? (base[c] + acc[q][r][c]) : 0.0;   // :40-44, :224-225
+            for (int c = 0; c < 4; ++c) outp[c] = (4 * g + c < d) ? (base[c] + acc[r][c]) : 0.0;   // :40-44, :224-225
           }
         }
       }
+#ifdef UBM_MVN_TIMING
+      long long tq2 = clock64();
+#endif
       consumer_bar();
+#ifdef UBM_MVN_TIMING
+      tb[3] += clock64() - tq2;
+#endif
       TMARK(2);
       // ---------------------------------------------------------------- phase C: w = Cinv_pi^T (prop - mean), |w|^2
       {
         const int nrows = S.nC;
-        if (((nrows + 1) / 2) * nPairs <= MVN_GT) {
-          int code[2], gs[2], ng;
-          double acc[2][2][4];
-          mvn_phase_compute<2, ZERO_MEAN ? 0 : 1>(sm.packC, sm, XIc, S.rowsC, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, gs, ng, acc);
-          for (int q = 0; q < ng; ++q)
+        int g;
+        bool has;
+        if (((nrows + 1) / 2) * nPairs * 2 <= MVN_GT) {
+          int code[2];
+          double acc[2][4];
+          mvn_phase_compute<2, ZERO_MEAN ? 0 : 1>(sm.packC, sm, XIc, S.rowsC, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, g, has, acc);
+          if (has) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
               if (code[r] < 0) continue;
               double t = 0.0;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) t = ubm_fma(acc[q][r][c], acc[q][r][c], t);
-              sm.TG[code[r] * 32 + gs[q]] = t;
+              for (int c = 0; c < 4; ++c) t = ubm_fma(acc[r][c], acc[r][c], t);
+              sm.TG[code[r] * 32 + g] = t;
             }
+          }
         } else {
-          int code[4], gs[2], ng;
-          double acc[2][4][4];
-          mvn_phase_compute<4, ZERO_MEAN ? 0 : 1>(sm.packC, sm, XIc, S.rowsC, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, gs, ng, acc);
-          for (int q = 0; q < ng; ++q)
+          int code[4];
+          double acc[4][4];
+          mvn_phase_compute<4, ZERO_MEAN ? 0 : 1>(sm.packC, sm, XIc, S.rowsC, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, g, has, acc);
+          if (has) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               if (code[r] < 0) continue;
               double t = 0.0;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) t = ubm_fma(acc[q][r][c], acc[q][r][c], t);
-              sm.TG[code[r] * 32 + gs[q]] = t;
+              for (int c = 0; c < 4; ++c) t = ubm_fma(acc[r][c], acc[r][c], t);
+              sm.TG[code[r] * 32 + g] = t;
             }
+          }
         }
       }
       TMARK(3);
     } else {
-      // ================================================================ PRODUCERS (warps 4-7): draws of the NEXT step
-      for (int s = warp - 4; s < R; s += 4) {
+      // ================================================================ PRODUCERS (warps 8-11): draws of the NEXT step
+      for (int s = warp - MVN_CW; s < R; s += MVN_PW) {
         const int ph = S.phase[s];
         if (ph == SL_IDLE) continue;
         const long long rep = S.rep[s];
@@ -661,8 +701,9 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
   }
 #ifdef UBM_MVN_TIMING
   if (tid == 0 && blockIdx.x == 0)
-    printf("mvn timing (cycles/step, block 0): steps %lld slot %.0f A+coupling %.0f B %.0f C %.0f\n", tsteps,
-           (double)tacc[0] / tsteps, (double)tacc[1] / tsteps, (double)tacc[2] / tsteps, (double)tacc[3] / tsteps);
+    printf("mvn timing (cycles/step, block 0): steps %lld slot %.0f A+coupling %.0f B %.0f C %.0f | B: compute(thread0) %.0f bar %.0f endbar %.0f\n", tsteps,
+           (double)tacc[0] / tsteps, (double)tacc[1] / tsteps, (double)tacc[2] / tsteps, (double)tacc[3] / tsteps,
+           (double)tb[0] / tsteps, (double)tb[1] / tsteps, (double)tb[3] / tsteps);
 #endif
 }
 
@@ -676,10 +717,10 @@ inline int mvn_launch(const MvnDevice& M, const RunParams& P, bool tape, int nsm
   const int acc_per_slot = (P.mode == MODE_ESTIMATOR) ? 2 * dimh : 0;
   int R = MVN_MAXR;
   while (R > 1 && mvn_smem_bytes(M.packLen, M.DPS, R, acc_per_slot) > budget) --R;
-  // every phase must fit one unit per GEMM thread: 4-row tiles over at most 2R rows
-  while (R > 1 && ((2 * R + 3) / 4) * M.nPairs > MVN_GT) --R;
+  // every phase must fit one unit per consumer thread: 2-row tiles over at most 2R rows
+  while (R > 1 && R * M.nPairs > MVN_GT) --R;
   size_t smem = mvn_smem_bytes(M.packLen, M.DPS, R, acc_per_slot);
-  if (smem > budget || ((2 * R + 3) / 4) * M.nPairs > MVN_GT) { *err = "mvn: d too large for shared memory"; return UBM_ERR_UNSUPPORTED; }
+  if (smem > budget || R * M.nPairs > MVN_GT) { *err = "mvn: d too large for shared memory"; return UBM_ERR_UNSUPPORTED; }
   int64_t need = (P.nrep + R - 1) / R;
   int grid = (int)std::min<int64_t>(nsm, need);
   void (*kern)(const MvnDevice, const RunParams, const int, const int);
