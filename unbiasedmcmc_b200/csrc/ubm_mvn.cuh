@@ -255,7 +255,7 @@ __device__ __forceinline__ void mvn_phase_compute(const double* __restrict__ pac
   const double* in2[RT];
 #pragma unroll
   for (int r = 0; r < RT; ++r) {
-    const int idx = RT * rg + r;
+    const int idx = r * nRG + rg;      // the rows read by one load instruction are consecutive: distinct banks
     code[r] = (active && idx < nrows) ? rows[idx] : -1;
     if (MODE == 2) {
       in[r] = (code[r] < 0) ? sm.ZERO : sm.X1 + (code[r] >> 1) * DPS;
