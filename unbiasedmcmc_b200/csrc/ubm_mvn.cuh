@@ -90,10 +90,10 @@ inline void mvn_bind_device(MvnDevice* M, const double* dev) {
 
 enum { SL_IDLE = 0, SL_WAIT = 1, SL_INIT = 2, SL_SINGLE = 3, SL_COUPLED = 4 };
 #define MVN_MAXR 16
-#define MVN_T 384      // threads per CTA
-#define MVN_GT 256     // consumer (GEMM) threads: warps 0-7 (two per SM sub-partition); warps 8-11 produce the draws of the next step
+#define MVN_T 512      // threads per CTA
+#define MVN_GT 256     // consumer (GEMM) threads: warps 0-7 (two per SM sub-partition); warps 8-15 produce the draws of the next step
 #define MVN_CW 8       // consumer warps
-#define MVN_PW 4       // producer warps
+#define MVN_PW 8       // producer warps
 
 struct MvnSlots {   // per-slot scalars, in shared memory
   long long rep[MVN_MAXR], time[MVN_MAXR], tau[MVN_MAXR];
@@ -167,15 +167,19 @@ __device__ __forceinline__ double warp_butterfly(double v) {
   return v;
 }
 
-// Four consecutive standard normals of a replicate's N stream starting at index i0, executed by a whole warp
-// (lanes with nvalid <= 0 idle).  AS241's central branch is evaluated for all draws first; the ~15 % of draws in the
-// tails are finished in a separate lane-local loop so that the warp does not run both branches for every draw.
+// Standard normals i0 + 4 lane .. + 3 of a replicate's N stream, written to row[4 lane .. 4 lane + 3] (shared memory;
+// entries past nvalid are zeroed, lanes with nvalid <= 0 write nothing), executed by a whole warp.  AS241's central
+// branch is evaluated in place; the ~15 % of draws that fall in the tails are COMPACTED over the warp (ballot + rank),
+// so that the log/sqrt branch runs once per warp for up to 32 tail draws instead of once per tail draw of the
+// unluckiest lane.
 template <bool TAPE>
 __device__ __forceinline__ void draw_n4_warp(const RunParams& P, long long rep, unsigned long long i0, int nvalid,
-                                             double (&out)[4], bool* bad) {
+                                             double* __restrict__ row, int lane, bool* bad) {
   if (TAPE) {
+    if (nvalid > 0) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) out[c] = (c < nvalid) ? draw_n_at<true>(P, rep, i0 + c, bad) : 0.0;
+      for (int c = 0; c < 4; ++c) row[4 * lane + c] = (c < nvalid) ? draw_n_at<true>(P, rep, i0 + c, bad) : 0.0;
+    }
     return;
   }
   const uint64_t grep = (uint64_t)(P.rep_offset + rep);
@@ -193,23 +197,27 @@ __device__ __forceinline__ void draw_n4_warp(const RunParams& P, long long rep, 
       pr[2] = ubm_u01_53(A1.w[0], A1.w[1]); pr[3] = ubm_u01_53(A1.w[2], A1.w[3]);
     }
   }
-  unsigned pending = 0;
+  unsigned bal[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const double q = pr[c] - 0.5;
-    out[c] = 0.0;
-    if (c < nvalid) {
-      if (fabs(q) <= 0.425) out[c] = ubm_qnorm_central(q);
-      else pending |= 1u << c;
-    }
+    const bool valid = c < nvalid;
+    const bool tail = valid && !(fabs(q) <= 0.425);
+    if (nvalid > 0 && !tail) row[4 * lane + c] = valid ? ubm_qnorm_central(q) : 0.0;
+    bal[c] = __ballot_sync(0xffffffffu, tail);
   }
-  while (__any_sync(0xffffffffu, pending != 0)) {
-    if (pending) {
-      const int c = __ffs(pending) - 1;
-      pending &= pending - 1;
-      const double pc = (c == 0) ? pr[0] : (c == 1) ? pr[1] : (c == 2) ? pr[2] : pr[3];
-      const double val = ubm_qnorm_tail(pc, pc - 0.5);
-      if (c == 0) out[0] = val; else if (c == 1) out[1] = val; else if (c == 2) out[2] = val; else out[3] = val;
+  const int n0 = __popc(bal[0]), n1 = n0 + __popc(bal[1]), n2 = n1 + __popc(bal[2]), n3 = n2 + __popc(bal[3]);
+  for (int first = 0; first < n3; first += 32) {      // one pass unless more than 32 of the 4 x 32 draws are in the tails
+    const int i = first + lane;
+    const int c = (i < n0) ? 0 : (i < n1) ? 1 : (i < n2) ? 2 : 3;
+    const int rank = i - ((c == 0) ? 0 : (c == 1) ? n0 : (c == 2) ? n1 : n2);
+    const unsigned m = (c == 0) ? bal[0] : (c == 1) ? bal[1] : (c == 2) ? bal[2] : bal[3];
+    const int src = (i < n3) ? (int)__fns(m, 0, rank + 1) : 0;
+    const double p0 = __shfl_sync(0xffffffffu, pr[0], src), p1 = __shfl_sync(0xffffffffu, pr[1], src);
+    const double p2 = __shfl_sync(0xffffffffu, pr[2], src), p3 = __shfl_sync(0xffffffffu, pr[3], src);
+    if (i < n3) {
+      const double pc = (c == 0) ? p0 : (c == 1) ? p1 : (c == 2) ? p2 : p3;
+      row[4 * src + c] = ubm_qnorm_tail(pc, pc - 0.5);
     }
   }
 }
@@ -321,9 +329,10 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
   const double denom = (double)(P.m - P.k + 1);
   const unsigned FULL = 0xffffffffu;
   int cur = 0;
+  const int RB = min(2 * MVN_MAXR, 2 * ((MVN_GT / 2) / nPairs));   // rows per GEMM batch: one half-unit per consumer thread
 
 #ifdef UBM_MVN_TIMING
-  long long tacc[5] = {0, 0, 0, 0, 0}, tsteps = 0, tb[4] = {0, 0, 0, 0};
+  long long tacc[5] = {0, 0, 0, 0, 0}, tsteps = 0;
 #define TMARK(i) do { long long now_ = clock64(); tacc[i] += now_ - tprev; tprev = now_; } while (0)
 #else
 #define TMARK(i) do { } while (0)
@@ -580,81 +589,43 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
       // ---------------------------------------------------------------- phase B: proposals = x + in^T C_prop (in place)
       // and, for freshly fetched slots, x0 = init_mean + in^T init_chol (matrix read from global memory / L2)
       for (int pass = 0; pass < 2; ++pass) {
-        const int nrows = pass ? S.nI : S.nB;
-        if (nrows == 0) continue;   // uniform over the consumer group
-        const int* rows = pass ? S.rowsI : S.rowsB;
-        int code[4] = {-1, -1, -1, -1}, g = 0, rt = 4;
-        bool has = false;
-        double acc[4][4];
-        if (((nrows + 1) / 2) * nPairs * 2 <= MVN_GT) {
-          rt = 2;
-          int code2[2];
-          double acc2[2][4];
-          if (pass) mvn_phase_compute<2, 0>(M.packI, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code2, g, has, acc2);
-          else mvn_phase_compute<2, 0>(sm.packB, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code2, g, has, acc2);
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            code[r] = code2[r];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = acc2[r][c];
-          }
-        } else {
-          if (pass) mvn_phase_compute<4, 0>(M.packI, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
-          else mvn_phase_compute<4, 0>(sm.packB, sm, XIc, rows, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
-        }
-#ifdef UBM_MVN_TIMING
-        long long tq0 = clock64();
-#endif
-        consumer_bar();   // every read of this pass's inputs is done: overwrite them with the outputs
-#ifdef UBM_MVN_TIMING
-        long long tq1 = clock64(); tb[0] += tq0 - tprev; tb[1] += tq1 - tq0;
-#endif
-        if (has) {
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            if (r >= rt || code[r] < 0) continue;
-            const int s = code[r] >> 1, which = code[r] & 1;
-            const double* base = pass ? (M.init_mean + 4 * g) : ((which ? sm.X2 : sm.X1) + s * DPS + 4 * g);
-            double* outp = (which ? sm.V2 : XIc) + s * DPS + 4 * g;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) outp[c] = (4 * g + c < d) ? (base[c] + acc[r][c]) : 0.0;   // :40-44, :224-225
-          }
-        }
-      }
-#ifdef UBM_MVN_TIMING
-      long long tq2 = clock64();
-#endif
-      consumer_bar();
-#ifdef UBM_MVN_TIMING
-      tb[3] += clock64() - tq2;
-#endif
-      TMARK(2);
-      // ---------------------------------------------------------------- phase C: w = Cinv_pi^T (prop - mean), |w|^2
-      {
-        const int nrows = S.nC;
-        int g;
-        bool has;
-        if (((nrows + 1) / 2) * nPairs * 2 <= MVN_GT) {
-          int code[2];
+        const int ntot = pass ? S.nI : S.nB;
+        const int* rows_all = pass ? S.rowsI : S.rowsB;
+        const double* pack = pass ? M.packI : sm.packB;
+        for (int r0 = 0; r0 < ntot; r0 += RB) {     // uniform over the consumer group; one batch unless 2R rows are live
+          const int nrows = min(RB, ntot - r0);
+          int code[2], g;
+          bool has;
           double acc[2][4];
-          mvn_phase_compute<2, ZERO_MEAN ? 0 : 1>(sm.packC, sm, XIc, S.rowsC, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, g, has, acc);
+          mvn_phase_compute<2, 0>(pack, sm, XIc, rows_all + r0, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
+          consumer_bar();   // every read of this batch's input rows is done: overwrite them with the outputs
           if (has) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
               if (code[r] < 0) continue;
-              double t = 0.0;
+              const int s = code[r] >> 1, which = code[r] & 1;
+              const double* base = pass ? (M.init_mean + 4 * g) : ((which ? sm.X2 : sm.X1) + s * DPS + 4 * g);
+              double* outp = (which ? sm.V2 : XIc) + s * DPS + 4 * g;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) t = ubm_fma(acc[r][c], acc[r][c], t);
-              sm.TG[code[r] * 32 + g] = t;
+              for (int c = 0; c < 4; ++c) outp[c] = (4 * g + c < d) ? (base[c] + acc[r][c]) : 0.0;   // :40-44, :224-225
             }
           }
-        } else {
-          int code[4];
-          double acc[4][4];
-          mvn_phase_compute<4, ZERO_MEAN ? 0 : 1>(sm.packC, sm, XIc, S.rowsC, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, g, has, acc);
+        }
+      }
+      consumer_bar();
+      TMARK(2);
+      // ---------------------------------------------------------------- phase C: w = Cinv_pi^T (prop - mean), |w|^2
+      {
+        const int ntot = S.nC;
+        for (int r0 = 0; r0 < ntot; r0 += RB) {
+          const int nrows = min(RB, ntot - r0);
+          int code[2], g;
+          bool has;
+          double acc[2][4];
+          mvn_phase_compute<2, ZERO_MEAN ? 0 : 1>(sm.packC, sm, XIc, S.rowsC + r0, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, g, has, acc);
           if (has) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < 2; ++r) {
               if (code[r] < 0) continue;
               double t = 0.0;
 #pragma unroll
@@ -666,44 +637,46 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
       }
       TMARK(3);
     } else {
-      // ================================================================ PRODUCERS (warps 8-11): draws of the NEXT step
-      for (int s = warp - MVN_CW; s < R; s += MVN_PW) {
+      // ================================================================ PRODUCERS (warps 8-15): draws of the NEXT step
+      const int pw = warp - MVN_CW;
+      for (int s = pw; s < R; s += MVN_PW) {
         const int ph = S.phase[s];
         if (ph == SL_IDLE) continue;
         const long long rep = S.rep[s];
         const unsigned long long base = (ph == SL_WAIT) ? 0ull : ((ph == SL_INIT) ? (unsigned long long)(2 * d) : S.in[s] + d);
         bool bad = false;
-        double z[4];
         const int nvalid = (lane < nCG) ? d - 4 * lane : 0;
-        draw_n4_warp<TAPE>(P, rep, base + 4 * lane, nvalid, z, &bad);
-        if (lane < nCG) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) XIn[s * DPS + 4 * lane + c] = z[c];
+        draw_n4_warp<TAPE>(P, rep, base + 4 * lane, nvalid, XIn + s * DPS, lane, &bad);
+        if (ph == SL_WAIT)        // rinit of chain 2 (draw order: chain 1's d normals, then chain 2's)
+          draw_n4_warp<TAPE>(P, rep, base + d + 4 * lane, nvalid, sm.V2 + s * DPS, lane, &bad);
+        if (bad) S.bad[s] = 1;
+      }
+      // log-uniform rings of this warp's slots (8 lanes per slot): keep them at least 4 draws ahead of the consumers
+      // (they use at most 2 per step)
+      {
+        const int s = pw + (lane >> 3) * MVN_PW, l8 = lane & 7;
+        const bool on = s < R && S.phase[s] != SL_IDLE;
+        unsigned long long pu = 0, target = 0;
+        bool bad = false;
+        if (on) {
+          pu = S.pu[s]; target = S.iu[s] + 6;
+          const unsigned long long idx = pu + l8;
+          if (idx < target) sm.LU[s * 8 + (int)(idx & 7ull)] = ubm_log(draw_u_at<TAPE>(P, S.rep[s], idx, &bad));
         }
-        if (ph == SL_WAIT) {      // rinit of chain 2 (draw order: chain 1's d normals, then chain 2's)
-          draw_n4_warp<TAPE>(P, rep, base + d + 4 * lane, nvalid, z, &bad);
-          if (lane < nCG) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) sm.V2[s * DPS + 4 * lane + c] = z[c];
-          }
-        }
-        // log-uniform ring: keep it at least 4 draws ahead of the consumers (they use at most 2 per step)
-        const unsigned long long pu = S.pu[s], target = S.iu[s] + 6;
-        const unsigned long long idx = pu + lane;
-        if (lane < 8 && idx < target) sm.LU[s * 8 + (int)(idx & 7ull)] = ubm_log(draw_u_at<TAPE>(P, rep, idx, &bad));
         __syncwarp();
-        if (lane == 0 && target > pu) S.pu[s] = target;
+        if (on && l8 == 0 && target > pu) S.pu[s] = target;
         if (bad) S.bad[s] = 1;
       }
     }
     __syncthreads();      // CTA barrier 2: step computed, draws of the next step in place
+    TMARK(4);
     cur ^= 1;
   }
 #ifdef UBM_MVN_TIMING
   if (tid == 0 && blockIdx.x == 0)
-    printf("mvn timing (cycles/step, block 0): steps %lld slot %.0f A+coupling %.0f B %.0f C %.0f | B: compute(thread0) %.0f bar %.0f endbar %.0f\n", tsteps,
+    printf("mvn timing (cycles/step, block 0, thread 0): steps %lld slot %.0f A+coupling %.0f B %.0f C %.0f wait-for-producers %.0f\n", tsteps,
            (double)tacc[0] / tsteps, (double)tacc[1] / tsteps, (double)tacc[2] / tsteps, (double)tacc[3] / tsteps,
-           (double)tb[0] / tsteps, (double)tb[1] / tsteps, (double)tb[3] / tsteps);
+           (double)tacc[4] / tsteps);
 #endif
 }
 
@@ -717,10 +690,8 @@ inline int mvn_launch(const MvnDevice& M, const RunParams& P, bool tape, int nsm
   const int acc_per_slot = (P.mode == MODE_ESTIMATOR) ? 2 * dimh : 0;
   int R = MVN_MAXR;
   while (R > 1 && mvn_smem_bytes(M.packLen, M.DPS, R, acc_per_slot) > budget) --R;
-  // every phase must fit one unit per consumer thread: 2-row tiles over at most 2R rows
-  while (R > 1 && R * M.nPairs > MVN_GT) --R;
   size_t smem = mvn_smem_bytes(M.packLen, M.DPS, R, acc_per_slot);
-  if (smem > budget || R * M.nPairs > MVN_GT) { *err = "mvn: d too large for shared memory"; return UBM_ERR_UNSUPPORTED; }
+  if (smem > budget || M.nPairs > MVN_GT / 2) { *err = "mvn: d too large for shared memory"; return UBM_ERR_UNSUPPORTED; }
   int64_t need = (P.nrep + R - 1) / R;
   int grid = (int)std::min<int64_t>(nsm, need);
   void (*kern)(const MvnDevice, const RunParams, const int, const int);
