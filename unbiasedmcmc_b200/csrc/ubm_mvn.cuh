@@ -107,40 +107,54 @@ struct MvnSlots {   // per-slot scalars, in shared memory
 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// One GEMM stream: RT input rows (smem, 16-byte aligned) against rows [k0, k1) of column group g of a packed matrix:
-// acc[r][c] += sum_{k0 <= k < k1} in_r[k] M[k][4g+c], sequential in k (k0, k1 even).  Operands for k+2, k+3 are
-// requested while k, k+1 are computed (reads run at most 32 bytes past the group / row, inside the padding).
+// One GEMM half-unit: RT input rows (smem, 16-byte aligned) against two consecutive row segments of a packed matrix,
+// executed as ONE loop so that the lanes of a warp — whose segments differ — run the same instruction stream:
+//   segment 1: n1 two-row steps of column group g1 from k = 0          -> first[r][c]
+//   segment 2: n2 two-row steps of column group g2 from k = k2 (even)  -> acc[r][c]
+// each sum sequential in k.  Operands of the next step are requested while this one is computed (reads run at most 32
+// bytes past a group / row, inside the padding).
 // MODE 0: plain input; 1: input minus `aux` vector (the target mean); 2: input = in2_r[k] - in_r[k] (x2 - x1).
 template <int RT, int MODE>
-__device__ __forceinline__ void mvn_range(const double* __restrict__ pack, int g, int k0, int k1,
-                                          const double* const* in, const double* const* in2,
-                                          const double* __restrict__ aux, double (&acc)[RT][4]) {
-  const double* mp = pack + mvn_group_off(g) + 4 * k0;
+__device__ __forceinline__ void mvn_unit(const double* __restrict__ pack, int g1, int n1, int g2, int k2, int n2,
+                                         const double* const* in, const double* const* in2,
+                                         const double* __restrict__ aux, double (&first)[RT][4], double (&acc)[RT][4]) {
+  const int n = n1 + n2;
+  const double* const mp2 = pack + mvn_group_off(g2) + 4 * k2;
+  const double* mp = (n1 > 0) ? pack + mvn_group_off(g1) : mp2;
+  int k = (n1 > 0) ? 0 : k2;
   double2 m0 = *reinterpret_cast<const double2*>(mp), m1 = *reinterpret_cast<const double2*>(mp + 2);
   double2 m2 = *reinterpret_cast<const double2*>(mp + 4), m3 = *reinterpret_cast<const double2*>(mp + 6);
   double2 v[RT], w[RT];
 #pragma unroll
   for (int r = 0; r < RT; ++r) {
-    v[r] = *reinterpret_cast<const double2*>(in[r] + k0);
-    if (MODE == 2) w[r] = *reinterpret_cast<const double2*>(in2[r] + k0);
+    v[r] = *reinterpret_cast<const double2*>(in[r] + k);
+    if (MODE == 2) w[r] = *reinterpret_cast<const double2*>(in2[r] + k);
   }
   double2 mu = make_double2(0.0, 0.0);
-  if (MODE == 1) mu = *reinterpret_cast<const double2*>(aux + k0);
+  if (MODE == 1) mu = *reinterpret_cast<const double2*>(aux + k);
 #pragma unroll 2
-  for (int k = k0; k < k1; k += 2) {
-    mp += 8;
+  for (int it = 0; it < n; ++it) {
+    const bool jump = (it + 1 == n1);
+    mp = jump ? mp2 : mp + 8;
+    k = jump ? k2 : k + 2;
     const double2 n0 = *reinterpret_cast<const double2*>(mp);
-    const double2 n1 = *reinterpret_cast<const double2*>(mp + 2);
-    const double2 n2 = *reinterpret_cast<const double2*>(mp + 4);
+    const double2 nn1 = *reinterpret_cast<const double2*>(mp + 2);
+    const double2 nn2 = *reinterpret_cast<const double2*>(mp + 4);
     const double2 n3 = *reinterpret_cast<const double2*>(mp + 6);
     double2 vn[RT], wn[RT];
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
-      vn[r] = *reinterpret_cast<const double2*>(in[r] + k + 2);
-      if (MODE == 2) wn[r] = *reinterpret_cast<const double2*>(in2[r] + k + 2);
+      vn[r] = *reinterpret_cast<const double2*>(in[r] + k);
+      if (MODE == 2) wn[r] = *reinterpret_cast<const double2*>(in2[r] + k);
     }
     double2 mun = make_double2(0.0, 0.0);
-    if (MODE == 1) mun = *reinterpret_cast<const double2*>(aux + k + 2);
+    if (MODE == 1) mun = *reinterpret_cast<const double2*>(aux + k);
+    if (it == n1 && it > 0) {      // segment 1 is complete (a few lanes, once per unit)
+#pragma unroll
+      for (int r = 0; r < RT; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { first[r][c] = acc[r][c]; acc[r][c] = 0.0; }
+    }
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       double2 x = v[r];
@@ -155,9 +169,15 @@ __device__ __forceinline__ void mvn_range(const double* __restrict__ pack, int g
       acc[r][2] = ubm_fma(x.y, m3.x, acc[r][2]);
       acc[r][3] = ubm_fma(x.y, m3.y, acc[r][3]);
     }
-    m0 = n0; m1 = n1; m2 = n2; m3 = n3; mu = mun;
+    m0 = n0; m1 = nn1; m2 = nn2; m3 = n3; mu = mun;
 #pragma unroll
     for (int r = 0; r < RT; ++r) { v[r] = vn[r]; if (MODE == 2) w[r] = wn[r]; }
+  }
+  if (n1 > 0 && n2 == 0) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { first[r][c] = acc[r][c]; acc[r][c] = 0.0; }
   }
 }
 
@@ -239,6 +259,9 @@ __host__ __device__ inline size_t mvn_smem_bytes(int packLen, int DPS, int R, in
          sizeof(MvnSlots) + 16;
 }
 
+#ifdef UBM_MVN_TIMING
+static __device__ long long g_mvn_tloop;      // debug builds only: cycles thread (0,0) spent inside the GEMM loops
+#endif
 // GEMM phase over a compact row list (row code = slot * 2 + which).  Work is cut into BALANCED HALF-UNITS: column
 // group gA = pr (K_A = 4 pr + 4 rows) is paired with gB = nCG-1-pr (K_B rows, K_A + K_B = 2 half), and the long
 // column group is summed in two segments [0, K_B - half) and [K_B - half, K_B) — the engine's canonical order
@@ -276,14 +299,18 @@ __device__ __forceinline__ void mvn_phase_compute(const double* __restrict__ pac
   double accA[RT][4], accB[RT][4];
 #pragma unroll
   for (int r = 0; r < RT; ++r) { accA[r][0] = accA[r][1] = accA[r][2] = accA[r][3] = 0.0; accB[r][0] = accB[r][1] = accB[r][2] = accB[r][3] = 0.0; }
-  if (active) {
-    if (h == 0) {
-      if (!middle) mvn_range<RT, MODE>(pack, gA, 0, KA, in, in2, aux, accA);
-      if (ks > 0) mvn_range<RT, MODE>(pack, gB, 0, ks, in, in2, aux, accB);
-    } else {
-      mvn_range<RT, MODE>(pack, gB, ks, KB, in, in2, aux, accB);
-    }
+#ifdef UBM_MVN_TIMING
+  const long long tl0_ = clock64();
+#endif
+  {
+    // h = 0: all of gA, then the first segment [0, ks) of gB; h = 1: the second segment [ks, KB) of gB
+    const int n1 = (active && h == 0 && !middle) ? KA / 2 : 0;
+    const int n2 = !active ? 0 : (h == 0 ? ks / 2 : (KB - ks) / 2);
+    mvn_unit<RT, MODE>(pack, gA, n1, gB, h ? ks : 0, n2, in, in2, aux, accA, accB);
   }
+#ifdef UBM_MVN_TIMING
+  if (threadIdx.x == 0 && blockIdx.x == 0) g_mvn_tloop += clock64() - tl0_;
+#endif
 #pragma unroll
   for (int r = 0; r < RT; ++r)
 #pragma unroll
@@ -591,13 +618,14 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
       for (int pass = 0; pass < 2; ++pass) {
         const int ntot = pass ? S.nI : S.nB;
         const int* rows_all = pass ? S.rowsI : S.rowsB;
-        const double* pack = pass ? M.packI : sm.packB;
         for (int r0 = 0; r0 < ntot; r0 += RB) {     // uniform over the consumer group; one batch unless 2R rows are live
           const int nrows = min(RB, ntot - r0);
           int code[2], g;
           bool has;
           double acc[2][4];
-          mvn_phase_compute<2, 0>(pack, sm, XIc, rows_all + r0, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
+          // two call sites so that the matrix loads are LDS (shared) resp. LDG (global), not generic loads
+          if (pass == 0) mvn_phase_compute<2, 0>(sm.packB, sm, XIc, rows_all + r0, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
+          else mvn_phase_compute<2, 0>(M.packI, sm, XIc, rows_all + r0, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
           consumer_bar();   // every read of this batch's input rows is done: overwrite them with the outputs
           if (has) {
 #pragma unroll
@@ -674,9 +702,9 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
   }
 #ifdef UBM_MVN_TIMING
   if (tid == 0 && blockIdx.x == 0)
-    printf("mvn timing (cycles/step, block 0, thread 0): steps %lld slot %.0f A+coupling %.0f B %.0f C %.0f wait-for-producers %.0f\n", tsteps,
+    printf("mvn timing (cycles/step, block 0, thread 0): steps %lld slot %.0f A+coupling %.0f B %.0f C %.0f wait-for-producers %.0f | GEMM loops %.0f\n", tsteps,
            (double)tacc[0] / tsteps, (double)tacc[1] / tsteps, (double)tacc[2] / tsteps, (double)tacc[3] / tsteps,
-           (double)tacc[4] / tsteps);
+           (double)tacc[4] / tsteps, (double)g_mvn_tloop / tsteps);
 #endif
 }
 
