@@ -134,10 +134,10 @@ struct MvnModel {
 
   // Canonical summation order of y_j = sum_{i<=j} v_i U[i,j] (the reference leaves it to Eigen): sequential fma in i,
   // except that for the long columns the range is cut once — columns of the 4-column group g with K_g = 4g+4 rows
-  // longer than half = 2 (ceil(d/4) + 1) are summed as (sum over i < K_g - half) + (sum over i >= K_g - half).
+  // longer than half = 4 floor((ceil(d/4) + 1) / 2) + 2 are summed as (sum over i < K_g - half) + (sum over i >= K_g - half).
   // This lets the device split every long column between two threads of equal work (ubm_mvn.cuh).
   void vec_times_upper(const double* v, const std::vector<double>& U, double* out) const {
-    const int nCG = (d + 3) / 4, half = 2 * (nCG + 1);
+    const int nCG = (d + 3) / 4, half = 4 * ((nCG + 1) / 2) + 2;
     for (int j = 0; j < d; ++j) {
       const int Kg = 4 * (j / 4) + 4;
       const int ks = (Kg > half) ? Kg - half : 0;

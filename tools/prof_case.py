@@ -13,6 +13,9 @@ eng = Engine(0)
 if which == "c2":
     nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 16
     res = eng.sample_unbiasedestimator(cases.c2_model(100), R.Draws(seed=1), k=400, m=2000, lag=1, nrep=nrep, want_bins=False)
+elif which == "c2bench":      # the bench workload's k, m on one wave of replicates
+    nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 16
+    res = eng.sample_unbiasedestimator(cases.c2_model(100), R.Draws(seed=1), k=2000, m=10000, lag=1, nrep=nrep, want_bins=False)
 elif which == "c2meet":
     nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 16
     res = eng.sample_meetingtime(cases.c2_model(100), R.Draws(seed=1), lag=1, nrep=nrep)

@@ -49,15 +49,21 @@ struct MvnDevice {
   size_t offs[6];              // host-side: offsets inside the blob
 };
 
-// column group g holds rows k = 0 .. 4g+3 (rows >= d and entries below the diagonal are zero), 4 doubles per row
-__host__ __device__ __forceinline__ int mvn_group_off(int g) { return 8 * g * (g + 1) + 2 * g; }
-__host__ __device__ __forceinline__ int mvn_pack_len(int nCG) { return mvn_group_off(nCG - 1) + 16 * nCG + 16; }
+// column group g holds rows k = 0 .. 4g+3 (rows >= d and entries below the diagonal are zero), 4 doubles per row.
+// Pads: group g starts 4 g (+2 for the long groups g >= nPairs) doubles late, so that the 16-byte words read by one
+// quarter-warp (a short group gA = pr and its partner gB = nCG-1-pr, at the same loop step) fall into different banks.
+__host__ __device__ __forceinline__ int mvn_group_off(int g, int nPairs) { return 8 * g * (g + 1) + 4 * g + (g >= nPairs ? 2 : 0); }
+__host__ __device__ __forceinline__ int mvn_pack_len(int nCG, int nPairs) { return mvn_group_off(nCG - 1, nPairs) + 16 * nCG + 16; }
+// The canonical cut of the long columns (oracle: vec_times_upper): K_g > half is summed as [0, K_g - half) + [K_g - half, K_g).
+// half == 2 (mod 4) keeps the two streams of a column group, `half` rows apart, in different banks.
+__host__ __device__ __forceinline__ int mvn_half(int nCG) { return 4 * ((nCG + 1) / 2) + 2; }
 
 inline void mvn_pack_matrix(const double* Ucm, int d, int nCG, std::vector<double>* blob) {
   size_t base = blob->size();
-  blob->resize(base + mvn_pack_len(nCG), 0.0);
+  const int nPairs = (nCG + 1) / 2;
+  blob->resize(base + mvn_pack_len(nCG, nPairs), 0.0);
   for (int g = 0; g < nCG; ++g) {
-    double* p = blob->data() + base + mvn_group_off(g);
+    double* p = blob->data() + base + mvn_group_off(g, nPairs);
     for (int k = 0; k < 4 * g + 4; ++k)
       for (int c = 0; c < 4; ++c) {
         int j = 4 * g + c;
@@ -68,13 +74,17 @@ inline void mvn_pack_matrix(const double* Ucm, int d, int nCG, std::vector<doubl
 
 inline void mvn_pack_host(const ubm_model_mvn* s, MvnDevice* M, std::vector<double>* blob) {
   const int d = s->d;
-  M->d = d; M->nCG = (d + 3) / 4; M->DP = 4 * M->nCG; M->DPS = M->DP + 2; M->nPairs = (M->nCG + 1) / 2;
+  M->d = d; M->nCG = (d + 3) / 4; M->DP = 4 * M->nCG; M->nPairs = (M->nCG + 1) / 2;
+  // row stride (in 16-byte words) == 2 (mod 8): four consecutive rows plus the same rows an odd number of words further
+  // on (the partner stream) cover the eight bank groups exactly once.  Reads of the GEMM prefetch may run 16 bytes past a
+  // row: that is the next row or the next array, never used.
+  M->DPS = M->DP + 2 * ((((2 - 2 * M->nCG) % 8) + 8) % 8);
   M->zero_mean = 1;
   for (int j = 0; j < d; ++j) if (s->mean_pi[j] != 0.0) M->zero_mean = 0;
   double halflogdet = 0.0;
   for (int j = 0; j < d; ++j) halflogdet = halflogdet + ubm_log(s->chol_inv_pi[(size_t)j * d + j]);
   M->cst = -(-halflogdet) - (d * 0.9189385);     // truncated constant kept verbatim (src/mvnorm.cpp:75)
-  M->packLen = mvn_pack_len(M->nCG);
+  M->packLen = mvn_pack_len(M->nCG, M->nPairs);
   blob->clear();
   M->offs[0] = blob->size(); for (int j = 0; j < M->DPS; ++j) blob->push_back(j < d ? s->mean_pi[j] : 0.0);
   M->offs[1] = blob->size(); for (int j = 0; j < M->DPS; ++j) blob->push_back(j < d ? s->init_mean[j] : 0.0);
@@ -90,10 +100,11 @@ inline void mvn_bind_device(MvnDevice* M, const double* dev) {
 
 enum { SL_IDLE = 0, SL_WAIT = 1, SL_INIT = 2, SL_SINGLE = 3, SL_COUPLED = 4 };
 #define MVN_MAXR 16
-#define MVN_T 512      // threads per CTA
-#define MVN_GT 256     // consumer (GEMM) threads: warps 0-7 (two per SM sub-partition); warps 8-15 produce the draws of the next step
-#define MVN_CW 8       // consumer warps
-#define MVN_PW 8       // producer warps
+#define MVN_RT 2       // rows per GEMM register tile (x 4 columns)
+#define MVN_CW 8       // consumer warps: warps 0-7 (two per SM sub-partition, so that one fills the other's DFMA issue gaps)
+#define MVN_PW 8       // producer warps: warps 8-15 produce the draws of the next step
+#define MVN_GT (32 * MVN_CW)               // consumer (GEMM) threads
+#define MVN_T (32 * (MVN_CW + MVN_PW))     // threads per CTA
 
 struct MvnSlots {   // per-slot scalars, in shared memory
   long long rep[MVN_MAXR], time[MVN_MAXR], tau[MVN_MAXR];
@@ -105,73 +116,91 @@ struct MvnSlots {   // per-slot scalars, in shared memory
   int exhausted;
 };
 
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(MVN_GT) : "memory"); }
+
+// Operands of one two-row step of a half-unit: 8 matrix entries (rows k, k+1 of a 4-column group) and the RT row pairs.
+template <int RT, int MODE>
+struct MvnOperands {
+  double2 m0, m1, m2, m3, v[RT], w[RT], mu;
+  __device__ __forceinline__ void load(const double* __restrict__ mp, const double* const* in, const double* const* in2,
+                                       const double* __restrict__ aux, int k) {
+    m0 = *reinterpret_cast<const double2*>(mp); m1 = *reinterpret_cast<const double2*>(mp + 2);
+    m2 = *reinterpret_cast<const double2*>(mp + 4); m3 = *reinterpret_cast<const double2*>(mp + 6);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      v[r] = *reinterpret_cast<const double2*>(in[r] + k);
+      if (MODE == 2) w[r] = *reinterpret_cast<const double2*>(in2[r] + k);
+    }
+    if (MODE == 1) mu = *reinterpret_cast<const double2*>(aux + k);
+  }
+  __device__ __forceinline__ void fma_into(double (&acc)[RT][4]) const {
+    double2 x[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      x[r] = v[r];
+      if (MODE == 1) { x[r].x = x[r].x - mu.x; x[r].y = x[r].y - mu.y; }
+      if (MODE == 2) { x[r].x = w[r].x - x[r].x; x[r].y = w[r].y - x[r].y; }
+    }
+    // row k for all accumulators, then row k+1: dependent fma pairs are 4 RT instructions apart
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      acc[r][0] = ubm_fma(x[r].x, m0.x, acc[r][0]);
+      acc[r][1] = ubm_fma(x[r].x, m0.y, acc[r][1]);
+      acc[r][2] = ubm_fma(x[r].x, m1.x, acc[r][2]);
+      acc[r][3] = ubm_fma(x[r].x, m1.y, acc[r][3]);
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      acc[r][0] = ubm_fma(x[r].y, m2.x, acc[r][0]);
+      acc[r][1] = ubm_fma(x[r].y, m2.y, acc[r][1]);
+      acc[r][2] = ubm_fma(x[r].y, m3.x, acc[r][2]);
+      acc[r][3] = ubm_fma(x[r].y, m3.y, acc[r][3]);
+    }
+  }
+};
 
 // One GEMM half-unit: RT input rows (smem, 16-byte aligned) against two consecutive row segments of a packed matrix,
 // executed as ONE loop so that the lanes of a warp — whose segments differ — run the same instruction stream:
-//   segment 1: n1 two-row steps of column group g1 from k = 0          -> first[r][c]
+//   segment 1: n1 (even) two-row steps of column group g1 from k = 0   -> first[r][c]
 //   segment 2: n2 two-row steps of column group g2 from k = k2 (even)  -> acc[r][c]
-// each sum sequential in k.  Operands of the next step are requested while this one is computed (reads run at most 32
-// bytes past a group / row, inside the padding).
+// each sum sequential in k.  The loop is unrolled by two steps with two operand sets (ping-pong): the operands of the
+// next step are requested while this one is computed, without register copies (reads run at most 32 bytes past a
+// group / row: padding, the next row or the next array, never used).
 // MODE 0: plain input; 1: input minus `aux` vector (the target mean); 2: input = in2_r[k] - in_r[k] (x2 - x1).
 template <int RT, int MODE>
-__device__ __forceinline__ void mvn_unit(const double* __restrict__ pack, int g1, int n1, int g2, int k2, int n2,
+__device__ __forceinline__ void mvn_unit(const double* __restrict__ pack, int nPairs, int g1, int n1, int g2, int k2, int n2,
                                          const double* const* in, const double* const* in2,
                                          const double* __restrict__ aux, double (&first)[RT][4], double (&acc)[RT][4]) {
   const int n = n1 + n2;
-  const double* const mp2 = pack + mvn_group_off(g2) + 4 * k2;
-  const double* mp = (n1 > 0) ? pack + mvn_group_off(g1) : mp2;
+  const double* const mp2 = pack + mvn_group_off(g2, nPairs) + 4 * k2;
+  const double* mp = (n1 > 0) ? pack + mvn_group_off(g1, nPairs) : mp2;
   int k = (n1 > 0) ? 0 : k2;
-  double2 m0 = *reinterpret_cast<const double2*>(mp), m1 = *reinterpret_cast<const double2*>(mp + 2);
-  double2 m2 = *reinterpret_cast<const double2*>(mp + 4), m3 = *reinterpret_cast<const double2*>(mp + 6);
-  double2 v[RT], w[RT];
-#pragma unroll
-  for (int r = 0; r < RT; ++r) {
-    v[r] = *reinterpret_cast<const double2*>(in[r] + k);
-    if (MODE == 2) w[r] = *reinterpret_cast<const double2*>(in2[r] + k);
-  }
-  double2 mu = make_double2(0.0, 0.0);
-  if (MODE == 1) mu = *reinterpret_cast<const double2*>(aux + k);
-#pragma unroll 2
-  for (int it = 0; it < n; ++it) {
-    const bool jump = (it + 1 == n1);
-    mp = jump ? mp2 : mp + 8;
-    k = jump ? k2 : k + 2;
-    const double2 n0 = *reinterpret_cast<const double2*>(mp);
-    const double2 nn1 = *reinterpret_cast<const double2*>(mp + 2);
-    const double2 nn2 = *reinterpret_cast<const double2*>(mp + 4);
-    const double2 n3 = *reinterpret_cast<const double2*>(mp + 6);
-    double2 vn[RT], wn[RT];
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      vn[r] = *reinterpret_cast<const double2*>(in[r] + k);
-      if (MODE == 2) wn[r] = *reinterpret_cast<const double2*>(in2[r] + k);
-    }
-    double2 mun = make_double2(0.0, 0.0);
-    if (MODE == 1) mun = *reinterpret_cast<const double2*>(aux + k);
+  MvnOperands<RT, MODE> A, B;
+  A.load(mp, in, in2, aux, k);
+  int it = 0;
+  for (; it + 1 < n; it += 2) {
     if (it == n1 && it > 0) {      // segment 1 is complete (a few lanes, once per unit)
 #pragma unroll
       for (int r = 0; r < RT; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) { first[r][c] = acc[r][c]; acc[r][c] = 0.0; }
     }
+    B.load(mp + 8, in, in2, aux, k + 2);                 // step it + 1 (odd: never the first of segment 2)
+    A.fma_into(acc);
+    const bool jump = (it + 2 == n1);
+    mp = jump ? mp2 : mp + 16;
+    k = jump ? k2 : k + 4;
+    A.load(mp, in, in2, aux, k);                         // step it + 2
+    B.fma_into(acc);
+  }
+  if (it < n) {                                          // odd number of steps: the last one is in A
+    if (it == n1 && it > 0) {
 #pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      double2 x = v[r];
-      if (MODE == 1) { x.x = x.x - mu.x; x.y = x.y - mu.y; }
-      if (MODE == 2) { x.x = w[r].x - x.x; x.y = w[r].y - x.y; }
-      acc[r][0] = ubm_fma(x.x, m0.x, acc[r][0]);
-      acc[r][1] = ubm_fma(x.x, m0.y, acc[r][1]);
-      acc[r][2] = ubm_fma(x.x, m1.x, acc[r][2]);
-      acc[r][3] = ubm_fma(x.x, m1.y, acc[r][3]);
-      acc[r][0] = ubm_fma(x.y, m2.x, acc[r][0]);
-      acc[r][1] = ubm_fma(x.y, m2.y, acc[r][1]);
-      acc[r][2] = ubm_fma(x.y, m3.x, acc[r][2]);
-      acc[r][3] = ubm_fma(x.y, m3.y, acc[r][3]);
+      for (int r = 0; r < RT; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { first[r][c] = acc[r][c]; acc[r][c] = 0.0; }
     }
-    m0 = n0; m1 = nn1; m2 = nn2; m3 = n3; mu = mun;
-#pragma unroll
-    for (int r = 0; r < RT; ++r) { v[r] = vn[r]; if (MODE == 2) w[r] = wn[r]; }
+    A.fma_into(acc);
   }
   if (n1 > 0 && n2 == 0) {
 #pragma unroll
@@ -279,7 +308,7 @@ __device__ __forceinline__ void mvn_phase_compute(const double* __restrict__ pac
   const int h = u & 1, ur = u >> 1;
   const int pr = active ? ur / nRG : 0, rg = active ? ur - pr * nRG : 0;
   const int gA = pr, gB = nCG - 1 - pr;
-  const int KA = 4 * gA + 4, KB = 4 * gB + 4, half = 2 * (nCG + 1);
+  const int KA = 4 * gA + 4, KB = 4 * gB + 4, half = mvn_half(nCG);
   const bool middle = (gA == gB);
   const int ks = (KB > half) ? KB - half : 0;
   const double* in[RT];
@@ -306,7 +335,7 @@ __device__ __forceinline__ void mvn_phase_compute(const double* __restrict__ pac
     // h = 0: all of gA, then the first segment [0, ks) of gB; h = 1: the second segment [ks, KB) of gB
     const int n1 = (active && h == 0 && !middle) ? KA / 2 : 0;
     const int n2 = !active ? 0 : (h == 0 ? ks / 2 : (KB - ks) / 2);
-    mvn_unit<RT, MODE>(pack, gA, n1, gB, h ? ks : 0, n2, in, in2, aux, accA, accB);
+    mvn_unit<RT, MODE>(pack, nPairs, gA, n1, gB, h ? ks : 0, n2, in, in2, aux, accA, accB);
   }
 #ifdef UBM_MVN_TIMING
   if (threadIdx.x == 0 && blockIdx.x == 0) g_mvn_tloop += clock64() - tl0_;
@@ -356,7 +385,7 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
   const double denom = (double)(P.m - P.k + 1);
   const unsigned FULL = 0xffffffffu;
   int cur = 0;
-  const int RB = min(2 * MVN_MAXR, 2 * ((MVN_GT / 2) / nPairs));   // rows per GEMM batch: one half-unit per consumer thread
+  const int RB = min(2 * MVN_MAXR, MVN_RT * ((MVN_GT / 2) / nPairs));   // rows per GEMM batch: one half-unit per consumer thread
 
 #ifdef UBM_MVN_TIMING
   long long tacc[5] = {0, 0, 0, 0, 0}, tsteps = 0;
@@ -375,7 +404,8 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
     // finishes the step just computed (densities -> accept/reject -> state/estimator update) and runs the slot state
     // machine (finish / write-out / fetch the next replicate).  No random-number work: uniforms come from the ring.
     int my_active = 0;
-    for (int s = warp; s < R; s += nwarp) {
+    // one slot per warp; slots beyond the warp count go to the producer warps (they are not on the critical path)
+    for (int s = warp; s < R; s = (s < nwarp && warp >= MVN_CW) ? nwarp + warp - MVN_CW : R) {
       int ph = S.phase[s];
       long long rep = S.rep[s];
       long long time = S.time[s];
@@ -541,14 +571,14 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
       const int nA = S.nA;
       // ---------------------------------------------------------------- phase A: z = -((x2 - x1)^T Cinv_prop) -> V2, |z|^2
       if (nA > 0) {
-        {
-          int code[2], g;
+        for (int r0 = 0; r0 < nA; r0 += RB) {
+          int code[MVN_RT], g;
           bool has;
-          double acc[2][4];
-          mvn_phase_compute<2, 2>(sm.packA, sm, XIc, S.rowsA, nA, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
+          double acc[MVN_RT][4];
+          mvn_phase_compute<MVN_RT, 2>(sm.packA, sm, XIc, S.rowsA + r0, min(RB, nA - r0), DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
           if (has) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
+            for (int r = 0; r < MVN_RT; ++r) {
               if (code[r] < 0) continue;
               const int s = code[r] >> 1;
               double t = 0.0;
@@ -620,16 +650,16 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
         const int* rows_all = pass ? S.rowsI : S.rowsB;
         for (int r0 = 0; r0 < ntot; r0 += RB) {     // uniform over the consumer group; one batch unless 2R rows are live
           const int nrows = min(RB, ntot - r0);
-          int code[2], g;
+          int code[MVN_RT], g;
           bool has;
-          double acc[2][4];
+          double acc[MVN_RT][4];
           // two call sites so that the matrix loads are LDS (shared) resp. LDG (global), not generic loads
-          if (pass == 0) mvn_phase_compute<2, 0>(sm.packB, sm, XIc, rows_all + r0, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
-          else mvn_phase_compute<2, 0>(M.packI, sm, XIc, rows_all + r0, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
+          if (pass == 0) mvn_phase_compute<MVN_RT, 0>(sm.packB, sm, XIc, rows_all + r0, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
+          else mvn_phase_compute<MVN_RT, 0>(M.packI, sm, XIc, rows_all + r0, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
           consumer_bar();   // every read of this batch's input rows is done: overwrite them with the outputs
           if (has) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
+            for (int r = 0; r < MVN_RT; ++r) {
               if (code[r] < 0) continue;
               const int s = code[r] >> 1, which = code[r] & 1;
               const double* base = pass ? (M.init_mean + 4 * g) : ((which ? sm.X2 : sm.X1) + s * DPS + 4 * g);
@@ -647,13 +677,13 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
         const int ntot = S.nC;
         for (int r0 = 0; r0 < ntot; r0 += RB) {
           const int nrows = min(RB, ntot - r0);
-          int code[2], g;
+          int code[MVN_RT], g;
           bool has;
-          double acc[2][4];
-          mvn_phase_compute<2, ZERO_MEAN ? 0 : 1>(sm.packC, sm, XIc, S.rowsC + r0, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, g, has, acc);
+          double acc[MVN_RT][4];
+          mvn_phase_compute<MVN_RT, ZERO_MEAN ? 0 : 1>(sm.packC, sm, XIc, S.rowsC + r0, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, g, has, acc);
           if (has) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
+            for (int r = 0; r < MVN_RT; ++r) {
               if (code[r] < 0) continue;
               double t = 0.0;
 #pragma unroll

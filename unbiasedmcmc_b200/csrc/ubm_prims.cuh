@@ -52,7 +52,7 @@ __global__ void prim_scalar_coupling_kernel(const RunParams P, int mode, double 
 // y_j = sum_{i <= j} v_i U[i, j], U column-major upper triangular, in the engine's canonical order (sequential fma,
 // long columns cut once at K_g - half; see ubm_mvn.cuh / oracle_models.hpp: vec_times_upper)
 __device__ inline void prim_vec_times_upper(const double* v, const double* __restrict__ U, int d, double* out) {
-  const int nCG = (d + 3) / 4, half = 2 * (nCG + 1);
+  const int nCG = (d + 3) / 4, half = 4 * ((nCG + 1) / 2) + 2;
   for (int j = 0; j < d; ++j) {
     const int Kg = 4 * (j / 4) + 4;
     const int ks = (Kg > half) ? Kg - half : 0;
