@@ -100,9 +100,15 @@ inline void mvn_bind_device(MvnDevice* M, const double* dev) {
 
 enum { SL_IDLE = 0, SL_WAIT = 1, SL_INIT = 2, SL_SINGLE = 3, SL_COUPLED = 4 };
 #define MVN_MAXR 16
+#ifndef MVN_RT
 #define MVN_RT 2       // rows per GEMM register tile (x 4 columns)
+#endif
+#ifndef MVN_CW
 #define MVN_CW 8       // consumer warps: warps 0-7 (two per SM sub-partition, so that one fills the other's DFMA issue gaps)
+#endif
+#ifndef MVN_PW
 #define MVN_PW 8       // producer warps: warps 8-15 produce the draws of the next step
+#endif
 #define MVN_GT (32 * MVN_CW)               // consumer (GEMM) threads
 #define MVN_T (32 * (MVN_CW + MVN_PW))     // threads per CTA
 
