@@ -63,23 +63,25 @@ struct VarselModel {
     const int s = (int)idx.size();
     double l = 0.0;
     if (s > 0) {
-      std::vector<double> L((size_t)s * s, 0.0), y(s);
+      std::vector<double> L((size_t)s * s, 0.0), y(s), rinv(s);
       for (int a = 0; a < s; ++a) for (int b = 0; b <= a; ++b) L[(size_t)a * s + b] = G[(size_t)idx[a] * p + idx[b]];
-      for (int j = 0; j < s; ++j) {                      // left-looking Cholesky, row-major lower
+      // Cholesky, row-major lower; columns are scaled by the reciprocal of the pivot (as LAPACK's dpotf2 does)
+      for (int j = 0; j < s; ++j) {
         double d = L[(size_t)j * s + j];
         for (int k = 0; k < j; ++k) d = ubm_fma(-L[(size_t)j * s + k], L[(size_t)j * s + k], d);
         const double ljj = sqrt(d);
         L[(size_t)j * s + j] = ljj;
+        rinv[j] = 1.0 / ljj;
         for (int i = j + 1; i < s; ++i) {
           double t = L[(size_t)i * s + j];
           for (int k = 0; k < j; ++k) t = ubm_fma(-L[(size_t)i * s + k], L[(size_t)j * s + k], t);
-          L[(size_t)i * s + j] = t / ljj;
+          L[(size_t)i * s + j] = t * rinv[j];
         }
       }
       for (int i = 0; i < s; ++i) {                      // L y = v_g
         double t = v[idx[i]];
-        for (int k = 0; k < i; ++k) t = ubm_fma(-L[(size_t)i * s + k], y[k], t);
-        y[i] = t / L[(size_t)i * s + i];
+        for (int k = 0; k < i; ++k) t = ubm_fma(-y[k], L[(size_t)i * s + k], t);
+        y[i] = t * rinv[i];
       }
       for (int i = 0; i < s; ++i) l = ubm_fma(y[i], y[i], l);
     }

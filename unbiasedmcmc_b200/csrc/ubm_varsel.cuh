@@ -23,6 +23,15 @@ namespace ubm {
 
 #define VS_MAXW 32
 #define FULLMASK 0xffffffffu
+#ifndef VS_SFAST
+#define VS_SFAST 63      // selections of at most this many variables are factorised in shared memory (17 KB per warp), larger ones in an L2-resident per-warp buffer
+#endif
+#ifndef VS_WPB
+#define VS_WPB 4         // replicates (warps) per CTA
+#endif
+#ifndef VS_MINB
+#define VS_MINB 3        // CTAs per SM asked of the register allocator (x VS_WPB warps)
+#endif
 
 struct VarselDevice {
   int n, p, s0, nwords;
@@ -91,13 +100,124 @@ __host__ __device__ inline int varsel_work_doubles(int s0, int p) {
   return work > init ? work : init;
 }
 
-struct VsWork {           // per-warp shared memory
-  double* Lb;             // packed lower triangle, rows 0..s (row s = right-hand side / solution), (s0+2)(s0+3)/2 doubles
-  int* idx;               // [s0 + 2]
+struct VsWork {           // per-warp work space
+  double* Lbs;            // shared: packed lower triangle for s <= VS_SFAST, rows 0..s (row s = right-hand side / solution)
+  double* Lbg;            // global (L2): the same for larger s, (s0+2)(s0+3)/2 doubles; also the rinit scratch
+  double* colk;           // shared [VS_SFAST + 1]: the scaled column of the current elimination step
+  int* idx;               // shared [s0 + 2]
 };
+__host__ __device__ inline int varsel_fast_doubles() { return (VS_SFAST + 2) * (VS_SFAST + 3) / 2; }
+
+#ifdef UBM_VS_TIMING
+static __device__ long long g_vs_t[8];      // debug builds: cycles of warp (0,0): gather, cholesky, calls, sum of s, steps, total
+#define VSMARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); g_vs_t[i] += n_ - vt_; vt_ = n_; } } while (0)
+#else
+#define VSMARK(i) do { } while (0)
+#endif
+// Cholesky of G[idx, idx] with the right-hand side as row s, in the packed buffer Lb; returns |L^{-1} v_g|^2
+template <bool RIGHT>
+__device__ __forceinline__ double vs_chol_core(const VarselDevice& M, double* __restrict__ Lb, double* __restrict__ colk,
+                                               const int* __restrict__ idx, int s, int lane) {
+#ifdef UBM_VS_TIMING
+  long long vt_ = clock64();
+  if (blockIdx.x == 0 && threadIdx.x == 0) { g_vs_t[2] += 1; g_vs_t[3] += s; }
+#endif
+  // gather G[idx, idx] (lower) and the right-hand side as row s: four independent L2 loads in flight per lane
+  const int tot = (s + 1) * (s + 2) / 2 - 1;           // last row has s entries (no diagonal)
+  for (int e0 = lane; e0 < tot; e0 += 128) {
+    double val[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = e0 + 32 * q;
+      val[q] = 0.0;
+      if (e < tot) {
+        int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while ((a + 1) * (a + 2) / 2 <= e) ++a;
+        while (a * (a + 1) / 2 > e) --a;
+        const int b = e - a * (a + 1) / 2;
+        val[q] = (a < s) ? __ldg(M.G + (size_t)idx[a] * M.p + idx[b]) : __ldg(M.v + idx[b]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (e0 + 32 * q < tot) Lb[e0 + 32 * q] = val[q];
+  }
+  __syncwarp();
+  VSMARK(0);
+  double l = 0.0;
+  if (RIGHT) {
+    // Cholesky, right-looking, reciprocal-scaled (dpotf2): at step k every remaining entry (i, c), k < c <= i <= s,
+    // takes its k-th update A[i][c] = fma(-L[i][k], L[c][k], A[i][c]) with L[x][k] = A[x][k] * (1 / L[k][k]).  Each
+    // entry therefore sees exactly the fma sequence k = 0, 1, ... of the textbook left-looking loop (the oracle's), but
+    // the updates of one step are independent, so a lane keeps many in flight instead of walking one dependent chain.
+    // Per step: the scaled column goes to a small vector `colk` (one entry per lane), one barrier, then lane r updates
+    // rows k+1+r, k+33+r; the next pivot is handed on by shuffle from lane 0, which always owns row k+1.
+    // Row s carries the forward substitution L y = v_g: |y|^2 is accumulated by lane 0 as the y_k appear.
+    double piv = Lb[0];
+    for (int k = 0; k < s; ++k) {
+      const double rinv = 1.0 / sqrt(piv);
+      for (int i = k + 1 + lane; i <= s; i += 32) colk[i] = Lb[i * (i + 1) / 2 + k] * rinv;
+      __syncwarp();
+      if (lane == 0) { const double yk = colk[s]; l = ubm_fma(yk, yk, l); }
+      double newpiv = 0.0;
+      for (int i = k + 1 + lane; i <= s; i += 32) {
+        double* __restrict__ row = Lb + i * (i + 1) / 2;
+        const double nl = -colk[i];
+        const int cmax = (i == s) ? s - 1 : i;           // the right-hand-side row has no diagonal entry
+        int c = k + 1;
+        for (; c + 3 <= cmax; c += 4) {
+          const double b0 = colk[c], b1 = colk[c + 1], b2 = colk[c + 2], b3 = colk[c + 3];
+          const double a0 = row[c], a1 = row[c + 1], a2 = row[c + 2], a3 = row[c + 3];
+          row[c] = ubm_fma(nl, b0, a0); row[c + 1] = ubm_fma(nl, b1, a1);
+          row[c + 2] = ubm_fma(nl, b2, a2); row[c + 3] = ubm_fma(nl, b3, a3);
+        }
+        for (; c <= cmax; ++c) row[c] = ubm_fma(nl, colk[c], row[c]);
+        if (i == k + 1) newpiv = row[k + 1];             // entry (k+1, k+1): the next pivot (lane 0)
+      }
+      piv = __shfl_sync(FULLMASK, newpiv, 0);
+      __syncwarp();
+    }
+  } else {
+    // left-looking, column by column (global-memory buffer: finished columns are only read, so they stay in L1)
+    for (int j = 0; j < s; ++j) {
+      const int rj = j * (j + 1) / 2;
+      double t[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int i = lane + 32 * q;
+        t[q] = 0.0;
+        if (i >= j && i <= s) {
+          const int ri = i * (i + 1) / 2;
+          double d = Lb[ri + j];
+          for (int k = 0; k < j; ++k) d = ubm_fma(-Lb[ri + k], Lb[rj + k], d);
+          t[q] = d;
+        }
+      }
+      const int ql = j >> 5;
+      const double sjj = __shfl_sync(FULLMASK, (ql == 0) ? t[0] : (ql == 1) ? t[1] : (ql == 2) ? t[2] : (ql == 3) ? t[3] : t[4], j & 31);
+      const double ljj = sqrt(sjj);
+      const double rinv = 1.0 / ljj;
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int i = lane + 32 * q;
+        if (i == j) Lb[rj + j] = ljj;
+        else if (i > j && i <= s) Lb[i * (i + 1) / 2 + j] = t[q] * rinv;
+      }
+      __syncwarp();
+    }
+  }
+  if (!RIGHT && lane == 0) {
+    const int rs = s * (s + 1) / 2;
+    for (int i = 0; i < s; ++i) l = ubm_fma(Lb[rs + i], Lb[rs + i], l);
+  }
+  l = __shfl_sync(FULLMASK, l, 0);
+  __syncwarp();
+  VSMARK(1);
+  return l;
+}
 
 // marginal_likelihood_c_2 (src/vs_mlikelihood.cpp:5-28) of the selection held one word per lane
-__device__ inline double vs_ml(const VarselDevice& M, const VsWork& W, unsigned word, int lane) {
+__device__ __forceinline__ double vs_ml(const VarselDevice& M, const VsWork& W, unsigned word, int lane) {
   const int c = __popc(word);
   const int off = warp_excl_scan(c, lane);
   const int s = warp_total(c);
@@ -109,49 +229,9 @@ __device__ inline double vs_ml(const VarselDevice& M, const VsWork& W, unsigned 
       while (w) { const int b = __ffs(w) - 1; w &= w - 1; W.idx[t++] = 32 * lane + b; }
     }
     __syncwarp();
-    // gather G[idx, idx] (lower) and the right-hand side as row s
-    const int tot = (s + 1) * (s + 2) / 2 - 1;           // last row has s entries (no diagonal)
-    for (int e = lane; e < tot; e += 32) {
-      int a = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-      while ((a + 1) * (a + 2) / 2 <= e) ++a;
-      while (a * (a + 1) / 2 > e) --a;
-      const int b = e - a * (a + 1) / 2;
-      W.Lb[e] = (a < s) ? M.G[(size_t)W.idx[a] * M.p + W.idx[b]] : M.v[W.idx[b]];
-    }
-    __syncwarp();
-    // left-looking Cholesky, column by column; row s carries the forward substitution L y = v_g
-    for (int j = 0; j < s; ++j) {
-      const int rj = j * (j + 1) / 2;
-      double t[5];
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const int i = lane + 32 * q;
-        t[q] = 0.0;
-        if (i >= j && i <= s) {
-          const int ri = i * (i + 1) / 2;
-          double d = W.Lb[ri + j];
-          for (int k = 0; k < j; ++k) d = ubm_fma(-W.Lb[ri + k], W.Lb[rj + k], d);
-          t[q] = d;
-        }
-      }
-      const int ql = j >> 5;
-      const double sjj = __shfl_sync(FULLMASK, (ql == 0) ? t[0] : (ql == 1) ? t[1] : (ql == 2) ? t[2] : (ql == 3) ? t[3] : t[4], j & 31);
-      const double ljj = sqrt(sjj);
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const int i = lane + 32 * q;
-        if (i == j) W.Lb[rj + j] = ljj;
-        else if (i > j && i <= s) W.Lb[i * (i + 1) / 2 + j] = t[q] / ljj;
-      }
-      __syncwarp();
-    }
-    if (lane == 0) {
-      const int rs = s * (s + 1) / 2;
-      for (int i = 0; i < s; ++i) l = ubm_fma(W.Lb[rs + i], W.Lb[rs + i], l);
-    }
-    l = __shfl_sync(FULLMASK, l, 0);
-    __syncwarp();
+    // two copies of the same code so that the small case compiles to LDS/STS and the large one to LDG/STG
+    if (s <= VS_SFAST) l = vs_chol_core<true>(M, W.Lbs, W.colk, W.idx, s, lane);
+    else l = vs_chol_core<false>(M, W.Lbg, W.colk, W.idx, s, lane);
   }
   return -((double)s + 1.) / 2. * M.lg1 - (double)M.n / 2. * ubm_log(M.Y2 - M.gg * l);   // :26
 }
@@ -161,16 +241,6 @@ __device__ __forceinline__ double vs_prior(const VarselDevice& M, int s) {   // 
   return -M.kappa * (double)s * M.logp;
 }
 __device__ __forceinline__ unsigned vs_bit(int pos, int lane) { return ((pos >> 5) == lane) ? (1u << (pos & 31)) : 0u; }
-
-// Metropolis-Hastings accept step for one chain: proposal word `prop` (per lane) with |prop| = sprop
-__device__ inline void vs_try_move(const VarselDevice& M, const VsWork& W, unsigned& word, int& s, double& pdf,
-                                   unsigned prop, int sprop, double logu, int lane) {
-  const double pp = vs_prior(M, sprop);
-  if (isfinite(pp)) {
-    const double ppdf = vs_ml(M, W, prop, lane) + pp;
-    if (logu < ppdf - pdf) { word = prop; s = sprop; pdf = ppdf; }
-  }
-}
 
 // exact lazy bookkeeping of sum_{t in [k, m]} gamma1_t[j]: counters live in global memory, touched only on flips
 struct VsEst {
@@ -183,17 +253,22 @@ struct VsEst {
 };
 
 template <bool TAPE>
-__global__ void __launch_bounds__(32) varsel_driver_kernel(const VarselDevice M, const RunParams P, int* scratch_i,
-                                                           long long* scratch_l) {
+__global__ void __launch_bounds__(32 * VS_WPB, VS_MINB) varsel_driver_kernel(const VarselDevice M, const RunParams P, int* scratch_i,
+                                                                            long long* scratch_l, double* scratch_d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int gw = blockIdx.x * VS_WPB + wib;              // resident-warp index: owns one slice of every scratch array
   const int p = M.p;
+  const int idx_ints = (M.s0 + 2 > 34 ? M.s0 + 2 : 34) + ((M.s0 + 2 > 34 ? M.s0 + 2 : 34) & 1);
+  const size_t per_warp = (size_t)(varsel_fast_doubles() + VS_SFAST + 1) * sizeof(double) + (size_t)idx_ints * sizeof(int);
   VsWork W;
-  W.Lb = reinterpret_cast<double*>(smem_raw);
-  W.idx = reinterpret_cast<int*>(W.Lb + varsel_work_doubles(M.s0, p));
+  W.Lbs = reinterpret_cast<double*>(smem_raw + wib * per_warp);
+  W.colk = W.Lbs + varsel_fast_doubles();
+  W.idx = reinterpret_cast<int*>(W.colk + VS_SFAST + 1);
+  W.Lbg = scratch_d + (size_t)gw * varsel_work_doubles(M.s0, p);
   const unsigned vmask = (32 * lane + 32 <= p) ? 0xffffffffu : ((32 * lane >= p) ? 0u : ((1u << (p - 32 * lane)) - 1u));
   VsEst E;
-  E.cnt = scratch_i + (size_t)blockIdx.x * 2 * p; E.last = E.cnt + p; E.corr = scratch_l + (size_t)blockIdx.x * p;
+  E.cnt = scratch_i + (size_t)gw * 2 * p; E.last = E.cnt + p; E.corr = scratch_l + (size_t)gw * p;
   E.k = P.k; E.m = P.m;
   const double denom = (double)(P.m - P.k + 1);
 
@@ -211,9 +286,9 @@ __global__ void __launch_bounds__(32) varsel_driver_kernel(const VarselDevice M,
     double pdf1 = 0, pdf2 = 0;
     for (int chain = 0; chain < 2; ++chain) {
       const int kk = M.s0 < p ? M.s0 : p;
-      int* x = reinterpret_cast<int*>(W.Lb);            // p ints: remaining indices (aliases the work buffer)
+      int* x = reinterpret_cast<int*>(W.Lbg);           // p ints: remaining indices (aliases the global work buffer)
       unsigned* gws = reinterpret_cast<unsigned*>(W.idx);   // not used yet: idx has s0 + 2 >= 32 ints? ensured by launch
-      double* ub = W.Lb + (p + 1) / 2;                  // kk doubles after the int array
+      double* ub = W.Lbg + (p + 1) / 2;                 // kk doubles after the int array
       for (int j = lane; j < p; j += 32) x[j] = j;
       if (lane < VS_MAXW) gws[lane] = 0u;
       __syncwarp();
@@ -261,8 +336,18 @@ __global__ void __launch_bounds__(32) varsel_driver_kernel(const VarselDevice M,
       }
       if (!go) break;
       time += 1;
+#ifdef UBM_VS_TIMING
+      if (blockIdx.x == 0 && threadIdx.x == 0) { const long long n_ = clock64(); if (g_vs_t[6]) g_vs_t[5] += n_ - g_vs_t[6]; g_vs_t[6] = n_; g_vs_t[4] += 1; }
+#endif
       const bool coupled_step = (time > P.lag) && !met;
       const unsigned old1 = g1;
+      // The branches below only PROPOSE (in the reference's draw order); the marginal likelihoods, which consume no
+      // draws, are evaluated in one place afterwards: two call sites instead of nine, and one evaluation when both
+      // chains propose the same selection.
+      bool need1 = false, need2 = false;
+      unsigned prop1 = 0u, prop2 = 0u;
+      int sp1 = 0, sp2 = 0;
+      double logu1 = 0.0, logu2 = 0.0;
       if (!coupled_step) {
         // ---- single_kernel (R/variableselection.R:17-55) on chain 1
         if (D.u() < M.prop_flip) {
@@ -270,23 +355,19 @@ __global__ void __launch_bounds__(32) varsel_driver_kernel(const VarselDevice M,
           if (c >= p) c = p - 1;
           const unsigned bit = vs_bit(c, lane);
           const int was = (int)__reduce_or_sync(FULLMASK, (g1 & bit) ? 1u : 0u);
-          const int sprop = s1 + (was ? -1 : 1);
-          const double pp = vs_prior(M, sprop);
-          if (isfinite(pp)) {
-            const double ppdf = vs_ml(M, W, g1 ^ bit, lane) + pp;
-            const double logu = ubm_log(D.u());                       // drawn only if the prior is finite (:24-26)
-            if (logu < ppdf - pdf1) { g1 ^= bit; s1 = sprop; pdf1 = ppdf; }
+          sp1 = s1 + (was ? -1 : 1);
+          if (isfinite(vs_prior(M, sp1))) {
+            need1 = true; prop1 = g1 ^ bit;
+            logu1 = ubm_log(D.u());                                   // drawn only if the prior is finite (:24-26)
           }
         } else if (s1 > 0 && s1 < p) {
           const double u0 = D.u(), u1 = D.u();                        // src/sample_pairs01.cpp:20-24
           const int i0 = vs_inv2(~g1 & vmask, 1. / (double)(p - s1), 0u, 0.0, u0, lane);
           const int i1 = vs_inv2(g1, 1. / (double)s1, 0u, 0.0, u1, lane);
-          const unsigned prop = (g1 | vs_bit(i0, lane)) & ~vs_bit(i1, lane);
-          const double pp = vs_prior(M, s1);
-          if (isfinite(pp)) {
-            const double ppdf = vs_ml(M, W, prop, lane) + pp;
-            const double logu = ubm_log(D.u());
-            if (logu < ppdf - pdf1) { g1 = prop; pdf1 = ppdf; }
+          sp1 = s1;
+          if (isfinite(vs_prior(M, sp1))) {
+            need1 = true; prop1 = (g1 | vs_bit(i0, lane)) & ~vs_bit(i1, lane);
+            logu1 = ubm_log(D.u());
           }
         }
       } else {
@@ -297,9 +378,10 @@ __global__ void __launch_bounds__(32) varsel_driver_kernel(const VarselDevice M,
           const unsigned bit = vs_bit(c, lane);
           const int was1 = (int)__reduce_or_sync(FULLMASK, (g1 & bit) ? 1u : 0u);
           const int was2 = (int)__reduce_or_sync(FULLMASK, (g2 & bit) ? 1u : 0u);
-          const double logu = ubm_log(D.u());                         // :67 always drawn
-          vs_try_move(M, W, g1, s1, pdf1, g1 ^ bit, s1 + (was1 ? -1 : 1), logu, lane);
-          vs_try_move(M, W, g2, s2, pdf2, g2 ^ bit, s2 + (was2 ? -1 : 1), logu, lane);
+          logu1 = logu2 = ubm_log(D.u());                             // :67 always drawn
+          sp1 = s1 + (was1 ? -1 : 1); sp2 = s2 + (was2 ? -1 : 1);
+          prop1 = g1 ^ bit; prop2 = g2 ^ bit;
+          need1 = isfinite(vs_prior(M, sp1)); need2 = isfinite(vs_prior(M, sp2));
         } else {
           const bool sw1 = s1 > 0 && s1 < p, sw2 = s2 > 0 && s2 < p;
           if (sw1 && sw2) {
@@ -324,40 +406,48 @@ __global__ void __launch_bounds__(32) varsel_driver_kernel(const VarselDevice M,
               }
               if (half) { e1 = x1; e2 = x2; } else { o1 = x1; o2 = x2; }
             }
-            const unsigned p1 = (g1 | vs_bit(e1, lane)) & ~vs_bit(o1, lane);   // R/variableselection.R:92-97
-            const unsigned p2 = (g2 | vs_bit(e2, lane)) & ~vs_bit(o2, lane);
-            const double logu = ubm_log(D.u());                       // :100 always drawn
-            vs_try_move(M, W, g1, s1, pdf1, p1, s1, logu, lane);
-            vs_try_move(M, W, g2, s2, pdf2, p2, s2, logu, lane);
+            prop1 = (g1 | vs_bit(e1, lane)) & ~vs_bit(o1, lane);      // R/variableselection.R:92-97
+            prop2 = (g2 | vs_bit(e2, lane)) & ~vs_bit(o2, lane);
+            logu1 = logu2 = ubm_log(D.u());                           // :100 always drawn
+            sp1 = s1; sp2 = s2;
+            need1 = isfinite(vs_prior(M, sp1)); need2 = isfinite(vs_prior(M, sp2));
           } else {
             if (sw1) {                                                // :118-131
               const double u0 = D.u(), u1 = D.u();
               const int i0 = vs_inv2(~g1 & vmask, 1. / (double)(p - s1), 0u, 0.0, u0, lane);
               const int i1 = vs_inv2(g1, 1. / (double)s1, 0u, 0.0, u1, lane);
-              const unsigned prop = (g1 | vs_bit(i0, lane)) & ~vs_bit(i1, lane);
-              const double pp = vs_prior(M, s1);
-              if (isfinite(pp)) {
-                const double ppdf = vs_ml(M, W, prop, lane) + pp;
-                const double logu = ubm_log(D.u());
-                if (logu < ppdf - pdf1) { g1 = prop; pdf1 = ppdf; }
+              sp1 = s1;
+              if (isfinite(vs_prior(M, sp1))) {
+                need1 = true; prop1 = (g1 | vs_bit(i0, lane)) & ~vs_bit(i1, lane);
+                logu1 = ubm_log(D.u());
               }
             }
             if (sw2) {                                                // :133-145
               const double u0 = D.u(), u1 = D.u();
               const int i0 = vs_inv2(~g2 & vmask, 1. / (double)(p - s2), 0u, 0.0, u0, lane);
               const int i1 = vs_inv2(g2, 1. / (double)s2, 0u, 0.0, u1, lane);
-              const unsigned prop = (g2 | vs_bit(i0, lane)) & ~vs_bit(i1, lane);
-              const double pp = vs_prior(M, s2);
-              if (isfinite(pp)) {
-                const double ppdf = vs_ml(M, W, prop, lane) + pp;
-                const double logu = ubm_log(D.u());
-                if (logu < ppdf - pdf2) { g2 = prop; pdf2 = ppdf; }
+              sp2 = s2;
+              if (isfinite(vs_prior(M, sp2))) {
+                need2 = true; prop2 = (g2 | vs_bit(i0, lane)) & ~vs_bit(i1, lane);
+                logu2 = ubm_log(D.u());
               }
             }
           }
         }
-        if (__all_sync(FULLMASK, g1 == g2)) { met = true; tau = time; }   // :187, :258
       }
+      // ---- Metropolis-Hastings accept steps (R/variableselection.R:27-30, :68-79, :101-112)
+      double ml1 = 0.0;
+      if (need1) {
+        ml1 = vs_ml(M, W, prop1, lane);
+        const double ppdf = ml1 + vs_prior(M, sp1);
+        if (logu1 < ppdf - pdf1) { g1 = prop1; s1 = sp1; pdf1 = ppdf; }
+      }
+      if (need2) {
+        const bool same = need1 && __all_sync(FULLMASK, prop1 == prop2);
+        const double ppdf = (same ? ml1 : vs_ml(M, W, prop2, lane)) + vs_prior(M, sp2);
+        if (logu2 < ppdf - pdf2) { g2 = prop2; s2 = sp2; pdf2 = ppdf; }
+      }
+      if (coupled_step && __all_sync(FULLMASK, g1 == g2)) { met = true; tau = time; }   // :187, :258
       // ---- estimator / trajectories
       if (P.mode == MODE_ESTIMATOR) {
         unsigned ch = old1 ^ g1;                                      // chain-1 coordinates that flipped at `time`
@@ -413,11 +503,21 @@ __global__ void __launch_bounds__(32) varsel_driver_kernel(const VarselDevice M,
       }
     }
     __syncwarp();
+#ifdef UBM_VS_TIMING
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      printf("varsel timing (warp 0 of block 0): steps %lld cycles/step %.0f | ml calls/step %.2f mean s %.1f gather %.0f chol %.0f cycles/call\n",
+             g_vs_t[4], (double)g_vs_t[5] / g_vs_t[4], (double)g_vs_t[2] / g_vs_t[4], (double)g_vs_t[3] / g_vs_t[2],
+             (double)g_vs_t[0] / g_vs_t[2], (double)g_vs_t[1] / g_vs_t[2]);
+      g_vs_t[6] = 0;
+    }
+#endif
   }
 }
 
-inline size_t varsel_smem_bytes(int s0, int p) {
-  return (size_t)varsel_work_doubles(s0, p) * sizeof(double) + (size_t)(std::max(s0 + 2, 34)) * sizeof(int) + 16;
+inline size_t varsel_smem_bytes(int s0) {      // per CTA
+  int idx_ints = std::max(s0 + 2, 34);
+  idx_ints += idx_ints & 1;
+  return (size_t)VS_WPB * ((size_t)(varsel_fast_doubles() + VS_SFAST + 1) * sizeof(double) + (size_t)idx_ints * sizeof(int));
 }
 
 template <class Buf>
@@ -425,23 +525,23 @@ inline int varsel_launch(const VarselDevice& M, const RunParams& P, bool tape, i
                          int64_t* launches, std::string* err) {
   if (P.nbreaks >= 2) { *err = "variable selection: histogram bins are not available for this model"; return UBM_ERR_UNSUPPORTED; }
   if (P.mode == MODE_ESTIMATOR && P.h_kind != UBM_H_IDENTITY) { *err = "variable selection: h must be the identity (inclusion indicators)"; return UBM_ERR_UNSUPPORTED; }
-  const size_t smem = varsel_smem_bytes(M.s0, M.p);
+  const size_t smem = varsel_smem_bytes(M.s0);
   auto kern = tape ? varsel_driver_kernel<true> : varsel_driver_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { *err = std::string("variable selection: smem attribute: ") + cudaGetErrorString(e); return UBM_ERR_CUDA; }
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * VS_WPB, smem);
   if (e != cudaSuccess || per_sm < 1) { *err = "variable selection: occupancy query failed"; return UBM_ERR_CUDA; }
-  const int grid = (int)std::min<int64_t>((int64_t)nsm * per_sm, P.nrep);
-  int* si = nullptr; long long* sl = nullptr;
-  if (P.mode == MODE_ESTIMATOR) {
-    const size_t bi = (size_t)grid * 2 * M.p * sizeof(int), bl = (size_t)grid * M.p * sizeof(long long);
-    const size_t bl_off = (bi + 15) & ~(size_t)15;
-    if (scratch.bytes < bl_off + bl) { if (scratch.alloc(bl_off + bl) != cudaSuccess) { *err = "variable selection: scratch alloc failed"; return UBM_ERR_NOMEM; } }
-    si = scratch.template as<int>();
-    sl = reinterpret_cast<long long*>(scratch.template as<unsigned char>() + bl_off);
-  }
-  kern<<<grid, 32, smem, st>>>(M, P, si, sl);
+  const int grid = (int)std::min<int64_t>((int64_t)nsm * per_sm, (P.nrep + VS_WPB - 1) / VS_WPB);
+  const size_t nw = (size_t)grid * VS_WPB;                 // resident warps: one slice of each scratch array per warp
+  const size_t bd = nw * (size_t)varsel_work_doubles(M.s0, M.p) * sizeof(double);
+  const size_t bi = (P.mode == MODE_ESTIMATOR) ? nw * 2 * M.p * sizeof(int) : 0;
+  const size_t bl = (P.mode == MODE_ESTIMATOR) ? nw * M.p * sizeof(long long) : 0;
+  const size_t bi_off = (bd + 15) & ~(size_t)15, bl_off = (bi_off + bi + 15) & ~(size_t)15;
+  if (scratch.bytes < bl_off + bl) { if (scratch.alloc(bl_off + bl) != cudaSuccess) { *err = "variable selection: scratch alloc failed"; return UBM_ERR_NOMEM; } }
+  unsigned char* base = scratch.template as<unsigned char>();
+  kern<<<grid, 32 * VS_WPB, smem, st>>>(M, P, reinterpret_cast<int*>(base + bi_off), reinterpret_cast<long long*>(base + bl_off),
+                                        reinterpret_cast<double*>(base));
   *launches += 1;
   return UBM_OK;
 }
