@@ -128,7 +128,7 @@ typedef struct {
  * m_sigma_function_ (src/logisticregression.cpp:32-56).  Prior beta ~ N(b, B); rinit: beta ~ N(b, B), w = 0.
  * The chain state exposed to h / trajectories is beta (dim = p), as the reference's scripts store it. */
 typedef struct {
-  int32_t n, p;           /* n <= 4096 observations, p <= 64 covariates */
+  int32_t n, p;           /* n <= 4096 observations, p <= 60 covariates */
   const double* X;        /* n x p column-major design matrix */
   const double* Y;        /* [n] responses in {0, 1} */
   const double* b;        /* [p] prior mean */

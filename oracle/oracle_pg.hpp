@@ -252,8 +252,11 @@ struct PgLogisticModel {
     int e = 0;
     for (int j1 = 0; j1 < p; ++j1)
       for (int j2 = j1; j2 < p; ++j2, ++e) {
-        double a = invB[(size_t)j2 * p + j1];                                     // :42
-        for (int i = 0; i < n; ++i) a = ubm_fma(Zprod[(size_t)i * ne + e], omega[i], a);   // :43-45
+        // :42-45.  Canonical order: four interleaved chains over the observations (i mod 4), added to invB in turn
+        double part[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < n; ++i) part[i & 3] = ubm_fma(Zprod[(size_t)i * ne + e], omega[i], part[i & 3]);
+        double a = invB[(size_t)j2 * p + j1];
+        for (int c = 0; c < 4; ++c) a = a + part[c];
         r.L[(size_t)j1 * p + j2] = a;                                             // lower triangle (column j1, row j2)
         r.L[(size_t)j2 * p + j1] = a;
       }

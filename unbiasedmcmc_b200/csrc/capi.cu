@@ -138,7 +138,7 @@ static int register_model(ubm_plan* p, int32_t kind, const void* model) {
   }
   if (kind == UBM_MODEL_PG_LOGISTIC) {
     const ubm_model_pg_logistic* s = (const ubm_model_pg_logistic*)model;
-    if (s->p < 1 || s->p > PG_MAXP || s->n < 1 || s->n > 4096) return fail(h, UBM_ERR_INVALID, "pg logistic: 1 <= p <= 64, 1 <= n <= 4096");
+    if (s->p < 1 || s->p > PG_PLIM || s->n < 1 || s->n > 4096) return fail(h, UBM_ERR_INVALID, "pg logistic: 1 <= p <= 60, 1 <= n <= 4096");
     if (!s->X || !s->Y || !s->b || !s->B) return fail(h, UBM_ERR_INVALID, "pg logistic: null data");
     p->dim = s->p;
     std::vector<double> blob;

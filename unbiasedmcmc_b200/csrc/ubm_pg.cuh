@@ -327,52 +327,78 @@ struct PgShared {   // scalars
   int flag;
 };
 
-// Gram build for one or two chains: A_c[j2, j1] (lower) = invB[j1, j2] + sum_i X(i,j1) X(i,j2) w_c[i]
+// Gram build for one or two chains: A_c[j2, j1] (lower) = invB[j1, j2] + sum_i X(i,j1) X(i,j2) w_c[i].
+// Register-tiled: a thread owns a 4 x 4 block of entries (column blocks bj1 <= bj2) for one of four interleaved
+// observation classes (i mod 4) and keeps its 16 (+16) sums in registers; per observation it reads two 32-byte row
+// segments of the staged X tile and the weights.  Canonical order (oracle: m_sigma): four chains over i mod 4, each
+// sequential in i, then ((((invB + P0) + P1) + P2) + P3).
+#define PG_GS (PG_MAXP + 4)      // row stride of the staged tile (doubles), 16-byte aligned rows
+#define PG_PLIM 60               // 4 classes x nb (nb + 1) / 2 blocks must fit the 512 threads: ceil(p / 4) <= 15
 template <bool TWO>
 __device__ inline void pg_gram(const PgDevice& M, const double* w1, const double* w2, double* A1, double* A2,
-                               double* xs /* [PG_TILE][p] */, int tid) {
-  const int n = M.n, p = M.p, ne = M.ne;
-  // up to 5 entries per thread (ne <= 2080 for p = 64, 512 threads -> 5); slots are indexed statically so that
-  // they stay in registers
-  int j1[5], j2[5];
-  double a1[5], a2[5];
-  bool on[5];
+                               double* xs /* [PG_TILE][PG_GS] */, int tid) {
+  const int n = M.n, p = M.p;
+  const int nb = (p + 3) / 4, nblk = nb * (nb + 1) / 2;
+  const int cls = tid / nblk, blk = tid - cls * nblk;
+  const bool on = cls < 4;
+  int bj1 = 0, rem = on ? blk : 0;
+  while (rem >= nb - bj1) { rem -= nb - bj1; ++bj1; }
+  const int bj2 = bj1 + rem;
+  double a1[4][4], a2[4][4];
 #pragma unroll
-  for (int c = 0; c < 5; ++c) {
-    const int e = tid + c * PG_T;
-    on[c] = e < ne;
-    int a = 0, rem = on[c] ? e : 0;
-    while (rem >= p - a) { rem -= p - a; ++a; }
-    j1[c] = a; j2[c] = a + rem;
-    a1[c] = M.invB[(size_t)(a + rem) * p + a];
-    a2[c] = a1[c];
-  }
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { a1[r][c] = 0.0; a2[r][c] = 0.0; }
   for (int i0 = 0; i0 < n; i0 += PG_TILE) {
     const int rows = (n - i0 < PG_TILE) ? (n - i0) : PG_TILE;
     __syncthreads();
-    for (int q = tid; q < PG_TILE * p; q += PG_T) {
+    for (int q = tid; q < PG_TILE * PG_GS; q += PG_T) {
       const int ii = q % PG_TILE, j = q / PG_TILE;
-      xs[ii * p + j] = (ii < rows) ? M.X[(size_t)j * n + i0 + ii] : 0.0;
+      xs[ii * PG_GS + j] = (ii < rows && j < p) ? M.X[(size_t)j * n + i0 + ii] : 0.0;
     }
     __syncthreads();
-    for (int ii = 0; ii < rows; ++ii) {
-      const double wa = w1[i0 + ii];
-      const double wb = TWO ? w2[i0 + ii] : 0.0;
+    if (on) {
+      for (int ii = cls; ii < rows; ii += 4) {
+        const double wa = w1[i0 + ii];
+        const double wb = TWO ? w2[i0 + ii] : 0.0;
+        const double2 xa0 = *reinterpret_cast<const double2*>(xs + ii * PG_GS + 4 * bj1);
+        const double2 xa1 = *reinterpret_cast<const double2*>(xs + ii * PG_GS + 4 * bj1 + 2);
+        const double2 xb0 = *reinterpret_cast<const double2*>(xs + ii * PG_GS + 4 * bj2);
+        const double2 xb1 = *reinterpret_cast<const double2*>(xs + ii * PG_GS + 4 * bj2 + 2);
+        const double xa[4] = {xa0.x, xa0.y, xa1.x, xa1.y}, xb[4] = {xb0.x, xb0.y, xb1.x, xb1.y};
 #pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        if (on[c]) {
-          const double z = xs[ii * p + j1[c]] * xs[ii * p + j2[c]];
-          a1[c] = ubm_fma(z, wa, a1[c]);
-          if (TWO) a2[c] = ubm_fma(z, wb, a2[c]);
-        }
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const double z = xa[r] * xb[c];
+            a1[r][c] = ubm_fma(z, wa, a1[r][c]);
+            if (TWO) a2[r][c] = ubm_fma(z, wb, a2[r][c]);
+          }
       }
     }
   }
+  // ((((invB + P0) + P1) + P2) + P3): the four classes add their sums in turn
+  for (int turn = 0; turn < 4; ++turn) {
+    __syncthreads();
+    if (on && cls == turn) {
 #pragma unroll
-  for (int c = 0; c < 5; ++c) {
-    if (on[c]) {
-      A1[j1[c] * p + j2[c]] = a1[c]; A1[j2[c] * p + j1[c]] = a1[c];
-      if (TWO) { A2[j1[c] * p + j2[c]] = a2[c]; A2[j2[c] * p + j1[c]] = a2[c]; }
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j1 = 4 * bj1 + r, j2 = 4 * bj2 + c;
+          if (j1 <= j2 && j2 < p) {
+            const double base = (turn == 0) ? M.invB[(size_t)j2 * p + j1] : A1[j1 * p + j2];
+            const double v1 = base + a1[r][c];
+            A1[j1 * p + j2] = v1;
+            if (turn == 3) A1[j2 * p + j1] = v1;
+            if (TWO) {
+              const double base2 = (turn == 0) ? M.invB[(size_t)j2 * p + j1] : A2[j1 * p + j2];
+              const double v2 = base2 + a2[r][c];
+              A2[j1 * p + j2] = v2;
+              if (turn == 3) A2[j2 * p + j1] = v2;
+            }
+          }
+        }
     }
   }
   __syncthreads();
@@ -400,7 +426,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
   double* MB1 = sp; sp += p * p;   //          Linv
   double* MA2 = sp; sp += p * p;
   double* MB2 = sp; sp += p * p;
-  double* xs = sp; sp += PG_TILE * p;
+  double* xs = sp; sp += PG_TILE * PG_GS;
   double* beta1 = sp; sp += PG_MAXP;
   double* beta2 = sp; sp += PG_MAXP;
   double* m1 = sp; sp += PG_MAXP;
@@ -656,7 +682,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
 }
 
 inline size_t pg_smem_bytes(int n, int p) {
-  return (size_t)(2 * n + 4 * p * p + PG_TILE * p + 8 * PG_MAXP + 4 * PG_MAXP + (n + 1) / 2) * sizeof(double) + sizeof(PgShared) + 16;
+  return (size_t)(2 * n + 4 * p * p + PG_TILE * PG_GS + 8 * PG_MAXP + 4 * PG_MAXP + (n + 1) / 2) * sizeof(double) + sizeof(PgShared) + 16;
 }
 
 inline int pg_launch(const PgDevice& M, const RunParams& P, bool tape, int nsm, cudaStream_t st, int64_t* launches,

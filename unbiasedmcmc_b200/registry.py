@@ -156,8 +156,8 @@ class PgLogistic(ModelSpec):
     def __init__(self, Y, X, b, B):
         X = np.asarray(X, dtype=np.float64)
         self.n, self.p = X.shape
-        if not (1 <= self.p <= 64 and 1 <= self.n <= 4096):
-            raise ValueError("PG logistic: n <= 4096, p <= 64")
+        if not (1 <= self.p <= 60 and 1 <= self.n <= 4096):
+            raise ValueError("PG logistic: n <= 4096, p <= 60")
         self.dim = self.p
         self.X = _colmajor(X)
         self.Y = _f64(Y)
