@@ -30,13 +30,15 @@ namespace ubm {
 #define PG_T 512
 #define PG_TILE 32
 #define PG_MAXP 64
+#define PG_GS (PG_MAXP + 4)      // row stride of the staged Gram tile (doubles), 16-byte aligned rows
 #define PG_PI_D 3.141592653589793238462643383279502884197
 #define PG_TRUNC_D 0.64
 
 struct PgDevice {
   int n, p, ne;
   const double *X, *invB, *ktk, *b, *cholB;   // device: X n x p col-major; invB p x p; ktk, b [p]; cholB upper p x p
-  size_t offs[5];
+  const double *Xt;                            // device: X again, row-major [ceil(n/32)*32][PG_GS], zero padded: the Gram tiles
+  size_t offs[6];
 };
 
 // host-side precomputation (logisticregression_precomputation, R/logistic_regression.R:34-50, and chol(B) for rinit)
@@ -88,54 +90,59 @@ inline void pg_pack_host(const ubm_model_pg_logistic* s, PgDevice* M, std::vecto
   M->offs[2] = put(ktk.data(), ktk.size());
   M->offs[3] = put(s->b, p);
   M->offs[4] = put(cholB.data(), cholB.size());
+  const int npad = (n + PG_TILE - 1) / PG_TILE * PG_TILE;
+  std::vector<double> Xt((size_t)npad * PG_GS, 0.0);
+  for (int i = 0; i < n; ++i) for (int j = 0; j < p; ++j) Xt[(size_t)i * PG_GS + j] = s->X[(size_t)j * n + i];
+  if (blob->size() & 1) blob->push_back(0.0);      // 16-byte alignment of the tiles
+  M->offs[5] = put(Xt.data(), Xt.size());
 }
 inline void pg_bind_device(PgDevice* M, const double* dev) {
   M->X = dev + M->offs[0]; M->invB = dev + M->offs[1]; M->ktk = dev + M->offs[2]; M->b = dev + M->offs[3];
-  M->cholB = dev + M->offs[4];
+  M->cholB = dev + M->offs[4]; M->Xt = dev + M->offs[5];
 }
+
+// ---- out-of-line helpers -----------------------------------------------------------------------------------------
+// The Devroye sampler calls log / exp / log-pnorm and the typed draws at some thirty places; inlined, the kernel grew
+// to 27 000 instructions (430 KB) and ncu showed `no_inst` (instruction-fetch) stalls on 50-80 % of the samples of the
+// sweep.  One copy of each keeps the hot loops inside the instruction cache; the arithmetic is unchanged.
+__device__ __noinline__ double pg_log(double x) { return ubm_log(x); }
+__device__ __noinline__ double pg_exp(double x) { return ubm_exp(x); }
+__device__ __noinline__ double pg_pnorm_log(double x) { return ubm_pnorm_log(x); }
+// draw k of a typed stream of (replicate, cell, attempt): one Philox block per call, no cached state
+__device__ __noinline__ double pg_cell_u(uint64_t seed, uint64_t rep_eff, uint64_t base, unsigned k) {
+  const ubm_u32x4 b = ubm_stream_block(seed, rep_eff, UBM_STREAM_U, base | (k >> 2));
+  const unsigned s = k & 3u;
+  return ubm_u01_32((s == 0) ? b.w[0] : (s == 1) ? b.w[1] : (s == 2) ? b.w[2] : b.w[3]);
+}
+__device__ __noinline__ double pg_cell_u53(uint64_t seed, uint64_t rep_eff, uint64_t base, unsigned k, int stream) {
+  const ubm_u32x4 b = ubm_stream_block(seed, rep_eff, stream, base | (k >> 1));
+  return (k & 1) ? ubm_u01_53(b.w[2], b.w[3]) : ubm_u01_53(b.w[0], b.w[1]);
+}
+__device__ __noinline__ double pg_qnorm(double p) { return ubm_qnorm(p); }
 
 // ---- per-cell typed draws (random access into the replicate's Philox streams) ----------------------------------
 struct PgCell {   // a cell = (sweep, observation); an attempt = 32 blocks of each typed stream (oracle/oracle_pg.hpp: CellDraws)
   uint64_t seed, rep, cell, base, rep_eff;
   unsigned ku, kn, ke;
-  ubm_u32x4 bu, bn, be;
-  unsigned long long cbu, cbn, cbe, cru, crn, cre;
-  __device__ PgCell(uint64_t seed_, uint64_t grep_, uint64_t cell_)
-      : seed(seed_), rep(grep_), cell(cell_), cbu(~0ull), cbn(~0ull), cbe(~0ull), cru(~0ull), crn(~0ull), cre(~0ull) { set_attempt(0); }
-  __device__ void set_attempt(uint64_t a) {
+  __device__ PgCell(uint64_t seed_, uint64_t grep_, uint64_t cell_) : seed(seed_), rep(grep_), cell(cell_) { set_attempt(0); }
+  __device__ __forceinline__ void set_attempt(uint64_t a) {
     base = (1ull << 59) | ((cell & ((1ull << 26) - 1)) << 33) | ((a & ((1ull << 28) - 1)) << 5);
     rep_eff = rep + ((a >> 28) << 44);
     ku = kn = ke = 0;
   }
-  __device__ double u() {
-    const unsigned k = (ku++) & 127u;
-    const uint64_t blk = base | (k >> 2);
-    if (blk != cbu || rep_eff != cru) { cbu = blk; cru = rep_eff; bu = ubm_stream_block(seed, rep_eff, UBM_STREAM_U, blk); }
-    const unsigned s = k & 3u;
-    return ubm_u01_32((s == 0) ? bu.w[0] : (s == 1) ? bu.w[1] : (s == 2) ? bu.w[2] : bu.w[3]);
-  }
-  __device__ double n() {
-    const unsigned k = (kn++) & 63u;
-    const uint64_t blk = base | (k >> 1);
-    if (blk != cbn || rep_eff != crn) { cbn = blk; crn = rep_eff; bn = ubm_stream_block(seed, rep_eff, UBM_STREAM_N, blk); }
-    return ubm_qnorm((k & 1) ? ubm_u01_53(bn.w[2], bn.w[3]) : ubm_u01_53(bn.w[0], bn.w[1]));
-  }
-  __device__ double e() {
-    const unsigned k = (ke++) & 63u;
-    const uint64_t blk = base | (k >> 1);
-    if (blk != cbe || rep_eff != cre) { cbe = blk; cre = rep_eff; be = ubm_stream_block(seed, rep_eff, UBM_STREAM_E, blk); }
-    return -ubm_log((k & 1) ? ubm_u01_53(be.w[2], be.w[3]) : ubm_u01_53(be.w[0], be.w[1]));
-  }
+  __device__ __forceinline__ double u() { return pg_cell_u(seed, rep_eff, base, (ku++) & 127u); }
+  __device__ __forceinline__ double n() { return pg_qnorm(pg_cell_u53(seed, rep_eff, base, (kn++) & 63u, UBM_STREAM_N)); }
+  __device__ __forceinline__ double e() { return -pg_log(pg_cell_u53(seed, rep_eff, base, (ke++) & 63u, UBM_STREAM_E)); }
 };
 
 // PolyaGamma::a — src/PolyaGamma.cpp:65-79
-__device__ inline double pg_a(int n, double x) {
+__device__ __noinline__ double pg_a(int n, double x) {
   const double K = (n + 0.5) * PG_PI_D;
   double y = 0;
-  if (x > PG_TRUNC_D) y = K * ubm_exp(-0.5 * K * K * x);
+  if (x > PG_TRUNC_D) y = K * pg_exp(-0.5 * K * K * x);
   else if (x > 0) {
-    const double expnt = -1.5 * (ubm_log(0.5 * PG_PI_D) + ubm_log(x)) + ubm_log(K) - 2.0 * (n + 0.5) * (n + 0.5) / x;
-    y = ubm_exp(expnt);
+    const double expnt = -1.5 * (pg_log(0.5 * PG_PI_D) + pg_log(x)) + pg_log(K) - 2.0 * (n + 0.5) * (n + 0.5) / x;
+    y = pg_exp(expnt);
   }
   return y;
 }
@@ -145,10 +152,10 @@ __device__ inline double pg_mass_texpon(double Z) {
   const double fz = 0.125 * PG_PI_D * PG_PI_D + 0.5 * Z * Z;
   const double b = sqrt(1.0 / t) * (t * Z - 1);
   const double a = sqrt(1.0 / t) * (t * Z + 1) * -1.0;
-  const double x0 = ubm_log(fz) + fz * t;
-  const double xb = x0 - Z + ubm_pnorm_log(b);
-  const double xa = x0 + Z + ubm_pnorm_log(a);
-  const double qdivp = 4 / PG_PI_D * (ubm_exp(xb) + ubm_exp(xa));
+  const double x0 = pg_log(fz) + fz * t;
+  const double xb = x0 - Z + pg_pnorm_log(b);
+  const double xa = x0 + Z + pg_pnorm_log(a);
+  const double qdivp = 4 / PG_PI_D * (pg_exp(xb) + pg_exp(xa));
   return 1.0 / (1.0 + qdivp);
 }
 // PolyaGamma::rtigauss — src/PolyaGamma.cpp:106-139
@@ -163,7 +170,7 @@ __device__ inline double pg_rtigauss(double Z, PgCell& r) {
       while (E1 * E1 > 2 * E2 / t) { E1 = r.e(); E2 = r.e(); }
       X = 1 + E1 * t;
       X = t / (X * X);
-      alpha = ubm_exp(-0.5 * Z * Z * X);
+      alpha = pg_exp(-0.5 * Z * Z * X);
     }
   } else {
     const double mu = 1.0 / Z;
@@ -204,37 +211,63 @@ __device__ inline double pg_draw(double Zin, PgCell& r) {
 }
 // logcosh — src/logisticregressioncoupling.cpp:9-17
 __device__ inline double pg_logcosh(double x) {
-  if (x > 0.) return x + ubm_log(1.0 + ubm_exp(-2.0 * x)) - 0.6931472;
-  return -x + ubm_log(1.0 + ubm_exp(2.0 * x)) - 0.6931472;
+  if (x > 0.) return x + pg_log(1.0 + pg_exp(-2.0 * x)) - 0.6931472;
+  return -x + pg_log(1.0 + pg_exp(2.0 * x)) - 0.6931472;
 }
 
 // ---- warp-level p x p linear algebra on column-major shared-memory matrices (stride p) --------------------------
-// in place: lower triangle of A becomes L (A = L L'); strict upper part is zeroed.  Same sums as the oracle's chol_lower.
+// in place: lower triangle of A becomes L (A = L L'); strict upper part is zeroed.  Right-looking: after column k is
+// scaled, every remaining entry (i, c), k < c <= i, takes its k-th update A[i][c] = fma(-L[i][k], L[c][k], A[i][c]) —
+// exactly the fma sequence k = 0, 1, ... of the oracle's left-looking chol_lower for that entry, but the updates of one
+// step are independent, so a lane keeps many in flight instead of walking one dependent load-fma chain per column.
 __device__ inline void pg_warp_chol(double* A, int p, int lane) {
-  for (int j = 0; j < p; ++j) {
-    double t[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int i = lane + 32 * q;
-      t[q] = 0.0;
-      if (i >= j && i < p) {
-        double s = A[j * p + i];
-        for (int k = 0; k < j; ++k) s = ubm_fma(-A[k * p + i], A[k * p + j], s);
-        t[q] = s;
-      }
-    }
-    const double sjj = __shfl_sync(0xffffffffu, (j >= 32) ? t[1] : t[0], j & 31);
-    const double ljj = sqrt(sjj);
+  for (int k = 0; k < p; ++k) {
+    const double lkk = sqrt(A[k * p + k]);
     __syncwarp();
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int i = lane + 32 * q;
-      if (i == j) A[j * p + i] = ljj;
-      else if (i > j && i < p) A[j * p + i] = t[q] / ljj;
-      else if (i < j) A[j * p + i] = 0.0;
+    for (int i = k + lane; i < p; i += 32) A[k * p + i] = (i == k) ? lkk : A[k * p + i] / lkk;
+    for (int i = lane; i < k; i += 32) A[k * p + i] = 0.0;
+    __syncwarp();
+    for (int i = k + 1 + lane; i < p; i += 32) {
+      const double nl = -A[k * p + i];
+      int c = k + 1;
+      for (; c + 3 <= i; c += 4) {
+        const double b0 = A[k * p + c], b1 = A[k * p + c + 1], b2 = A[k * p + c + 2], b3 = A[k * p + c + 3];
+        const double a0 = A[c * p + i], a1 = A[(c + 1) * p + i], a2 = A[(c + 2) * p + i], a3 = A[(c + 3) * p + i];
+        A[c * p + i] = ubm_fma(nl, b0, a0); A[(c + 1) * p + i] = ubm_fma(nl, b1, a1);
+        A[(c + 2) * p + i] = ubm_fma(nl, b2, a2); A[(c + 3) * p + i] = ubm_fma(nl, b3, a3);
+      }
+      for (; c <= i; ++c) A[c * p + i] = ubm_fma(nl, A[k * p + c], A[c * p + i]);
     }
     __syncwarp();
   }
+}
+// The same factorisation by the whole CTA, for one matrix (A2 == nullptr) or two at once (threads split in halves):
+// thread (ti, tc) updates entries (k+1+ti+.., k+1+tc+..) of the trailing block, so a column step costs the pivot chain
+// (sqrt, one division) plus two or three independent fma per thread and two CTA barriers, instead of a warp walking
+// ~40 entries per lane.  `dg` [2][PG_MAXP] keeps the new diagonal until the end, so that the pivot can be read and the
+// column scaled between the same two barriers.  Same per-entry fma sequence as pg_warp_chol / the oracle.
+__device__ inline void pg_cta_chol(double* A1, double* A2, double* dg, int p, int tid) {
+  const bool two = (A2 != nullptr);
+  const int nthr = two ? PG_T / 2 : PG_T;
+  const int half = two ? tid / (PG_T / 2) : 0;
+  const int t = two ? tid % (PG_T / 2) : tid;
+  double* A = half ? A2 : A1;
+  double* d = dg + half * PG_MAXP;
+  const int tc = t & 15, ti = t >> 4, nti = nthr >> 4;
+  for (int k = 0; k < p; ++k) {
+    const double lkk = sqrt(A[k * p + k]);
+    if (t == 0) d[k] = lkk;
+    for (int i = k + 1 + t; i < p; i += nthr) A[k * p + i] = A[k * p + i] / lkk;
+    for (int i = t; i < k; i += nthr) A[k * p + i] = 0.0;
+    __syncthreads();
+    for (int i = k + 1 + ti; i < p; i += nti) {
+      const double nl = -A[k * p + i];
+      for (int c = k + 1 + tc; c <= i; c += 16) A[c * p + i] = ubm_fma(nl, A[k * p + c], A[c * p + i]);
+    }
+    __syncthreads();
+  }
+  for (int k = t; k < p; k += nthr) A[k * p + k] = d[k];
+  __syncthreads();
 }
 // solve L y = rhs (forward), y overwrites `v` (shared); terms taken in increasing column order
 __device__ inline void pg_warp_forward(const double* L, int p, int lane, double* v) {
@@ -283,16 +316,22 @@ __device__ inline void pg_warp_tri_inverse(const double* L, double* Li, int p, i
     Li[j * p + j] = 1.0 / L[j * p + j];
     for (int i = j + 1; i < p; ++i) {
       double s = 0.0;
-      for (int k = j; k < i; ++k) s = ubm_fma(L[k * p + i], Li[j * p + k], s);
+      int k = j;
+      for (; k + 3 < i; k += 4) {        // operands first, then the four dependent fma (same order as the plain loop)
+        const double l0 = L[k * p + i], l1 = L[(k + 1) * p + i], l2 = L[(k + 2) * p + i], l3 = L[(k + 3) * p + i];
+        const double y0 = Li[j * p + k], y1 = Li[j * p + k + 1], y2 = Li[j * p + k + 2], y3 = Li[j * p + k + 3];
+        s = ubm_fma(l0, y0, s); s = ubm_fma(l1, y1, s); s = ubm_fma(l2, y2, s); s = ubm_fma(l3, y3, s);
+      }
+      for (; k < i; ++k) s = ubm_fma(L[k * p + i], Li[j * p + k], s);
       Li[j * p + i] = -s / L[i * p + i];
     }
   }
   __syncwarp();
 }
-// S = Li' Li (both triangles), S[a,c] = sum_{i >= c} Li(i,a) Li(i,c), c >= a
-__device__ inline void pg_warp_ltl(const double* Li, double* S, int p, int lane) {
+// S = Li' Li (both triangles), S[a,c] = sum_{i >= c} Li(i,a) Li(i,c), c >= a; entries strided over `nthr` threads
+__device__ inline void pg_ltl(const double* Li, double* S, int p, int t, int nthr) {
   const int ne = p * (p + 1) / 2;
-  for (int e = lane; e < ne; e += 32) {
+  for (int e = t; e < ne; e += nthr) {
     // e -> (a, c), a <= c, enumerated a-major
     int a = 0, rem = e;
     while (rem >= p - a) { rem -= p - a; ++a; }
@@ -301,7 +340,6 @@ __device__ inline void pg_warp_ltl(const double* Li, double* S, int p, int lane)
     for (int i = c; i < p; ++i) s = ubm_fma(Li[a * p + i], Li[c * p + i], s);
     S[c * p + a] = s; S[a * p + c] = s;
   }
-  __syncwarp();
 }
 // fast_dmvnorm_ (src/mvnorm.cpp:49-67) with the lower factor Ls of the covariance; tmp: shared scratch [p]
 __device__ inline double pg_warp_dmvnorm(const double* x, const double* mean, const double* Ls, int p, int lane, double* tmp) {
@@ -309,9 +347,16 @@ __device__ inline double pg_warp_dmvnorm(const double* x, const double* mean, co
   __syncwarp();
   pg_warp_forward(Ls, p, lane, tmp);
   double res = 0.0;
+  // the logs of the diagonal are taken by all lanes at once and then added in the reference order by lane 0
+  double lg[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) { const int j = lane + 32 * q; lg[q] = (j < p) ? pg_log(Ls[j * p + j]) : 0.0; }
+  double halflogdet = 0.0;
+  for (int j = 0; j < p; ++j) {
+    const double t = __shfl_sync(0xffffffffu, (j >= 32) ? lg[1] : lg[0], j & 31);
+    halflogdet = halflogdet + t;
+  }
   if (lane == 0) {
-    double halflogdet = 0.0;
-    for (int j = 0; j < p; ++j) halflogdet = halflogdet + ubm_log(Ls[j * p + j]);
     const double cst = -(halflogdet) - (p * 0.9189385);
     double sq = 0.0;
     for (int i = 0; i < p; ++i) sq = ubm_fma(tmp[i], tmp[i], sq);
@@ -332,11 +377,10 @@ struct PgShared {   // scalars
 // observation classes (i mod 4) and keeps its 16 (+16) sums in registers; per observation it reads two 32-byte row
 // segments of the staged X tile and the weights.  Canonical order (oracle: m_sigma): four chains over i mod 4, each
 // sequential in i, then ((((invB + P0) + P1) + P2) + P3).
-#define PG_GS (PG_MAXP + 4)      // row stride of the staged tile (doubles), 16-byte aligned rows
 #define PG_PLIM 60               // 4 classes x nb (nb + 1) / 2 blocks must fit the 512 threads: ceil(p / 4) <= 15
 template <bool TWO>
 __device__ inline void pg_gram(const PgDevice& M, const double* w1, const double* w2, double* A1, double* A2,
-                               double* xs /* [PG_TILE][PG_GS] */, int tid) {
+                               double* xs /* [2][PG_TILE][PG_GS] */, int tid) {
   const int n = M.n, p = M.p;
   const int nb = (p + 3) / 4, nblk = nb * (nb + 1) / 2;
   const int cls = tid / nblk, blk = tid - cls * nblk;
@@ -349,22 +393,36 @@ __device__ inline void pg_gram(const PgDevice& M, const double* w1, const double
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) { a1[r][c] = 0.0; a2[r][c] = 0.0; }
-  for (int i0 = 0; i0 < n; i0 += PG_TILE) {
+  // tiles of 32 observations, double-buffered: the next tile is fetched into registers (three 16-byte loads per thread
+  // from the row-major padded copy of X) before the current one is consumed, and stored afterwards
+  constexpr int NV = PG_TILE * PG_GS / 2;                 // double2 per tile
+  constexpr int PER = (NV + PG_T - 1) / PG_T;
+  __syncthreads();
+  {
+    const double2* src = reinterpret_cast<const double2*>(M.Xt);
+    double2* dst = reinterpret_cast<double2*>(xs);
+    for (int q = tid; q < NV; q += PG_T) dst[q] = src[q];
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int i0 = 0; i0 < n; i0 += PG_TILE, buf ^= 1) {
     const int rows = (n - i0 < PG_TILE) ? (n - i0) : PG_TILE;
-    __syncthreads();
-    for (int q = tid; q < PG_TILE * PG_GS; q += PG_T) {
-      const int ii = q % PG_TILE, j = q / PG_TILE;
-      xs[ii * PG_GS + j] = (ii < rows && j < p) ? M.X[(size_t)j * n + i0 + ii] : 0.0;
+    const double* xt = xs + buf * (PG_TILE * PG_GS);
+    const bool more = i0 + PG_TILE < n;
+    double2 nxt[PER];
+    if (more) {
+      const double2* src = reinterpret_cast<const double2*>(M.Xt + (size_t)(i0 + PG_TILE) * PG_GS);
+#pragma unroll
+      for (int u = 0; u < PER; ++u) { const int q = tid + u * PG_T; nxt[u] = (q < NV) ? src[q] : make_double2(0.0, 0.0); }
     }
-    __syncthreads();
     if (on) {
       for (int ii = cls; ii < rows; ii += 4) {
         const double wa = w1[i0 + ii];
         const double wb = TWO ? w2[i0 + ii] : 0.0;
-        const double2 xa0 = *reinterpret_cast<const double2*>(xs + ii * PG_GS + 4 * bj1);
-        const double2 xa1 = *reinterpret_cast<const double2*>(xs + ii * PG_GS + 4 * bj1 + 2);
-        const double2 xb0 = *reinterpret_cast<const double2*>(xs + ii * PG_GS + 4 * bj2);
-        const double2 xb1 = *reinterpret_cast<const double2*>(xs + ii * PG_GS + 4 * bj2 + 2);
+        const double2 xa0 = *reinterpret_cast<const double2*>(xt + ii * PG_GS + 4 * bj1);
+        const double2 xa1 = *reinterpret_cast<const double2*>(xt + ii * PG_GS + 4 * bj1 + 2);
+        const double2 xb0 = *reinterpret_cast<const double2*>(xt + ii * PG_GS + 4 * bj2);
+        const double2 xb1 = *reinterpret_cast<const double2*>(xt + ii * PG_GS + 4 * bj2 + 2);
         const double xa[4] = {xa0.x, xa0.y, xa1.x, xa1.y}, xb[4] = {xb0.x, xb0.y, xb1.x, xb1.y};
 #pragma unroll
         for (int r = 0; r < 4; ++r)
@@ -376,6 +434,12 @@ __device__ inline void pg_gram(const PgDevice& M, const double* w1, const double
           }
       }
     }
+    if (more) {
+      double2* dst = reinterpret_cast<double2*>(xs + (buf ^ 1) * (PG_TILE * PG_GS));
+#pragma unroll
+      for (int u = 0; u < PER; ++u) { const int q = tid + u * PG_T; if (q < NV) dst[q] = nxt[u]; }
+    }
+    __syncthreads();
   }
   // ((((invB + P0) + P1) + P2) + P3): the four classes add their sums in turn
   for (int turn = 0; turn < 4; ++turn) {
@@ -426,7 +490,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
   double* MB1 = sp; sp += p * p;   //          Linv
   double* MA2 = sp; sp += p * p;
   double* MB2 = sp; sp += p * p;
-  double* xs = sp; sp += PG_TILE * PG_GS;
+  double* xs = sp; sp += 2 * PG_TILE * PG_GS;
   double* beta1 = sp; sp += PG_MAXP;
   double* beta2 = sp; sp += PG_MAXP;
   double* m1 = sp; sp += PG_MAXP;
@@ -480,7 +544,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
     long long time = 0, tau = 0;
     bool met = false;
 #ifdef UBM_PG_TIMING
-    long long tacc[4] = {0, 0, 0, 0}, tprev = clock64(), tsteps = 0, tcoupled = 0;
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tprev = clock64(), tsteps = 0, tcoupled = 0;
 #define PGMARK(i) do { long long now_ = clock64(); tacc[i] += now_ - tprev; tprev = now_; } while (0)
 #else
 #define PGMARK(i) do { } while (0)
@@ -522,7 +586,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
           const double z2 = fabs(xb2);
           const double u1 = cell.u();
           const double la1 = pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * a1 - (pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * a1);
-          if (ubm_log(u1) <= la1) w2[i] = a1;
+          if (pg_log(u1) <= la1) w2[i] = a1;
           else { all_equal = 0; plist[atomicAdd(&sh.flag, 1)] = i; }
         }
       }
@@ -546,7 +610,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
             const double a2 = pg_draw(z2, cell);
             const double u2 = cell.u();
             const double la2 = pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * a2 - (pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * a2);
-            const unsigned okm = __ballot_sync(0xffffffffu, ubm_log(u2) > la2);
+            const unsigned okm = __ballot_sync(0xffffffffu, pg_log(u2) > la2);
             if (okm) {
               const double win = __shfl_sync(0xffffffffu, a2, __ffs(okm) - 1);
               if (lane == 0) w2[i] = win;
@@ -562,8 +626,20 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
       else pg_gram<false>(M, w1, w2, MA1, MA2, xs, tid);
       PGMARK(1);
       // ---- 3. m, L, Linv per chain (warp 0: chain 1, warp 1: chain 2)
-      if (warp == 0) pg_warp_m_sigma(M, MA1, MB1, m1, lane);
-      else if (warp == 1 && coupled_step) pg_warp_m_sigma(M, MA2, MB2, m2, lane);
+      pg_cta_chol(MA1, coupled_step ? MA2 : nullptr, tmp, p, tid);   // src/logisticregression.cpp:49-50 (tmp, zz: scratch)
+      PGMARK(3);
+      if (warp < 2 && (warp == 0 || coupled_step)) {             // warp 0: chain 1, warp 1: chain 2
+        double* A = warp ? MA2 : MA1;
+        double* Linv = warp ? MB2 : MB1;
+        double* m = warp ? m2 : m1;
+        for (int i = lane; i < p; i += 32) m[i] = M.ktk[i];
+        __syncwarp();
+        pg_warp_forward(A, p, lane, m);                          // :51  L y = b
+        pg_warp_backward(A, p, lane, m);                         //      L' x = y
+        PGMARK(4);
+        pg_warp_tri_inverse(A, Linv, p, lane);                   // :55
+        PGMARK(5);
+      }
       __syncthreads();
       if (!coupled_step) {
         // single kernel: beta = fast_rmvnorm_chol(1, m, Linv) (germancredit.run.R:27-28): y_j = sum_{i >= j} z_i Linv(i, j)
@@ -580,9 +656,10 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
         }
       } else {
         // sample_beta (R/logistic_regression.R:180-209): Sigma_c = Linv_c' Linv_c, then LLT of Sigma_c (src/mvnorm.cpp:12,52)
-        if (warp == 0) { pg_warp_ltl(MB1, MA1, p, lane); pg_warp_chol(MA1, p, lane); }
-        else if (warp == 1) { pg_warp_ltl(MB2, MA2, p, lane); pg_warp_chol(MA2, p, lane); }
+        pg_ltl(MB1, MA1, p, tid, PG_T);                                  // all warps: the entries are independent
+        pg_ltl(MB2, MA2, p, tid, PG_T);
         __syncthreads();
+        pg_cta_chol(MA1, MA2, tmp, p, tid);
         if (warp == 0) {                                                  // rmvnorm_max_coupling_ (src/mvnorm.cpp:91-129)
           unsigned long long in0 = sh.in, iu0 = sh.iu;
           // x1 = z U1 + m1, U1 = Ls1': y_j = sum_{i <= j} z_i Ls1(j, i)
@@ -656,8 +733,9 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
     __syncthreads();
 #ifdef UBM_PG_TIMING
     if (tid == 0 && blockIdx.x == 0)
-      printf("pg timing (cycles/step, block 0): steps %lld coupled %lld pg-sweep %.0f gram %.0f linalg+sample %.0f\n", tsteps,
-             tcoupled, (double)tacc[0] / tsteps, (double)tacc[1] / tsteps, (double)tacc[2] / tsteps);
+      printf("pg timing (cycles/step, block 0): steps %lld coupled %lld pg-sweep %.0f gram %.0f | chol %.0f solves %.0f tri-inverse %.0f rest(sample, coupled linalg) %.0f\n", tsteps,
+             tcoupled, (double)tacc[0] / tsteps, (double)tacc[1] / tsteps, (double)tacc[3] / tsteps, (double)tacc[4] / tsteps,
+             (double)tacc[5] / tsteps, (double)tacc[2] / tsteps);
 #endif
     // ---- results
     if (tid == 0) {
@@ -682,7 +760,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
 }
 
 inline size_t pg_smem_bytes(int n, int p) {
-  return (size_t)(2 * n + 4 * p * p + PG_TILE * PG_GS + 8 * PG_MAXP + 4 * PG_MAXP + (n + 1) / 2) * sizeof(double) + sizeof(PgShared) + 16;
+  return (size_t)(2 * n + 4 * p * p + 2 * PG_TILE * PG_GS + 8 * PG_MAXP + 4 * PG_MAXP + (n + 1) / 2) * sizeof(double) + sizeof(PgShared) + 16;
 }
 
 inline int pg_launch(const PgDevice& M, const RunParams& P, bool tape, int nsm, cudaStream_t st, int64_t* launches,
