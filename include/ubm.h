@@ -244,6 +244,10 @@ int ubm_estimator_bins(ubm_handle* h, int32_t dim, const ubm_bins* bins, int64_t
  *   ubm_rnorm_reflectionmax       R/rnorm_reflectionmax.R:18-39                                xy [n][2]
  *   ubm_rmvnorm_reflectionmax     R/mvnorm_couplings.R:94-100 -> src/mvnorm.cpp:185-236        xy [n][2][d]
  *                                 (d = 1 is UBM_ERR_INVALID with the reference's stop() message)
+ *   ubm_rmvnorm_max               R/mvnorm_couplings.R:25 -> src/mvnorm.cpp:91-129 (rmvnorm_max_coupling_)
+ *                                 Sigma1, Sigma2: d x d covariances (LLT taken once on the host)  xy [n][2][d]
+ *   ubm_rmvnorm_max_chol          R/mvnorm_couplings.R:57 -> src/mvnorm.cpp:133-174 (the `<=` of :152 kept) xy [n][2][d]
+ *                                 nattempts [n]: rejection-loop trips (the reference returns it for the cov version)
  *   ubm_fast_rmvnorm_chol         R/mvnorm.R:32 -> src/mvnorm.cpp:30-46                        out [n][d]
  *   ubm_fast_dmvnorm_chol_inverse R/mvnorm.R:69 -> src/mvnorm.cpp:71-86    x [n][d] row-major   out [n]
  * chol / chol_inv: d x d column-major upper-triangular, as R's chol() / solve(chol()).
@@ -255,6 +259,13 @@ int ubm_rnorm_reflectionmax(ubm_handle* h, const ubm_draws* draws, int64_t n, in
 int ubm_rmvnorm_reflectionmax(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d,
                               const double* mu1, const double* mu2, const double* chol, const double* chol_inv,
                               double* xy, int32_t* identical);
+int ubm_rmvnorm_max(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d, const double* mu1,
+                    const double* mu2, const double* Sigma1, const double* Sigma2, double* xy, int32_t* identical,
+                    int32_t* nattempts);
+int ubm_rmvnorm_max_chol(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d,
+                         const double* mu1, const double* mu2, const double* chol1, const double* chol2,
+                         const double* chol_inv1, const double* chol_inv2, double* xy, int32_t* identical,
+                         int32_t* nattempts);
 int ubm_fast_rmvnorm_chol(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d,
                           const double* mean, const double* chol, double* out);
 int ubm_fast_dmvnorm_chol_inverse(ubm_handle* h, int64_t n, int32_t d, const double* x, const double* mean,

@@ -222,6 +222,101 @@ int orc_mvn_sample(int32_t mode, const ubm_draws* draws, int64_t n, int64_t rep_
   return bad ? UBM_ERR_TAPE : UBM_OK;
 }
 
+// rmvnorm_max_coupling_ (src/mvnorm.cpp:91-129, variant 1: A = covariances) and rmvnorm_max_coupling_cholesky
+// (:133-174, variant 0: A = chol, B = chol_inverse, both upper).  Variant 1 takes the LLT once (PgLogisticModel::chol_lower,
+// the same code path as sample_beta's use of this coupling) and then draws / evaluates with sequential sums; variant 0
+// goes through MvnModel's fast_rmvnorm_cholesky_ / fast_dmvnorm_cholesky_inverse_ restatements.
+int orc_mvn_max(int32_t variant, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d, const double* mu1,
+                const double* mu2, const double* A1, const double* A2, const double* B1, const double* B2, double* xy,
+                int32_t* identical, int32_t* nattempts) {
+  int bad = 0;
+  if (variant == 0) {
+    std::vector<double> eye((size_t)d * d, 0.0);
+    for (int j = 0; j < d; ++j) eye[(size_t)j * d + j] = 1.0;
+    ubm_model_mvn s1{}, s2{};
+    s1.d = d; s1.mean_pi = mu1; s1.chol_inv_pi = B1; s1.chol_prop = A1; s1.chol_inv_prop = eye.data(); s1.init_mean = mu1; s1.init_chol = eye.data();
+    s2.d = d; s2.mean_pi = mu2; s2.chol_inv_pi = B2; s2.chol_prop = A2; s2.chol_inv_prop = eye.data(); s2.init_mean = mu2; s2.init_chol = eye.data();
+    MvnModel M1(&s1), M2(&s2);
+    for (int64_t i = 0; i < n; ++i) {
+      Draws D = make_draws(draws, i, rep_offset);
+      double* X = xy + (size_t)i * 2 * d;
+      double* Y = X + d;
+      std::vector<double> x(d);
+      M1.rmvnorm_chol(mu1, M1.c_prop, D, x.data());                                     // :144
+      for (int j = 0; j < d; ++j) X[j] = x[j];
+      const double u1 = ubm_log(D.u());                                                 // :149
+      int na = 0;
+      const bool same = (M1.target(x.data()) + u1) <= M2.target(x.data());              // :152
+      if (!same) {
+        bool accept = false;
+        while (!accept && !D.exhausted) {                                               // :159-168
+          ++na;
+          M2.rmvnorm_chol(mu2, M2.c_prop, D, x.data());
+          const double u2 = ubm_log(D.u());
+          if ((M2.target(x.data()) + u2) > M1.target(x.data())) accept = true;
+        }
+      }
+      for (int j = 0; j < d; ++j) Y[j] = x[j];
+      identical[i] = same ? 1 : 0;
+      if (nattempts) nattempts[i] = na;
+      if (D.exhausted) bad = 1;
+    }
+    return bad ? UBM_ERR_TAPE : UBM_OK;
+  }
+  std::vector<double> L1(A1, A1 + (size_t)d * d), L2(A2, A2 + (size_t)d * d);
+  bool ok = true;
+  PgLogisticModel::chol_lower(L1, d, &ok);
+  PgLogisticModel::chol_lower(L2, d, &ok);
+  auto draw = [&](const double* mu, const std::vector<double>& L, Draws& D, double* out) {   // fast_rmvnorm_ :9-26
+    std::vector<double> z(d);
+    for (int j = 0; j < d; ++j) z[j] = D.n();
+    for (int j = 0; j < d; ++j) {
+      double a = 0.0;
+      for (int q = 0; q <= j; ++q) a = ubm_fma(z[q], L[(size_t)q * d + j], a);
+      out[j] = a + mu[j];
+    }
+  };
+  auto dens = [&](const double* x, const double* mu, const std::vector<double>& L) {         // fast_dmvnorm_ :49-67
+    double halflogdet = 0.0;
+    for (int j = 0; j < d; ++j) halflogdet = halflogdet + ubm_log(L[(size_t)j * d + j]);
+    const double cst = -(halflogdet) - (d * 0.9189385);
+    std::vector<double> y(d);
+    for (int r = 0; r < d; ++r) {
+      double a = x[r] - mu[r];
+      for (int k = 0; k < r; ++k) a = ubm_fma(-L[(size_t)k * d + r], y[k], a);
+      y[r] = a / L[(size_t)r * d + r];
+    }
+    double sq = 0.0;
+    for (int r = 0; r < d; ++r) sq = ubm_fma(y[r], y[r], sq);
+    return -0.5 * sq + cst;
+  };
+  for (int64_t i = 0; i < n; ++i) {
+    Draws D = make_draws(draws, i, rep_offset);
+    double* X = xy + (size_t)i * 2 * d;
+    double* Y = X + d;
+    std::vector<double> x(d);
+    draw(mu1, L1, D, x.data());                                                         // :96
+    for (int j = 0; j < d; ++j) X[j] = x[j];
+    const double logu = ubm_log(D.u());                                                 // :103-106
+    int na = 0;
+    const bool same = (dens(x.data(), mu1, L1) + logu) < dens(x.data(), mu2, L2);       // :107
+    if (!same) {
+      bool accept = false;
+      while (!accept && !D.exhausted) {                                                 // :113-123
+        ++na;
+        draw(mu2, L2, D, x.data());
+        const double lu = ubm_log(D.u());
+        if ((dens(x.data(), mu2, L2) + lu) > dens(x.data(), mu1, L1)) accept = true;
+      }
+    }
+    for (int j = 0; j < d; ++j) Y[j] = x[j];
+    identical[i] = same ? 1 : 0;
+    if (nattempts) nattempts[i] = na;
+    if (D.exhausted) bad = 1;
+  }
+  return bad ? UBM_ERR_TAPE : UBM_OK;
+}
+
 int orc_dmvnorm_chol_inverse(int64_t n, int32_t d, const double* x, const double* mean, const double* chol_inv, double* out) {
   std::vector<double> eye((size_t)d * d, 0.0);
   for (int j = 0; j < d; ++j) eye[(size_t)j * d + j] = 1.0;

@@ -207,6 +207,28 @@ def rmvnorm_reflectionmax(mu1, mu2, Cholesky, Cholesky_inverse, draws, n=1, rep_
     return {"xy": xy, "identical": ident.astype(bool)}
 
 
+def rmvnorm_max(mu1, mu2, Sigma1, Sigma2, draws, n=1, rep_offset=0):
+    mu1, mu2 = np.ascontiguousarray(mu1, dtype=np.float64), np.ascontiguousarray(mu2, dtype=np.float64)
+    d = len(mu1)
+    s1, s2 = _cm(Sigma1), _cm(Sigma2)
+    xy, ident, na = np.zeros((n, 2, d)), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    ds = draws.struct(n)
+    _check(_prim_lib().orc_mvn_max(1, C.byref(ds), n, rep_offset, d, A.dptr(mu1), A.dptr(mu2), A.dptr(s1), A.dptr(s2),
+                                   None, None, A.dptr(xy), A.i32ptr(ident), A.i32ptr(na)))
+    return {"xy": xy, "identical": ident.astype(bool), "nattempts": na}
+
+
+def rmvnorm_max_chol(mu1, mu2, Cholesky1, Cholesky2, Cholesky_inverse1, Cholesky_inverse2, draws, n=1, rep_offset=0):
+    mu1, mu2 = np.ascontiguousarray(mu1, dtype=np.float64), np.ascontiguousarray(mu2, dtype=np.float64)
+    d = len(mu1)
+    c1, c2, i1, i2 = _cm(Cholesky1), _cm(Cholesky2), _cm(Cholesky_inverse1), _cm(Cholesky_inverse2)
+    xy, ident, na = np.zeros((n, 2, d)), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    ds = draws.struct(n)
+    _check(_prim_lib().orc_mvn_max(0, C.byref(ds), n, rep_offset, d, A.dptr(mu1), A.dptr(mu2), A.dptr(c1), A.dptr(c2),
+                                   A.dptr(i1), A.dptr(i2), A.dptr(xy), A.i32ptr(ident), A.i32ptr(na)))
+    return {"xy": xy, "identical": ident.astype(bool), "nattempts": na}
+
+
 def fast_rmvnorm_chol(nparticles, mean, chol, draws, rep_offset=0):
     mean = np.ascontiguousarray(mean, dtype=np.float64)
     d = len(mean)

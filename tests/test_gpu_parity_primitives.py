@@ -50,3 +50,30 @@ def test_rmvnorm_reflectionmax_rejects_univariate(engine):
     with pytest.raises(UbmError) as e:     # R/mvnorm_couplings.R:96-98 stop()
         engine.rmvnorm_reflectionmax([0.0], [1.0], [[1.0]], [[1.0]], R.Draws(seed=1), n=2)
     assert e.value.status == A.UBM_ERR_INVALID
+
+
+@pytest.mark.parametrize("d", [2, 5, 49])
+def test_mvn_max_couplings_bit_exact(engine, oracle, d):
+    """rmvnorm_max (src/mvnorm.cpp:91-129) and rmvnorm_max_chol (:133-174): xy, identical and nattempts, bit for bit."""
+    rng = np.random.default_rng(100 + d)
+    G1, G2 = rng.standard_normal((d, d)), rng.standard_normal((d, d))
+    S1 = G1 @ G1.T / d + np.eye(d)
+    S2 = 0.8 * (G2 @ G2.T / d + np.eye(d))
+    mu1, mu2 = rng.standard_normal(d) * 0.2, rng.standard_normal(d) * 0.2
+    U1, U2 = np.linalg.cholesky(S1).T, np.linalg.cholesky(S2).T
+    I1, I2 = np.triu(np.linalg.inv(U1)), np.triu(np.linalg.inv(U2))
+    n = 400
+    g = engine.rmvnorm_max(mu1, mu2, S1, S2, R.Draws(seed=21), n=n, rep_offset=5)
+    c = oracle.rmvnorm_max(mu1, mu2, S1, S2, R.Draws(seed=21), n=n, rep_offset=5)
+    for key in ("xy", "identical", "nattempts"):
+        assert np.array_equal(g[key], c[key]), key
+    g = engine.rmvnorm_max_chol(mu1, mu2, U1, U2, I1, I2, R.Draws(seed=22), n=n)
+    c = oracle.rmvnorm_max_chol(mu1, mu2, U1, U2, I1, I2, R.Draws(seed=22), n=n)
+    for key in ("xy", "identical", "nattempts"):
+        assert np.array_equal(g[key], c[key]), key
+    assert 0 < g["identical"].mean() < 1 or d > 20
+    # replay tapes (rows long enough for the rejection loops; exhaustion is reported identically)
+    dr = R.Draws(tape_u=rng.uniform(size=(32, 64)), tape_n=rng.standard_normal((32, 64 * d)))
+    g = engine.rmvnorm_max(mu1, mu2, S1, S2, dr, n=32)
+    c = oracle.rmvnorm_max(mu1, mu2, S1, S2, dr, n=32)
+    assert np.array_equal(g["xy"], c["xy"]) and np.array_equal(g["nattempts"], c["nattempts"])

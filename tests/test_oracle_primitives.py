@@ -60,3 +60,44 @@ def test_rmvnorm_reflectionmax_and_densities(oracle):
     lp = oracle.fast_dmvnorm_chol_inverse(s[:200], mu1, Ui)
     ref = stats.multivariate_normal(mu1, Sigma).logpdf(s[:200])
     np.testing.assert_allclose(lp, ref + d * (0.918938533204672741780329736406 - 0.9189385), rtol=0, atol=1e-10)
+
+
+def _mvn_pair(d, seed):
+    rng = np.random.default_rng(seed)
+    G1, G2 = rng.standard_normal((d, d)), rng.standard_normal((d, d))
+    S1 = G1 @ G1.T / d + np.eye(d)
+    S2 = 0.7 * (G2 @ G2.T / d + np.eye(d))
+    mu1, mu2 = rng.standard_normal(d) * 0.3, rng.standard_normal(d) * 0.3
+    return mu1, mu2, S1, S2
+
+
+def _mvn_overlap_mc(mu1, mu2, S1, S2, n=400000, seed=1):
+    """integral of min(p, q) by importance sampling from p."""
+    rng = np.random.default_rng(seed)
+    x = rng.multivariate_normal(mu1, S1, size=n)
+    lp = stats.multivariate_normal(mu1, S1).logpdf(x)
+    lq = stats.multivariate_normal(mu2, S2).logpdf(x)
+    w = np.minimum(1.0, np.exp(lq - lp))
+    return w.mean(), w.std() / np.sqrt(n)
+
+
+def test_rmvnorm_max_marginals_and_meeting_probability(oracle):
+    """src/mvnorm.cpp:91-129 and :133-174: marginals N(mu1, S1), N(mu2, S2); P(identical) = overlap of the two densities;
+    identical <=> bitwise equality; the two parametrisations agree in law."""
+    d, n = 3, 100000
+    mu1, mu2, S1, S2 = _mvn_pair(d, 7)
+    p, pse = _mvn_overlap_mc(mu1, mu2, S1, S2)
+    U1, U2 = np.linalg.cholesky(S1).T, np.linalg.cholesky(S2).T
+    for r in (oracle.rmvnorm_max(mu1, mu2, S1, S2, R.Draws(seed=8), n=n),
+              oracle.rmvnorm_max_chol(mu1, mu2, U1, U2, np.triu(np.linalg.inv(U1)), np.triu(np.linalg.inv(U2)),
+                                      R.Draws(seed=9), n=n)):
+        x, y, ident = r["xy"][:, 0, :], r["xy"][:, 1, :], r["identical"]
+        assert np.array_equal(ident, np.all(x == y, axis=1))
+        for v, mu, S in ((x, mu1, S1), (y, mu2, S2)):
+            assert np.all(np.abs(v.mean(0) - mu) < 5 * np.sqrt(np.diag(S) / n))
+            assert np.max(np.abs(np.cov(v.T) - S)) < 0.03 * np.max(np.diag(S)) + 0.02
+        assert abs(ident.mean() - p) < 4 * np.sqrt(p * (1 - p) / n) + 4 * pse
+        assert np.all(r["nattempts"][ident] == 0) and np.all(r["nattempts"][~ident] >= 1)
+    # equal Normals always meet at the first test
+    r = oracle.rmvnorm_max(mu1, mu1, S1, S1, R.Draws(seed=3), n=64)
+    assert r["identical"].all()

@@ -139,10 +139,15 @@ def load_lib():
                                             c_double_p, c_int32_p]
     lib.ubm_rmvnorm_reflectionmax.argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_int32, c_double_p, c_double_p,
                                               c_double_p, c_double_p, c_double_p, c_int32_p]
+    lib.ubm_rmvnorm_max.argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p,
+                                    c_double_p, c_double_p, c_int32_p, c_int32_p]
+    lib.ubm_rmvnorm_max_chol.argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p,
+                                         c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p, c_int32_p]
     lib.ubm_fast_rmvnorm_chol.argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p]
     lib.ubm_fast_dmvnorm_chol_inverse.argtypes = [vp, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p,
                                                   c_double_p]
     for name in ("ubm_rnorm_max_coupling", "ubm_rnorm_reflectionmax", "ubm_rmvnorm_reflectionmax",
+                 "ubm_rmvnorm_max", "ubm_rmvnorm_max_chol",
                  "ubm_fast_rmvnorm_chol", "ubm_fast_dmvnorm_chol_inverse"):
         getattr(lib, name).restype = C.c_int
     lib.ubm_plan_create.argtypes = [vp, C.c_int32, vp, C.c_int32, C.POINTER(ubm_bins), C.c_int64, C.c_int64,

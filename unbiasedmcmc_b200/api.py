@@ -258,6 +258,20 @@ def rmvnorm_reflectionmax(mu1, mu2, Cholesky, Cholesky_inverse, n=1, seed=1):
     return _squeeze(_eng().rmvnorm_reflectionmax(mu1, mu2, Cholesky, Cholesky_inverse, R.Draws(seed=seed), n=n), n)
 
 
+def rmvnorm_max(mu1, mu2, Sigma1, Sigma2, n=1, seed=1):
+    """R/mvnorm_couplings.R:25 — list(xy, identical, nattempts): maximal coupling of N(mu1, Sigma1) and N(mu2, Sigma2)."""
+    return _squeeze(_eng().rmvnorm_max(mu1, mu2, Sigma1, Sigma2, R.Draws(seed=seed), n=n), n)
+
+
+def rmvnorm_max_chol(mu1, mu2, Cholesky1, Cholesky2, Cholesky_inverse1, Cholesky_inverse2, n=1, seed=1):
+    """R/mvnorm_couplings.R:57 — the same coupling from chol(Sigma) and solve(chol(Sigma)) of both Normals."""
+    for Ch in (Cholesky1, Cholesky2):                                          # :59-61 stopifnot(valid_Cholesky)
+        if np.any(np.tril(np.asarray(Ch, dtype=np.float64), -1) != 0):
+            raise ValueError("valid_Cholesky1, valid_Cholesky2 are not all TRUE: pass chol(Sigma), not its transpose")
+    return _squeeze(_eng().rmvnorm_max_chol(mu1, mu2, Cholesky1, Cholesky2, Cholesky_inverse1, Cholesky_inverse2,
+                                            R.Draws(seed=seed), n=n), n)
+
+
 def fast_rmvnorm_chol(nparticles, mean, chol, seed=1):
     """R/mvnorm.R:32."""
     return _eng().fast_rmvnorm_chol(nparticles, mean, chol, R.Draws(seed=seed))

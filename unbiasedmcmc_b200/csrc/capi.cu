@@ -701,6 +701,61 @@ static int mvn_sample(ubm_handle* h, const ubm_draws* draws, int mode, int64_t n
   return st;
 }
 
+static int mvn_max(ubm_handle* h, const ubm_draws* draws, int variant, int64_t n, int64_t rep_offset, int32_t d,
+                   const double* mu1, const double* mu2, const double* A1, const double* A2, const double* B1,
+                   const double* B2, double* xy, int32_t* identical, int32_t* nattempts) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!mu1 || !mu2 || !A1 || !A2 || !xy || !identical || (variant == 0 && (!B1 || !B2))) return fail(h, UBM_ERR_INVALID, "null argument");
+  if (d < 1 || d > PRIM_MAXD) return fail(h, UBM_ERR_INVALID, "1 <= d <= 128");
+  const size_t vb = (size_t)d * 8, mb = (size_t)d * d * 8;
+  std::vector<double> L1, L2;
+  double cst1, cst2;
+  if (variant == 1) {       // LLT of the covariances (src/mvnorm.cpp:12, :52), once for the whole batch
+    L1.assign(A1, A1 + (size_t)d * d); L2.assign(A2, A2 + (size_t)d * d);
+    pg_chol_lower_host(L1, d); pg_chol_lower_host(L2, d);
+    for (int j = 0; j < d; ++j)
+      if (!(L1[(size_t)j * d + j] > 0.0) || !(L2[(size_t)j * d + j] > 0.0)) return fail(h, UBM_ERR_INVALID, "rmvnorm_max: covariance not positive definite");
+    double h1 = 0.0, h2 = 0.0;
+    for (int j = 0; j < d; ++j) { h1 = h1 + ubm_log(L1[(size_t)j * d + j]); h2 = h2 + ubm_log(L2[(size_t)j * d + j]); }
+    cst1 = -(h1) - (d * 0.9189385); cst2 = -(h2) - (d * 0.9189385);            // :55-56
+    A1 = L1.data(); A2 = L2.data();
+  } else {
+    double h1 = 0.0, h2 = 0.0;
+    for (int j = 0; j < d; ++j) { h1 = h1 + ubm_log(B1[(size_t)j * d + j]); h2 = h2 + ubm_log(B2[(size_t)j * d + j]); }
+    cst1 = -(-h1) - (d * 0.9189385); cst2 = -(-h2) - (d * 0.9189385);          // :74-75
+  }
+  RunParams P; DevBuf tu, tn, status, dm1, dm2, da1, da2, db1, db2, dout, did, dna;
+  int st = prim_params(h, draws, n, rep_offset, &P, &tu, &tn, &status);
+  if (st != UBM_OK) return st;
+  CU(dm1.alloc(vb)); CU(dm2.alloc(vb)); CU(da1.alloc(mb)); CU(da2.alloc(mb)); CU(db1.alloc(mb)); CU(db2.alloc(mb));
+  CU(dout.alloc((size_t)n * 2 * d * 8)); CU(did.alloc((size_t)n * 4)); CU(dna.alloc((size_t)n * 4));
+  CU(cudaMemcpy(dm1.p, mu1, vb, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dm2.p, mu2, vb, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(da1.p, A1, mb, cudaMemcpyHostToDevice)); CU(cudaMemcpy(da2.p, A2, mb, cudaMemcpyHostToDevice));
+  if (variant == 0) { CU(cudaMemcpy(db1.p, B1, mb, cudaMemcpyHostToDevice)); CU(cudaMemcpy(db2.p, B2, mb, cudaMemcpyHostToDevice)); }
+  const unsigned grid = (unsigned)((n + 63) / 64);
+  if (draws->mode == UBM_DRAWS_TAPE)
+    prim_mvn_max_kernel<true><<<grid, 64, 0, h->stream>>>(P, variant, d, dm1.as<double>(), dm2.as<double>(), da1.as<double>(), da2.as<double>(), db1.as<double>(), db2.as<double>(), cst1, cst2, dout.as<double>(), did.as<int>(), dna.as<int>());
+  else
+    prim_mvn_max_kernel<false><<<grid, 64, 0, h->stream>>>(P, variant, d, dm1.as<double>(), dm2.as<double>(), da1.as<double>(), da2.as<double>(), db1.as<double>(), db2.as<double>(), cst1, cst2, dout.as<double>(), did.as<int>(), dna.as<int>());
+  h->launches += 1;
+  st = prim_finish(h, &status);
+  CU(cudaMemcpy(xy, dout.p, (size_t)n * 2 * d * 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(identical, did.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (nattempts) CU(cudaMemcpy(nattempts, dna.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return st;
+}
+int ubm_rmvnorm_max(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d, const double* mu1,
+                    const double* mu2, const double* Sigma1, const double* Sigma2, double* xy, int32_t* identical,
+                    int32_t* nattempts) {
+  return mvn_max(h, draws, 1, n, rep_offset, d, mu1, mu2, Sigma1, Sigma2, nullptr, nullptr, xy, identical, nattempts);
+}
+int ubm_rmvnorm_max_chol(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d,
+                         const double* mu1, const double* mu2, const double* chol1, const double* chol2,
+                         const double* chol_inv1, const double* chol_inv2, double* xy, int32_t* identical,
+                         int32_t* nattempts) {
+  return mvn_max(h, draws, 0, n, rep_offset, d, mu1, mu2, chol1, chol2, chol_inv1, chol_inv2, xy, identical, nattempts);
+}
+
 int ubm_fast_rmvnorm_chol(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d,
                           const double* mean, const double* chol, double* out) {
   return mvn_sample(h, draws, 0, n, rep_offset, d, mean, nullptr, chol, nullptr, out, nullptr);

@@ -120,6 +120,78 @@ __global__ void prim_mvn_sample_kernel(const RunParams P, int mode, int d, const
   if (D.bad) atomicExch(P.status, UBM_ERR_TAPE);
 }
 
+// Maximal coupling of two multivariate Normals by rejection, one thread per sample.
+//   variant 0: rmvnorm_max_coupling_cholesky (src/mvnorm.cpp:133-174): F?a = chol (upper), F?b = chol_inverse (upper);
+//              draws through fast_rmvnorm_cholesky_ (:30-46), densities through fast_dmvnorm_cholesky_inverse_ (:71-86),
+//              first test `<=` (:152), loop test `>` (:163)
+//   variant 1: rmvnorm_max_coupling_ (src/mvnorm.cpp:91-129): F?a = lower Cholesky factor L of the covariance (the
+//              LLT of fast_rmvnorm_ :12 / fast_dmvnorm_ :52, taken once on the host); y = z L' + mean, density by
+//              forward substitution; first test `<` (:107), loop test `>` (:118)
+// cst? = the density constants (sum of log-diagonals and -d * 0.9189385), computed on the host in the oracle's order.
+template <bool TAPE>
+__global__ void prim_mvn_max_kernel(const RunParams P, int variant, int d, const double* __restrict__ mu1,
+                                    const double* __restrict__ mu2, const double* __restrict__ F1a,
+                                    const double* __restrict__ F2a, const double* __restrict__ F1b,
+                                    const double* __restrict__ F2b, double cst1, double cst2, double* __restrict__ xy,
+                                    int* __restrict__ ident, int* __restrict__ natt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nrep) return;
+  ScalarDraws<TAPE> D;
+  D.init(P, i);
+  double z[PRIM_MAXD], x[PRIM_MAXD], t[PRIM_MAXD];
+  auto draw = [&](const double* mu, const double* Fa, double* out) {
+    for (int j = 0; j < d; ++j) z[j] = D.n();
+    if (variant == 0) {
+      prim_vec_times_upper(z, Fa, d, t);
+      for (int j = 0; j < d; ++j) out[j] = t[j] + mu[j];
+    } else {
+      for (int j = 0; j < d; ++j) {                                   // y_j = sum_{i <= j} z_i L(j, i)
+        double a = 0.0;
+        for (int q = 0; q <= j; ++q) a = ubm_fma(z[q], Fa[(size_t)q * d + j], a);
+        out[j] = a + mu[j];
+      }
+    }
+  };
+  auto dens = [&](const double* pt, const double* mu, const double* Fa, const double* Fb, double cst) -> double {
+    if (variant == 0) {
+      for (int j = 0; j < d; ++j) z[j] = pt[j] - mu[j];
+      prim_vec_times_upper(z, Fb, d, t);
+      return -0.5 * prim_sum_g4(t, t, d) + cst;
+    }
+    for (int r = 0; r < d; ++r) {                                     // L y = pt - mu
+      double a = pt[r] - mu[r];
+      for (int k = 0; k < r; ++k) a = ubm_fma(-Fa[(size_t)k * d + r], t[k], a);
+      t[r] = a / Fa[(size_t)r * d + r];
+    }
+    double sq = 0.0;
+    for (int r = 0; r < d; ++r) sq = ubm_fma(t[r], t[r], sq);
+    return -0.5 * sq + cst;
+  };
+  double* X = xy + (size_t)i * 2 * d;
+  double* Y = X + d;
+  draw(mu1, F1a, x);
+  for (int j = 0; j < d; ++j) X[j] = x[j];
+  const double logu = ubm_log(D.u());
+  const double d11 = dens(x, mu1, F1a, F1b, cst1), d12 = dens(x, mu2, F2a, F2b, cst2);
+  const bool same = (variant == 0) ? (d11 + logu <= d12) : (d11 + logu < d12);
+  int n = 0;
+  if (same) { for (int j = 0; j < d; ++j) Y[j] = x[j]; }
+  else {
+    bool accept = false;
+    while (!accept && !D.bad) {
+      ++n;
+      draw(mu2, F2a, x);
+      const double lu = ubm_log(D.u());
+      const double d22 = dens(x, mu2, F2a, F2b, cst2), d21 = dens(x, mu1, F1a, F1b, cst1);
+      if (d22 + lu > d21) accept = true;
+    }
+    for (int j = 0; j < d; ++j) Y[j] = x[j];
+  }
+  ident[i] = same ? 1 : 0;
+  natt[i] = n;
+  if (D.bad) atomicExch(P.status, UBM_ERR_TAPE);
+}
+
 // fast_dmvnorm_cholesky_inverse_ (src/mvnorm.cpp:71-86): x [n][d] -> out [n]
 __global__ void prim_dmvnorm_kernel(int64_t n, int d, const double* __restrict__ x, const double* __restrict__ mean,
                                     const double* __restrict__ chol_inv, double cst, double* __restrict__ out) {

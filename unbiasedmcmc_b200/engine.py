@@ -153,6 +153,32 @@ class Engine:
                                                        A.dptr(ch), A.dptr(ci), A.dptr(xy), A.i32ptr(ident)))
         return {"xy": xy, "identical": ident.astype(bool)}
 
+    def rmvnorm_max(self, mu1, mu2, Sigma1, Sigma2, draws, n=1, rep_offset=0):
+        """R/mvnorm_couplings.R:25 -> src/mvnorm.cpp:91-129."""
+        mu1, mu2 = np.ascontiguousarray(mu1, dtype=np.float64), np.ascontiguousarray(mu2, dtype=np.float64)
+        d = len(mu1)
+        cm = lambda M: np.ascontiguousarray(np.asarray(M, dtype=np.float64).T).reshape(-1)       # column-major
+        s1, s2 = cm(Sigma1), cm(Sigma2)
+        xy, ident, na = np.zeros((n, 2, d)), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        ds = draws.struct(n)
+        self._check(self.lib.ubm_rmvnorm_max(self.h, C.byref(ds), n, rep_offset, d, A.dptr(mu1), A.dptr(mu2), A.dptr(s1),
+                                             A.dptr(s2), A.dptr(xy), A.i32ptr(ident), A.i32ptr(na)))
+        return {"xy": xy, "identical": ident.astype(bool), "nattempts": na}
+
+    def rmvnorm_max_chol(self, mu1, mu2, Cholesky1, Cholesky2, Cholesky_inverse1, Cholesky_inverse2, draws, n=1,
+                         rep_offset=0):
+        """R/mvnorm_couplings.R:57 -> src/mvnorm.cpp:133-174."""
+        mu1, mu2 = np.ascontiguousarray(mu1, dtype=np.float64), np.ascontiguousarray(mu2, dtype=np.float64)
+        d = len(mu1)
+        cm = lambda M: np.ascontiguousarray(np.asarray(M, dtype=np.float64).T).reshape(-1)
+        c1, c2, i1, i2 = cm(Cholesky1), cm(Cholesky2), cm(Cholesky_inverse1), cm(Cholesky_inverse2)
+        xy, ident, na = np.zeros((n, 2, d)), np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        ds = draws.struct(n)
+        self._check(self.lib.ubm_rmvnorm_max_chol(self.h, C.byref(ds), n, rep_offset, d, A.dptr(mu1), A.dptr(mu2),
+                                                  A.dptr(c1), A.dptr(c2), A.dptr(i1), A.dptr(i2), A.dptr(xy),
+                                                  A.i32ptr(ident), A.i32ptr(na)))
+        return {"xy": xy, "identical": ident.astype(bool), "nattempts": na}
+
     def fast_rmvnorm_chol(self, nparticles, mean, chol, draws, rep_offset=0):
         mean = np.ascontiguousarray(mean, dtype=np.float64)
         d = len(mean)
