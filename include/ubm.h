@@ -133,6 +133,9 @@ typedef struct {
   const double* Y;        /* [n] responses in {0, 1} */
   const double* b;        /* [p] prior mean */
   const double* B;        /* p x p prior covariance (column-major, symmetric positive definite) */
+  int32_t w_coupling;     /* sample_w(mode=) of R/logistic_regression.R:166-175: 0 = 'max' (w_max_couplingC, the scripts'
+                             choice), 1 = 'rej_samp' (w_rejsamplerC, src/logisticregressioncoupling.cpp:42-75) */
+  int32_t reserved;
 } ubm_model_pg_logistic;
 
 /* C5: Bayesian variable selection, g-prior spike-and-slab, flip / swap Metropolis-Hastings on gamma in {0,1}^p,

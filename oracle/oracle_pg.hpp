@@ -156,7 +156,7 @@ inline double pg_logcosh(double x) {
 
 struct PgLogisticModel {
   struct State { std::vector<double> beta; uint64_t sweep = 0; };
-  int n = 0, p = 0;
+  int n = 0, p = 0, w_coupling = 0;   // w_coupling: sample_w(mode=): 0 'max', 1 'rej_samp'
   std::vector<double> X;        // n x p column-major
   std::vector<double> invB;     // p x p column-major  (logisticregression_precomputation, R/logistic_regression.R:34-50)
   std::vector<double> ktk;      // KTkappaplusinvBtimesb = X^T (Y - 1/2) + invB b
@@ -180,7 +180,7 @@ struct PgLogisticModel {
   }
 
   explicit PgLogisticModel(const ubm_model_pg_logistic* s) {
-    n = s->n; p = s->p;
+    n = s->n; p = s->p; w_coupling = s->w_coupling;
     X.assign(s->X, s->X + (size_t)n * p);
     b.assign(s->b, s->b + p);
     // invB = solve(B); ktk = t(X) %*% (Y - 0.5) + invB %*% b  (host-side precomputation, as in R)
@@ -338,6 +338,19 @@ struct PgLogisticModel {
     for (int i = 0; i < n; ++i) {                                    // src/logisticregressioncoupling.cpp:87-113
       CellDraws c(&D, s1.sweep * (uint64_t)n + i);
       const double z1 = fabs(z1s[i]), z2 = fabs(z2s[i]);
+      if (w_coupling == 1) {                                         // w_rejsamplerC — src/logisticregressioncoupling.cpp:42-75
+        const double z_min = z1 < z2 ? z1 : z2, z_max = z1 < z2 ? z2 : z1;   // std::min / std::max (:54-55)
+        const double w_min = pg_draw(z_min, c);                      // :57
+        const double log_u = ubm_log(c.u());                         // :59
+        const double log_ratio = -0.5 * w_min * (z_max * z_max - z_min * z_min);   // :61 (pow(z, 2.) is exact)
+        double w_max;
+        if (log_u < log_ratio) w_max = w_min;                        // :62-63
+        else { c.set_attempt(1); w_max = pg_draw(z_max, c); }        // :65, second draw = attempt 1 of the cell
+        if (z1 < z2) { w1[i] = w_min; w2[i] = w_max; } else { w1[i] = w_max; w2[i] = w_min; }   // :67-73
+        if (w1[i] != w2[i]) all_equal = false;
+        if (c.overflow) D.exhausted = true;
+        continue;
+      }
       const double a1 = pg_draw(z1, c);
       double a2;
       const double u1 = c.u();

@@ -55,10 +55,10 @@ def c3_data(n=1000, p=49, seed=SEED):
     return Y, X
 
 
-def c3_model(n=1000, p=49, seed=SEED):
+def c3_model(n=1000, p=49, seed=SEED, mode="max"):
     """germancredit.run.R:18-20: prior b = 0, B = 10 I."""
     Y, X = c3_data(n, p, seed)
-    return R.PgLogistic(Y, X, np.zeros(p), 10.0 * np.eye(p))
+    return R.PgLogistic(Y, X, np.zeros(p), 10.0 * np.eye(p), mode=mode)
 
 
 def c5_data(n=500, p=1000, snr=1.0, seed=SEED):

@@ -39,6 +39,20 @@ def test_c3_meetingtime_and_chains(engine, oracle):
         assert np.array_equal(g["samples2"][r, :nrow - 1], c["samples2"][r, :nrow - 1])
 
 
+def test_c3_rejsampler_coupling_bit_exact(engine, oracle):
+    """sample_w(mode = 'rej_samp'): w_rejsamplerC (src/logisticregressioncoupling.cpp:42-75) instead of w_max_couplingC."""
+    mdl = cases.c3_model(200, 7, seed=4, mode="rej_samp")
+    kw = dict(h_kind=A.UBM_H_BOTH, k=5, m=40, lag=1, nrep=32, max_iterations=400)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=6), **kw)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=6), nthreads=8, **kw)
+    assert_same(g, c, KEYS)
+    assert np.isfinite(g["meetingtime"]).mean() > 0.5
+    # the two couplings share the marginal kernel: identical chains until the first coupled step, different meeting times
+    g0 = engine.sample_meetingtime(cases.c3_model(200, 7, seed=4), R.Draws(seed=6), lag=1, nrep=32)
+    g1 = engine.sample_meetingtime(mdl, R.Draws(seed=6), lag=1, nrep=32)
+    assert not np.array_equal(g0["meetingtime"], g1["meetingtime"])
+
+
 def test_c3_tape_mode_is_refused(engine):
     from unbiasedmcmc_b200.engine import UbmError
     mdl = cases.c3_model(60, 3)

@@ -65,3 +65,18 @@ def test_c5_marginal_likelihood_and_inclusion_probabilities(oracle):
     assert np.all(s.mean(0)[:10] > 0.9) and np.all(s.mean(0)[10:] < 0.2)      # the 10 true signals are found
     # states are 0/1 vectors with at most s0 ones
     assert set(np.unique(s)) <= {0.0, 1.0} and s.sum(1).max() <= 10
+
+
+def test_c3_rejsampler_coupling_is_a_valid_coupling(oracle):
+    """w_rejsamplerC (src/logisticregressioncoupling.cpp:42-75): chain 1 follows the same single-chain law as under the
+    max coupling (same posterior means from the unbiased estimators), and the chains meet."""
+    est = {}
+    for mode in ("max", "rej_samp"):
+        mdl = cases.c3_model(120, 4, seed=3, mode=mode)
+        r = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=11), k=20, m=120, lag=1, nrep=400, nthreads=8,
+                                            max_iterations=5000)
+        assert np.isfinite(r["meetingtime"]).all()
+        est[mode] = (r["uestimator"].mean(0), r["uestimator"].std(0, ddof=1) / np.sqrt(400))
+    diff = est["max"][0] - est["rej_samp"][0]
+    se = np.sqrt(est["max"][1] ** 2 + est["rej_samp"][1] ** 2)
+    assert np.all(np.abs(diff) < 4.5 * se)

@@ -100,9 +100,10 @@ def ising_pt_kernels(betas, proba_swapmove):
     return {"single_kernel": m, "coupled_kernel": m, "rinit": m}
 
 
-def logisticregression_kernels(Y, X, b, B):
-    """single_kernel / coupled_kernel / rinit of inst/reproducegermancredit/germancredit.run.R:23-49."""
-    m = R.PgLogistic(Y, X, b, B)
+def logisticregression_kernels(Y, X, b, B, mode="max"):
+    """single_kernel / coupled_kernel / rinit of inst/reproducegermancredit/germancredit.run.R:23-49; `mode` is
+    sample_w's (R/logistic_regression.R:166): 'max' (w_max_couplingC) or 'rej_samp' (w_rejsamplerC)."""
+    m = R.PgLogistic(Y, X, b, B, mode=mode)
     return {"single_kernel": m, "coupled_kernel": m, "rinit": m}
 
 

@@ -35,7 +35,7 @@ namespace ubm {
 #define PG_TRUNC_D 0.64
 
 struct PgDevice {
-  int n, p, ne;
+  int n, p, ne, w_coupling;
   const double *X, *invB, *ktk, *b, *cholB;   // device: X n x p col-major; invB p x p; ktk, b [p]; cholB upper p x p
   const double *Xt;                            // device: X again, row-major [ceil(n/32)*32][PG_GS], zero padded: the Gram tiles
   size_t offs[6];
@@ -58,7 +58,7 @@ inline void pg_chol_lower_host(std::vector<double>& A, int p) {
 }
 inline void pg_pack_host(const ubm_model_pg_logistic* s, PgDevice* M, std::vector<double>* blob) {
   const int n = s->n, p = s->p;
-  M->n = n; M->p = p; M->ne = p * (p + 1) / 2;
+  M->n = n; M->p = p; M->ne = p * (p + 1) / 2; M->w_coupling = s->w_coupling;
   std::vector<double> LB(s->B, s->B + (size_t)p * p);
   pg_chol_lower_host(LB, p);
   std::vector<double> cholB((size_t)p * p, 0.0), Li((size_t)p * p, 0.0), invB((size_t)p * p, 0.0), ktk(p, 0.0);
@@ -580,6 +580,20 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
         }
         PgCell cell(P.seed, grep, sweep * (unsigned long long)n + (unsigned long long)i);
         const double z1 = fabs(xb1);
+        if (coupled_step && M.w_coupling == 1) {                          // w_rejsamplerC (logisticregressioncoupling.cpp:42-75)
+          const double z2 = fabs(xb2);
+          const double z_min = z1 < z2 ? z1 : z2, z_max = z1 < z2 ? z2 : z1;
+          const double w_min = pg_draw(z_min, cell);
+          const double log_u = pg_log(cell.u());
+          const double log_ratio = -0.5 * w_min * (z_max * z_max - z_min * z_min);
+          double w_max;
+          if (log_u < log_ratio) w_max = w_min;
+          else { cell.set_attempt(1); w_max = pg_draw(z_max, cell); }
+          const double wa = (z1 < z2) ? w_min : w_max, wb = (z1 < z2) ? w_max : w_min;
+          w1[i] = wa; w2[i] = wb;
+          if (wa != wb) all_equal = 0;
+          continue;
+        }
         const double a1 = pg_draw(z1, cell);
         w1[i] = a1;
         if (coupled_step) {
