@@ -104,7 +104,7 @@ def workload(name):
             s = 15.0
             per = s ** 3 / 3.0 + 2.0 * s * s
             return per * (sum_iter + (sum_tau - S[0]))
-        return mdl, kw, 2960, desc, flops, "fp64"
+        return mdl, kw, 8288, desc, flops, "fp64"      # 4 waves of 148 SMs x 14 resident warps
     raise SystemExit(f"unknown workload {name}")
 
 

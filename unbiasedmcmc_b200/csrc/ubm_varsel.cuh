@@ -24,13 +24,14 @@ namespace ubm {
 #define VS_MAXW 32
 #define FULLMASK 0xffffffffu
 #ifndef VS_SFAST
-#define VS_SFAST 63      // selections of at most this many variables are factorised in shared memory (17 KB per warp), larger ones in an L2-resident per-warp buffer
+#define VS_SFAST 59      // selections of at most this many variables are factorised in shared memory (16 KB per warp), larger ones in an L2-resident per-warp buffer
+                         // (measured on C5: 63 -> 4.65 K est/s at 12 warps/SM, 59 -> 5.58 K at 14, 55 -> 5.3 K at 16, 51 -> 4.2 K: the fallback is slow)
 #endif
 #ifndef VS_WPB
-#define VS_WPB 4         // replicates (warps) per CTA
+#define VS_WPB 2         // replicates (warps) per CTA
 #endif
 #ifndef VS_MINB
-#define VS_MINB 3        // CTAs per SM asked of the register allocator (x VS_WPB warps)
+#define VS_MINB 7        // CTAs per SM asked of the register allocator (x VS_WPB warps)
 #endif
 
 struct VarselDevice {
