@@ -164,14 +164,19 @@ __device__ __forceinline__ double vs_chol_core(const VarselDevice& M, double* __
         double* __restrict__ row = Lb + i * (i + 1) / 2;
         const double nl = -colk[i];
         const int cmax = (i == s) ? s - 1 : i;           // the right-hand-side row has no diagonal entry
-        int c = k + 1;
-        for (; c + 3 <= cmax; c += 4) {
-          const double b0 = colk[c], b1 = colk[c + 1], b2 = colk[c + 2], b3 = colk[c + 3];
-          const double a0 = row[c], a1 = row[c + 1], a2 = row[c + 2], a3 = row[c + 3];
-          row[c] = ubm_fma(nl, b0, a0); row[c + 1] = ubm_fma(nl, b1, a1);
-          row[c + 2] = ubm_fma(nl, b2, a2); row[c + 3] = ubm_fma(nl, b3, a3);
+        // eight independent entries per trip, guarded (a scalar remainder loop of dependent load-fma-store trips cost
+        // as much as the unrolled part: ncu, profiles/r01_other_kernels.md)
+        for (int c0 = k + 1; c0 <= cmax; c0 += 8) {
+          double a[8], b[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const bool ok = c0 + q <= cmax;
+            a[q] = ok ? row[c0 + q] : 0.0;
+            b[q] = ok ? colk[c0 + q] : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) if (c0 + q <= cmax) row[c0 + q] = ubm_fma(nl, b[q], a[q]);
         }
-        for (; c <= cmax; ++c) row[c] = ubm_fma(nl, colk[c], row[c]);
         if (i == k + 1) newpiv = row[k + 1];             // entry (k+1, k+1): the next pivot (lane 0)
       }
       piv = __shfl_sync(FULLMASK, newpiv, 0);
