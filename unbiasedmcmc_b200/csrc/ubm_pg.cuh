@@ -269,20 +269,27 @@ __device__ inline void pg_cta_chol(double* A1, double* A2, double* dg, int p, in
   for (int k = t; k < p; k += nthr) A[k * p + k] = d[k];
   __syncthreads();
 }
-// solve L y = rhs (forward), y overwrites `v` (shared); terms taken in increasing column order
+// solve L y = rhs (forward), y overwrites `v` (shared); terms taken in increasing column order.  The diagonal sits in
+// registers (lane k mod 32) and the column of the next step is requested one step ahead, so a step is one shuffle
+// pair, one division and one fma deep.
 __device__ inline void pg_warp_forward(const double* L, int p, int lane, double* v) {
-  double s[2];
+  double s[2], dg[2];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) { const int i = lane + 32 * q; s[q] = (i < p) ? v[i] : 0.0; }
+  for (int q = 0; q < 2; ++q) {
+    const int i = lane + 32 * q;
+    s[q] = (i < p) ? v[i] : 0.0;
+    dg[q] = (i < p) ? L[i * p + i] : 1.0;
+  }
+  double c0 = (lane < p) ? L[lane] : 0.0, c1 = (lane + 32 < p) ? L[lane + 32] : 0.0;          // column 0
   for (int k = 0; k < p; ++k) {
     const double sk = __shfl_sync(0xffffffffu, (k >= 32) ? s[1] : s[0], k & 31);
-    const double yk = sk / L[k * p + k];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int i = lane + 32 * q;
-      if (i == k) s[q] = yk;
-      else if (i > k && i < p) s[q] = ubm_fma(-L[k * p + i], yk, s[q]);
-    }
+    const double dk = __shfl_sync(0xffffffffu, (k >= 32) ? dg[1] : dg[0], k & 31);
+    double n0 = 0.0, n1 = 0.0;
+    if (k + 1 < p) { if (lane < p) n0 = L[(k + 1) * p + lane]; if (lane + 32 < p) n1 = L[(k + 1) * p + lane + 32]; }
+    const double yk = sk / dk;
+    if (lane == k) s[0] = yk; else if (lane > k && lane < p) s[0] = ubm_fma(-c0, yk, s[0]);
+    if (lane + 32 == k) s[1] = yk; else if (lane + 32 > k && lane + 32 < p) s[1] = ubm_fma(-c1, yk, s[1]);
+    c0 = n0; c1 = n1;
   }
 #pragma unroll
   for (int q = 0; q < 2; ++q) { const int i = lane + 32 * q; if (i < p) v[i] = s[q]; }
@@ -290,18 +297,24 @@ __device__ inline void pg_warp_forward(const double* L, int p, int lane, double*
 }
 // solve L' x = y (backward), in place in `v`; terms taken from the last row upwards (as the oracle)
 __device__ inline void pg_warp_backward(const double* L, int p, int lane, double* v) {
-  double s[2];
+  double s[2], dg[2];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) { const int i = lane + 32 * q; s[q] = (i < p) ? v[i] : 0.0; }
+  for (int q = 0; q < 2; ++q) {
+    const int i = lane + 32 * q;
+    s[q] = (i < p) ? v[i] : 0.0;
+    dg[q] = (i < p) ? L[i * p + i] : 1.0;
+  }
+  // row k of L, element i: L(k, i) = L[i * p + k]
+  double c0 = (lane < p) ? L[lane * p + p - 1] : 0.0, c1 = (lane + 32 < p) ? L[(lane + 32) * p + p - 1] : 0.0;
   for (int k = p - 1; k >= 0; --k) {
     const double sk = __shfl_sync(0xffffffffu, (k >= 32) ? s[1] : s[0], k & 31);
-    const double xk = sk / L[k * p + k];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int i = lane + 32 * q;
-      if (i == k) s[q] = xk;
-      else if (i < k) s[q] = ubm_fma(-L[i * p + k], xk, s[q]);     // L(k, i)
-    }
+    const double dk = __shfl_sync(0xffffffffu, (k >= 32) ? dg[1] : dg[0], k & 31);
+    double n0 = 0.0, n1 = 0.0;
+    if (k > 0) { if (lane < p) n0 = L[lane * p + k - 1]; if (lane + 32 < p) n1 = L[(lane + 32) * p + k - 1]; }
+    const double xk = sk / dk;
+    if (lane == k) s[0] = xk; else if (lane < k) s[0] = ubm_fma(-c0, xk, s[0]);
+    if (lane + 32 == k) s[1] = xk; else if (lane + 32 < k) s[1] = ubm_fma(-c1, xk, s[1]);
+    c0 = n0; c1 = n1;
   }
 #pragma unroll
   for (int q = 0; q < 2; ++q) { const int i = lane + 32 * q; if (i < p) v[i] = s[q]; }
