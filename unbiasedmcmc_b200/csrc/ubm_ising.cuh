@@ -171,7 +171,13 @@ __device__ __forceinline__ void ising_swap_move(const IsingDevice& M, IsingShare
 
 // One CTA per replicate, warp c = temperature c.
 template <bool TAPE>
-__global__ void __launch_bounds__(1024) ising_driver_kernel(const IsingDevice M, const RunParams P) {
+#ifndef ISING_MAXT
+#define ISING_MAXT 1024      // threads per CTA the kernel is compiled for (32 temperatures)
+#endif
+#ifndef ISING_MINB
+#define ISING_MINB 1
+#endif
+__global__ void __launch_bounds__(ISING_MAXT, ISING_MINB) ising_driver_kernel(const IsingDevice M, const RunParams P) {
   __shared__ IsingShared sh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = M.N;
