@@ -151,6 +151,33 @@ def test_c2_estimator_bit_exact(engine, oracle, d, lag, k, m, h):
     assert_same(g, c, ["meetingtime", "iteration", "cost", "uestimator", "mcmcestimator", "correction", "summary"])
 
 
+def test_c2_full_size_properties(engine):
+    """BASELINE.json configs[1] at full size (d = 100, k = 2000, m = 10000, lag = 1), where the oracle is too slow to be the
+    checker: size-independent properties instead — cost / iteration identities (R/coupled_chains.R:82), uestimator =
+    mcmc + correction (R/unbiasedestimator.R:98-102), unbiasedness for E[x] = 0 and E[x^2] = diag(Sigma), the summary's
+    fixed-order means, and independence of the results from how the replicates are split over launches."""
+    d, k, m, nrep = 100, 2000, 10000, 1184
+    mdl = cases.c2_model(d)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=4), h_kind=A.UBM_H_BOTH, k=k, m=m, lag=1, nrep=nrep)
+    tau, it, cost = g["meetingtime"], g["iteration"], g["cost"]
+    assert np.isfinite(tau).all() and tau.min() >= 2
+    assert np.array_equal(it, np.maximum(tau, m).astype(np.int64))
+    assert np.array_equal(cost, 1 + 2 * (tau - 1) + np.maximum(0, it - tau))
+    u = g["uestimator"]          # (mcmc + correction) / (m - k + 1): one rounding away from the sum of the two outputs
+    np.testing.assert_allclose(u, g["mcmcestimator"] + g["correction"], rtol=1e-14, atol=1e-15)
+    se = u.std(0, ddof=1) / np.sqrt(nrep)
+    truth = np.concatenate([np.zeros(d), np.diag(cases.mvn_sigma(d))])
+    zs = (u.mean(0) - truth) / se
+    assert np.abs(zs).max() < 5.0 and (np.abs(zs) > 3).sum() <= 4
+    assert g["summary"][0] == nrep and g["summary"][1] == 0            # all done, none censored
+    np.testing.assert_allclose(g["summary"][6:6 + 2 * d] / nrep, u.mean(0), rtol=1e-10, atol=1e-13)
+    h1 = engine.sample_unbiasedestimator(mdl, R.Draws(seed=4), h_kind=A.UBM_H_BOTH, k=k, m=m, lag=1, nrep=300)
+    h2 = engine.sample_unbiasedestimator(mdl, R.Draws(seed=4), h_kind=A.UBM_H_BOTH, k=k, m=m, lag=1, nrep=nrep - 300,
+                                         rep_offset=300)
+    assert np.array_equal(u, np.concatenate([h1["uestimator"], h2["uestimator"]]))
+    assert np.array_equal(tau, np.concatenate([h1["meetingtime"], h2["meetingtime"]]))
+
+
 def test_c2_chains_and_hbar(engine, oracle):
     mdl = cases.c2_model(7, "dense", "offset")
     kw = dict(m=40, lag=3, stride=1024, nrep=50)
