@@ -178,6 +178,23 @@ def test_c2_full_size_properties(engine):
     assert np.array_equal(tau, np.concatenate([h1["meetingtime"], h2["meetingtime"]]))
 
 
+def test_c2_censoring_and_ragged_batches(engine, oracle):
+    """max_iterations reached before meeting (R/meetingtime.R:41-44: meetingtime = Inf), batches that do not fill the 16
+    slots of a CTA, and more CTAs than replicates: identical to the oracle, censored replicates counted in the summary."""
+    mdl = cases.c2_model(12, "dense", "offset")
+    for nrep in (1, 7, 17, 150):
+        kw = dict(k=5, m=40, lag=2, nrep=nrep, max_iterations=200)      # about 60 % of the replicates are censored
+        g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=12), **kw)
+        c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=12), nthreads=4, **kw)
+        assert_same(g, c, ["meetingtime", "iteration", "cost", "uestimator", "mcmcestimator", "correction", "summary"])
+        assert g["summary"][1] == np.isinf(g["meetingtime"]).sum()
+    assert np.isinf(g["meetingtime"]).any() and np.isfinite(g["meetingtime"]).any()
+    assert np.all(g["iteration"][np.isinf(g["meetingtime"])] == 200)
+    g = engine.sample_meetingtime(mdl, R.Draws(seed=12), lag=3, nrep=33, max_iterations=25)
+    c = oracle.sample_meetingtime(mdl, R.Draws(seed=12), lag=3, nrep=33, max_iterations=25, nthreads=4)
+    assert_same(g, c, ["meetingtime"])
+
+
 def test_c2_chains_and_hbar(engine, oracle):
     mdl = cases.c2_model(7, "dense", "offset")
     kw = dict(m=40, lag=3, stride=1024, nrep=50)
