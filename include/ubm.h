@@ -240,6 +240,20 @@ int ubm_estimator_bins(ubm_handle* h, int32_t dim, const ubm_bins* bins, int64_t
                        int64_t stride, int64_t nrep, const double* samples1, const double* samples2,
                        const double* meetingtime, double* binvals /* [nrep][nbins] */);
 
+/* Signed empirical measure of stored coupled chains: c_chains_to_measure_as_list_ (src/c_chains_to_measure.cpp:38-84,
+ * R/c_chains_to_measure_as_list.R:19-27), batched over replicates.  Replicate r yields
+ *   size_r = (m - k + 1) + 2 max(0, tau_r - (k + lag))   atoms,
+ * first the MCMC part (X_t, t = k..m, weight 1 / (m-k+1)), then for t = k+lag .. tau-1 the pair X_t (+w_t) and
+ * Y_{t-lag} (-w_t) with w_t the estimator's weight / (m-k+1).  Outputs are padded to `cap` rows per replicate
+ * (rows >= size_r are zeroed); UBM_ERR_INVALID if some size_r > cap, if k > m or m > iteration_r (the R stops), or if a
+ * replicate is censored (tau = Inf).  mcmc_part: 1 = MCMC atom, 0 = bias-correction atom (the reference's `MCMC`). */
+int64_t ubm_measure_size(int64_t k, int64_t m, int64_t lag, double meetingtime);
+int ubm_c_chains_to_measure(ubm_handle* h, int32_t dim, int64_t k, int64_t m, int64_t lag, int64_t stride, int64_t nrep,
+                            const double* samples1, const double* samples2, const double* meetingtime,
+                            const int64_t* iteration, int64_t cap, double* atoms /* [nrep][cap][dim] */,
+                            double* weights /* [nrep][cap] */, int32_t* mcmc_part /* [nrep][cap] */,
+                            int64_t* sizes /* [nrep] */);
+
 /* ---------------------------------------------------------------------------------------------
  * stand-alone coupling / MVN primitives of the R API, batched over n samples.  Sample i draws from the typed
  * streams of replicate index rep_offset + i (from draw 0), or from row i of the tapes.

@@ -173,6 +173,46 @@ int orc_h_bar(int32_t dim, int32_t h_kind, int64_t k, int64_t m, int64_t lag, in
   return UBM_OK;
 }
 
+// c_chains_to_measure_as_list_ — src/c_chains_to_measure.cpp:38-84 (R/c_chains_to_measure_as_list.R:19-27), per replicate
+int orc_c_chains_to_measure(int32_t dim, int64_t k, int64_t m, int64_t lag, int64_t stride, int64_t nrep,
+                            const double* samples1, const double* samples2, const double* meetingtime,
+                            const int64_t* iteration, int64_t cap, double* atoms, double* weights, int32_t* mcmc_part,
+                            int64_t* sizes) {
+  if (k > m) return UBM_ERR_INVALID;                                                   // R :20-22
+  for (int64_t r = 0; r < nrep; ++r) {
+    if (m > iteration[r]) return UBM_ERR_INVALID;                                      // R :23-25
+    if (!(meetingtime[r] < 9.0e18)) return UBM_ERR_INVALID;
+    const int64_t meeting = (int64_t)meetingtime[r];
+    int64_t size;                                                                      // :45-49
+    if (((meeting - 1) - (k + lag) + 1) > 0) size = (m - k + 1) + 2 * ((meeting - 1) - (k + lag) + 1);
+    else size = (m - k + 1);
+    if (size > cap) return UBM_ERR_INVALID;
+    sizes[r] = size;
+    const double eqweight = 1. / (double)(m - k + 1);                                  // :51
+    const double* s1 = samples1 + (size_t)r * stride * dim;
+    const double* s2 = samples2 + (size_t)r * stride * dim;
+    double* A = atoms + (size_t)r * cap * dim;
+    double* W = weights + (size_t)r * cap;
+    int32_t* P = mcmc_part + (size_t)r * cap;
+    for (int64_t i = 0; i < cap; ++i) { W[i] = 0.0; P[i] = 0; for (int c = 0; c < dim; ++c) A[i * dim + c] = 0.0; }
+    for (int64_t i = 0; i < (m - k + 1); ++i) {                                        // :62-66
+      for (int c = 0; c < dim; ++c) A[i * dim + c] = s1[(k + i) * dim + c];
+      W[i] = eqweight; P[i] = 1;
+    }
+    int64_t index = m - k + 1;
+    if (((meeting - 1) - (k + lag) + 1) > 0) {                                         // :70-82
+      for (int64_t time = k + lag; time <= meeting - 1; ++time) {
+        for (int c = 0; c < dim; ++c) { A[index * dim + c] = s1[time * dim + c]; A[(index + 1) * dim + c] = s2[(time - lag) * dim + c]; }
+        double w = floor(((double)time - k) / (double)lag) - ceil(std::max<double>((double)lag, (double)time - m) / (double)lag) + 1.;
+        w = w * eqweight;
+        W[index] = w; W[index + 1] = -w;
+        index += 2;
+      }
+    }
+  }
+  return UBM_OK;
+}
+
 int orc_estimator_bins(int32_t dim, const ubm_bins* bins, int64_t k, int64_t m, int64_t lag, int64_t stride,
                        int64_t nrep, const double* samples1, const double* samples2, const double* meetingtime,
                        double* binvals) {

@@ -40,6 +40,9 @@ def lib():
         L.orc_estimator_bins.argtypes = [C.c_int32, C.POINTER(A.ubm_bins), C.c_int64, C.c_int64, C.c_int64,
                                          C.c_int64, C.c_int64, A.c_double_p, A.c_double_p, A.c_double_p,
                                          A.c_double_p]
+        L.orc_c_chains_to_measure.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                              A.c_double_p, A.c_double_p, A.c_double_p, A.c_int64_p, C.c_int64,
+                                              A.c_double_p, A.c_double_p, A.c_int32_p, A.c_int64_p]
         L.orc_pg_draws.argtypes = [C.c_uint64, C.c_double, C.c_int64, A.c_double_p]
         L.orc_pg_draws.restype = None
         for f in ("orc_vec_log", "orc_vec_exp", "orc_vec_log1p", "orc_vec_qnorm", "orc_vec_pnorm_log"):
@@ -141,6 +144,22 @@ def sample_coupled_chains(model, draws, m=1, lag=1, max_iterations=0, stride=Non
                                            rep_offset, A.dptr(s1), A.dptr(s2), A.dptr(mt), A.i64ptr(it), A.dptr(cost),
                                            nthreads))
     return {"samples1": s1, "samples2": s2, "meetingtime": mt, "iteration": it, "cost": cost, "lag": lag}
+
+
+def c_chains_to_measure(chains, k=0, m=1):
+    s1, s2 = chains["samples1"], chains["samples2"]
+    nrep, stride, d = s1.shape
+    lag = chains["lag"]
+    tau = chains["meetingtime"]
+    sizes = [(m - k + 1) + 2 * max(0, int(t) - (k + lag)) for t in tau]
+    cap = max(max(sizes), 1)
+    atoms, weights = np.zeros((nrep, cap, d)), np.zeros((nrep, cap))
+    part, sz = np.zeros((nrep, cap), dtype=np.int32), np.zeros(nrep, dtype=np.int64)
+    _check(lib().orc_c_chains_to_measure(d, k, m, lag, stride, nrep, A.dptr(s1), A.dptr(s2), A.dptr(tau),
+                                         A.i64ptr(chains["iteration"]), cap, A.dptr(atoms), A.dptr(weights),
+                                         A.i32ptr(part), A.i64ptr(sz)))
+    return [{"atoms": atoms[r, :sz[r]], "weights": weights[r, :sz[r]], "MCMC": part[r, :sz[r]].astype(bool)}
+            for r in range(nrep)]
 
 
 def h_bar(chains, h_kind=A.UBM_H_IDENTITY, k=0, m=1):

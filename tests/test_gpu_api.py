@@ -27,6 +27,11 @@ def test_readme_workflow():
     est = api.H_bar(chains, h="identity", k=500, m=2000)[:, 0]                     # README.Rmd:119
     half = 1.96 * est.std(ddof=1) / np.sqrt(nrep)
     assert abs(est.mean()) < 2 * half and 0.10 < half < 0.20                       # README.md:171: 0.0055 +/- 0.1459
+    # signed-measure export (R/c_chains_to_measure_as_list.R:19): sum of weights x atoms reproduces H_bar of that chain
+    meas = api.c_chains_to_measure_as_list(chains[:3], 500, 2000)
+    for M, e in zip(meas, est[:3]):
+        assert M["atoms"].shape[1] == 1 and M["MCMC"].sum() == 1501
+        np.testing.assert_allclose(np.dot(M["weights"], M["atoms"][:, 0]), e, rtol=1e-10, atol=1e-12)
     # on-the-fly estimator: same numbers without storing the chains
     u = api.sample_unbiasedestimator(single_kernel, coupled_kernel, rinit, k=500, m=2000, lag=500, nrep=nrep, seed=1)
     np.testing.assert_allclose(u["uestimator"][:, 0], est, rtol=1e-11, atol=1e-11)

@@ -77,3 +77,17 @@ def test_mvn_max_couplings_bit_exact(engine, oracle, d):
     g = engine.rmvnorm_max(mu1, mu2, S1, S2, dr, n=32)
     c = oracle.rmvnorm_max(mu1, mu2, S1, S2, dr, n=32)
     assert np.array_equal(g["xy"], c["xy"]) and np.array_equal(g["nattempts"], c["nattempts"])
+
+
+def test_signed_measure_bit_exact(engine, oracle):
+    """ubm_c_chains_to_measure vs the oracle on stored chains of C1 (d = 1) and C2 (d = 7), and the R-named wrapper."""
+    from tests import cases
+    for mdl, lag, k, m in ((cases.c1_model(), 5, 10, 60), (cases.c2_model(7, "dense", "offset"), 2, 4, 30)):
+        ch = oracle.sample_coupled_chains(mdl, R.Draws(seed=3), m=m, lag=lag, stride=3000, nrep=25)
+        g = engine.c_chains_to_measure(ch, k=k, m=m)
+        c = oracle.c_chains_to_measure(ch, k=k, m=m)
+        for a, b in zip(g, c):
+            for key in ("atoms", "weights", "MCMC"):
+                assert np.array_equal(a[key], b[key]), key
+    with pytest.raises(Exception):
+        engine.c_chains_to_measure(ch, k=5, m=3)            # k must be <= m

@@ -143,3 +143,22 @@ def test_argument_guards(oracle):
         with pytest.raises(oracle.OracleError) as e:
             oracle.sample_unbiasedestimator(mdl, R.Draws(seed=1), nrep=2, **kw)
         assert e.value.status == A.UBM_ERR_INVALID
+
+
+def test_signed_measure_reproduces_hbar(oracle):
+    """c_chains_to_measure_as_list_ (src/c_chains_to_measure.cpp:38-84): number of atoms (m-k+1) + 2 max(0, tau-(k+lag)),
+    MCMC weights 1/(m-k+1) summing to one, correction weights in +/- pairs summing to zero, and
+    sum_n w_n h(Z_n) == H_bar(c_chains, h, k, m) for any h (inst/check/check_hbar.R compares the two the same way)."""
+    mdl = cases.c1_model()
+    for lag, k, m in ((1, 3, 40), (5, 10, 60), (7, 0, 25)):
+        ch = oracle.sample_coupled_chains(mdl, R.Draws(seed=17), m=m, lag=lag, stride=4000, nrep=40)
+        ms = oracle.c_chains_to_measure(ch, k=k, m=m)
+        hb = oracle.h_bar(ch, A.UBM_H_BOTH, k=k, m=m)
+        for r, M in enumerate(ms):
+            tau = int(ch["meetingtime"][r])
+            assert len(M["weights"]) == (m - k + 1) + 2 * max(0, tau - (k + lag))
+            assert M["MCMC"].sum() == m - k + 1 and np.allclose(M["weights"][M["MCMC"]], 1.0 / (m - k + 1))
+            cw = M["weights"][~M["MCMC"]]
+            assert np.array_equal(cw[0::2], -cw[1::2]) and np.all(cw[0::2] > 0)
+            x = M["atoms"][:, 0]
+            np.testing.assert_allclose([np.dot(M["weights"], x), np.dot(M["weights"], x * x)], hb[r], rtol=1e-11, atol=1e-12)

@@ -132,6 +132,12 @@ def load_lib():
                               c_double_p, c_double_p, c_double_p, c_int64_p, c_double_p]
     lib.ubm_estimator_bins.argtypes = [vp, C.c_int32, C.POINTER(ubm_bins), C.c_int64, C.c_int64, C.c_int64,
                                        C.c_int64, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]
+    lib.ubm_measure_size.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_double]
+    lib.ubm_measure_size.restype = C.c_int64
+    lib.ubm_c_chains_to_measure.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                            c_double_p, c_double_p, c_double_p, c_int64_p, C.c_int64, c_double_p,
+                                            c_double_p, c_int32_p, c_int64_p]
+    lib.ubm_c_chains_to_measure.restype = C.c_int
     dp = C.POINTER(ubm_draws)
     lib.ubm_rnorm_max_coupling.argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double,
                                            C.c_double, c_double_p, c_int32_p]

@@ -205,6 +205,20 @@ def H_bar(c_chains, h="identity", k=0, m=1):
     return out if isinstance(c_chains, list) else out[0]
 
 
+def c_chains_to_measure_as_list(c_chains, k, m):
+    """R/c_chains_to_measure_as_list.R:19 — list(atoms, weights, MCMC): the signed empirical measure
+    (m-k+1)^-1 [sum_{t=k}^m delta_{X_t} + sum_{t=k+lag}^{tau-1} w_t (delta_{X_t} - delta_{Y_{t-lag}})] of one coupled chain
+    (a list of chains gives a list of measures)."""
+    if k > m:
+        raise ValueError("k must be <= than m")                                               # :20-22
+    lst = c_chains if isinstance(c_chains, list) else [c_chains]
+    if any(m > c["iteration"] for c in lst):
+        raise ValueError("m has to be less than the time horizon of the coupled chains")    # :23-25
+    batch, n = _batch_of(c_chains)
+    out = _eng().c_chains_to_measure(batch, k=k, m=m)
+    return out if isinstance(c_chains, list) else out[0]
+
+
 def create_mids(breaks):
     """R/histogram_c_chains.R:77-83."""
     breaks = np.asarray(breaks, dtype=np.float64)

@@ -579,6 +579,46 @@ int ubm_h_bar(ubm_handle* h, int32_t dim, int32_t h_kind, int64_t k, int64_t m, 
   return UBM_OK;
 }
 
+int64_t ubm_measure_size(int64_t k, int64_t m, int64_t lag, double meetingtime) {
+  if (!(meetingtime < 9.0e18)) return -1;                       // censored
+  const int64_t T = (int64_t)meetingtime;
+  return (m - k + 1) + 2 * ((T - (k + lag) > 0) ? T - (k + lag) : 0);
+}
+
+int ubm_c_chains_to_measure(ubm_handle* h, int32_t dim, int64_t k, int64_t m, int64_t lag, int64_t stride, int64_t nrep,
+                            const double* samples1, const double* samples2, const double* meetingtime,
+                            const int64_t* iteration, int64_t cap, double* atoms, double* weights, int32_t* mcmc_part,
+                            int64_t* sizes) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!samples1 || !samples2 || !meetingtime || !iteration || !atoms || !weights || !mcmc_part || !sizes) return fail(h, UBM_ERR_INVALID, "null buffer");
+  if (k > m) return fail(h, UBM_ERR_INVALID, "k must be <= than m");                     // R/c_chains_to_measure_as_list.R:20-22
+  if (dim < 1 || nrep < 1 || cap < 1 || lag < 1 || k < 0) return fail(h, UBM_ERR_INVALID, "invalid sizes");
+  for (int64_t r = 0; r < nrep; ++r) {
+    if (m > iteration[r]) return fail(h, UBM_ERR_INVALID, "m has to be less than the time horizon of the coupled chains");   // :23-25
+    const int64_t sz = ubm_measure_size(k, m, lag, meetingtime[r]);
+    if (sz < 0) return fail(h, UBM_ERR_INVALID, "c_chains_to_measure: a replicate did not meet (meetingtime = Inf)");
+    if (sz > cap) return fail(h, UBM_ERR_INVALID, "c_chains_to_measure: cap is smaller than the number of atoms of a replicate");
+    sizes[r] = sz;
+  }
+  CU(cudaSetDevice(h->device));
+  DevBuf s1, s2, mt, da, dw, dp;
+  const size_t sz = (size_t)nrep * stride * dim * 8, rows = (size_t)nrep * cap;
+  CU(s1.alloc(sz)); CU(s2.alloc(sz)); CU(mt.alloc((size_t)nrep * 8));
+  CU(da.alloc(rows * dim * 8)); CU(dw.alloc(rows * 8)); CU(dp.alloc(rows * 4));
+  CU(cudaMemcpyAsync(s1.p, samples1, sz, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(s2.p, samples2, sz, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(mt.p, meetingtime, (size_t)nrep * 8, cudaMemcpyHostToDevice, h->stream));
+  const int64_t total = (int64_t)rows * dim;
+  measure_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(s1.as<double>(), s2.as<double>(), mt.as<double>(), dim, k, m, lag, stride, nrep, cap, da.as<double>(), dw.as<double>(), dp.as<int>());
+  h->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(atoms, da.p, rows * dim * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(weights, dw.p, rows * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(mcmc_part, dp.p, rows * 4, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return UBM_OK;
+}
+
 int ubm_estimator_bins(ubm_handle* h, int32_t dim, const ubm_bins* bins, int64_t k, int64_t m, int64_t lag,
                        int64_t stride, int64_t nrep, const double* samples1, const double* samples2,
                        const double* meetingtime, double* binvals) {

@@ -70,4 +70,34 @@ __global__ void estimator_bin_kernel(const double* __restrict__ s1, const double
   out[idx] = estimator / ((double)(m - k) + 1.);                                                // :41
 }
 
+// c_chains_to_measure_as_list_ (src/c_chains_to_measure.cpp:38-84): one thread per (replicate, atom row, coordinate);
+// coordinate 0 also writes the weight and the MCMC flag.  HBM-bound copy: 8 dim bytes read and written per atom.
+__global__ void measure_kernel(const double* __restrict__ s1, const double* __restrict__ s2, const double* __restrict__ mt,
+                               int dim, int64_t k, int64_t m, int64_t lag, int64_t stride, int64_t nrep, int64_t cap,
+                               double* __restrict__ atoms, double* __restrict__ weights, int* __restrict__ part) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nrep * cap * dim) return;
+  const int64_t row_all = idx / dim;
+  const int c = (int)(idx - row_all * dim);
+  const int64_t r = row_all / cap, row = row_all - r * cap;
+  const int64_t nm = m - k + 1;
+  const int64_t T = (int64_t)mt[r];
+  const int64_t ncorr = (T - (k + lag) > 0) ? T - (k + lag) : 0;          // :45-49
+  const double eq = 1. / (double)nm;                                      // :51
+  const double* a = s1 + r * stride * dim;
+  const double* b = s2 + r * stride * dim;
+  double v = 0.0, w = 0.0;
+  int flag = 0;
+  if (row < nm) {                                                         // :62-66
+    v = a[(k + row) * dim + c]; w = eq; flag = 1;
+  } else if (row < nm + 2 * ncorr) {                                      // :70-82
+    const int64_t q = row - nm, t = k + lag + (q >> 1);
+    const double wt = (double)corr_weight(t, k, m, lag) * eq;             // :78-79
+    if (q & 1) { v = b[(t - lag) * dim + c]; w = -wt; }
+    else { v = a[t * dim + c]; w = wt; }
+  }
+  atoms[idx] = v;
+  if (c == 0) { weights[row_all] = w; part[row_all] = flag; }
+}
+
 }  // namespace ubm

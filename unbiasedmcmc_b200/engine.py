@@ -127,6 +127,21 @@ class Engine:
                                                 A.dptr(s2), A.dptr(chains["meetingtime"]), A.dptr(out)))
         return out
 
+    def c_chains_to_measure(self, chains, k=0, m=1):
+        """src/c_chains_to_measure.cpp:38-84 for every replicate of a stored batch: list of dicts(atoms, weights, MCMC)."""
+        s1, s2 = chains["samples1"], chains["samples2"]
+        nrep, stride, d = s1.shape
+        lag = chains["lag"]
+        sizes = [self.lib.ubm_measure_size(k, m, lag, float(t)) for t in chains["meetingtime"]]
+        cap = max(max(sizes), 1)
+        atoms, weights = np.zeros((nrep, cap, d)), np.zeros((nrep, cap))
+        part, sz = np.zeros((nrep, cap), dtype=np.int32), np.zeros(nrep, dtype=np.int64)
+        self._check(self.lib.ubm_c_chains_to_measure(self.h, d, k, m, lag, stride, nrep, A.dptr(s1), A.dptr(s2),
+                                                     A.dptr(chains["meetingtime"]), A.i64ptr(chains["iteration"]), cap,
+                                                     A.dptr(atoms), A.dptr(weights), A.i32ptr(part), A.i64ptr(sz)))
+        return [{"atoms": atoms[r, :sz[r]], "weights": weights[r, :sz[r]], "MCMC": part[r, :sz[r]].astype(bool)}
+                for r in range(nrep)]
+
     # ---- stand-alone primitives of the R API, batched over n samples ----------------------------------
     def rnorm_max_coupling(self, mu1, mu2, sigma1, sigma2, draws, n=1, rep_offset=0):
         xy, ident = np.zeros((n, 2)), np.zeros(n, dtype=np.int32)
