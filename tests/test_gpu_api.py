@@ -32,6 +32,23 @@ def test_readme_workflow():
     for M, e in zip(meas, est[:3]):
         assert M["atoms"].shape[1] == 1 and M["MCMC"].sum() == 1501
         np.testing.assert_allclose(np.dot(M["weights"], M["atoms"][:, 0]), e, rtol=1e-10, atol=1e-12)
+    # data-frame form with pruning (R/c_chains_to_dataframe.R:22-53, src/prune.cpp:6-45) against a row-by-row restatement
+    df = api.c_chains_to_dataframe(chains[:5], 500, 2000)
+    np.testing.assert_allclose(np.dot(df["weight"], df["atom"][:, 0]), est[:5].mean(), rtol=1e-9, atol=1e-12)
+    assert np.all(np.diff(df["rep"]) >= 0) and set(df["rep"]) == {1, 2, 3, 4, 5}
+    raw = api.c_chains_to_dataframe(chains[:5], 500, 2000, prune=False)
+    assert len(df["weight"]) < len(raw["weight"])                       # RW-MH rejections repeat atoms
+    M = np.column_stack([raw["rep"], raw["MCMC"], raw["weight"], raw["atom"]])
+    M = M[np.lexsort([M[:, 3], M[:, 1], M[:, 0]])]
+    ref = [M[0].copy()]
+    for i in range(1, len(M)):                                         # src/prune.cpp:19-42, literally
+        if M[i, 0] == M[i - 1, 0] and np.abs(M[i, 3:] - M[i - 1, 3:]).sum() < 1e-20:
+            ref[-1][2] += M[i, 2]
+        else:
+            ref.append(M[i].copy())
+    ref = np.array(ref)
+    ref = ref[np.lexsort([ref[:, 1], ref[:, 0]])]
+    assert np.array_equal(ref[:, 3], df["atom"][:, 0]) and np.allclose(ref[:, 2], df["weight"], rtol=1e-12, atol=1e-18)
     # on-the-fly estimator: same numbers without storing the chains
     u = api.sample_unbiasedestimator(single_kernel, coupled_kernel, rinit, k=500, m=2000, lag=500, nrep=nrep, seed=1)
     np.testing.assert_allclose(u["uestimator"][:, 0], est, rtol=1e-11, atol=1e-11)

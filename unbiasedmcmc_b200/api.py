@@ -219,6 +219,39 @@ def c_chains_to_measure_as_list(c_chains, k, m):
     return out if isinstance(c_chains, list) else out[0]
 
 
+def prune_measure_(df):
+    """src/prune.cpp:6-45 on a matrix with columns (rep, MCMC, weight, atom.1, ...) sorted lexicographically: consecutive
+    rows of the same repeat whose atoms differ by less than 1e-20 in l1 are merged, their weights added (vectorised:
+    run boundaries + segmented sums; the first row of a run is kept, as in the reference)."""
+    df = np.asarray(df, dtype=np.float64)
+    if df.shape[0] == 0:
+        return df.copy()
+    same_rep = df[1:, 0] == df[:-1, 0]
+    close = np.abs(df[1:, 3:] - df[:-1, 3:]).sum(axis=1) < 1e-20
+    new_run = np.concatenate([[True], ~(same_rep & close)])
+    run_id = np.cumsum(new_run) - 1
+    out = df[new_run].copy()
+    out[:, 2] = np.bincount(run_id, weights=df[:, 2], minlength=out.shape[0])
+    return out
+
+
+def c_chains_to_dataframe(c_chains, k, m, dopar=False, prune=True):
+    """R/c_chains_to_dataframe.R:22-53 — the signed measure of one coupled chain or of a list of them as a table with
+    columns rep (1-based), MCMC, weight (divided by the number of chains), atom.1..atom.d; identical atoms of a chain
+    pruned.  Returned as a dict of columns (`atom` is the (rows, d) matrix); `dopar` is accepted and ignored."""
+    lst = [c_chains] if isinstance(c_chains, dict) else list(c_chains)
+    measures = c_chains_to_measure_as_list(lst, k, m)
+    nsamples = len(lst)
+    rows = [np.column_stack([np.full(len(M["weights"]), r + 1.0), M["MCMC"].astype(np.float64), M["weights"] / nsamples,
+                             M["atoms"]]) for r, M in enumerate(measures)]
+    df = np.concatenate(rows, axis=0)
+    if prune:
+        keys = [df[:, j] for j in range(df.shape[1] - 1, 2, -1)] + [df[:, 1], df[:, 0]]      # order(rep, MCMC, atom.1, ...)
+        df = prune_measure_(df[np.lexsort(keys)])
+    df = df[np.lexsort([df[:, 1], df[:, 0]])]                                                # order(rep, MCMC), stable
+    return {"rep": df[:, 0].astype(np.int64), "MCMC": df[:, 1] != 0, "weight": df[:, 2], "atom": df[:, 3:]}
+
+
 def create_mids(breaks):
     """R/histogram_c_chains.R:77-83."""
     breaks = np.asarray(breaks, dtype=np.float64)
