@@ -254,6 +254,13 @@ int ubm_c_chains_to_measure(ubm_handle* h, int32_t dim, int64_t k, int64_t m, in
                             double* weights /* [nrep][cap] */, int32_t* mcmc_part /* [nrep][cap] */,
                             int64_t* sizes /* [nrep] */);
 
+/* L-lag total-variation upper bounds from meeting times (Biswas, Jacob & Vanetti 2019), as computed by the callers
+ * directly above the path (vignettes/polyagammagibbs.Rmd:238-244, inst/reproducegermancredit/germancredit.run.R:171-186):
+ *   bound[j] = mean_r max(0, ceil((tau_r - lag - t[j]) / lag)).
+ * Integer sums, fixed order: the result does not depend on the launch geometry.  UBM_ERR_INVALID for a censored tau. */
+int ubm_tv_upper_bounds(ubm_handle* h, const double* meetingtime, int64_t nrep, int64_t lag, const int64_t* t, int32_t nt,
+                        double* bound /* [nt] */);
+
 /* ---------------------------------------------------------------------------------------------
  * stand-alone coupling / MVN primitives of the R API, batched over n samples.  Sample i draws from the typed
  * streams of replicate index rep_offset + i (from draw 0), or from row i of the tapes.

@@ -213,6 +213,19 @@ int orc_c_chains_to_measure(int32_t dim, int64_t k, int64_t m, int64_t lag, int6
   return UBM_OK;
 }
 
+// tv_upper_bound — vignettes/polyagammagibbs.Rmd:238-244: mean over meeting times of pmax(0, ceiling((tau - lag - t) / lag))
+int orc_tv_upper_bounds(const double* meetingtime, int64_t nrep, int64_t lag, const int64_t* t, int32_t nt, double* bound) {
+  for (int32_t j = 0; j < nt; ++j) {
+    double s = 0.0;
+    for (int64_t r = 0; r < nrep; ++r) {
+      if (!(meetingtime[r] < 9.0e18)) return UBM_ERR_INVALID;
+      s += std::max(0.0, ceil((meetingtime[r] - (double)lag - (double)t[j]) / (double)lag));
+    }
+    bound[j] = s / (double)nrep;
+  }
+  return UBM_OK;
+}
+
 int orc_estimator_bins(int32_t dim, const ubm_bins* bins, int64_t k, int64_t m, int64_t lag, int64_t stride,
                        int64_t nrep, const double* samples1, const double* samples2, const double* meetingtime,
                        double* binvals) {

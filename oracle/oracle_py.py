@@ -40,6 +40,7 @@ def lib():
         L.orc_estimator_bins.argtypes = [C.c_int32, C.POINTER(A.ubm_bins), C.c_int64, C.c_int64, C.c_int64,
                                          C.c_int64, C.c_int64, A.c_double_p, A.c_double_p, A.c_double_p,
                                          A.c_double_p]
+        L.orc_tv_upper_bounds.argtypes = [A.c_double_p, C.c_int64, C.c_int64, A.c_int64_p, C.c_int32, A.c_double_p]
         L.orc_c_chains_to_measure.argtypes = [C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                               A.c_double_p, A.c_double_p, A.c_double_p, A.c_int64_p, C.c_int64,
                                               A.c_double_p, A.c_double_p, A.c_int32_p, A.c_int64_p]
@@ -144,6 +145,14 @@ def sample_coupled_chains(model, draws, m=1, lag=1, max_iterations=0, stride=Non
                                            rep_offset, A.dptr(s1), A.dptr(s2), A.dptr(mt), A.i64ptr(it), A.dptr(cost),
                                            nthreads))
     return {"samples1": s1, "samples2": s2, "meetingtime": mt, "iteration": it, "cost": cost, "lag": lag}
+
+
+def tv_upper_bounds(meetingtimes, lag, t):
+    mt = np.ascontiguousarray(meetingtimes, dtype=np.float64).reshape(-1)
+    tg = np.ascontiguousarray(np.atleast_1d(t), dtype=np.int64)
+    out = np.zeros(len(tg))
+    _check(lib().orc_tv_upper_bounds(A.dptr(mt), len(mt), int(lag), A.i64ptr(tg), len(tg), A.dptr(out)))
+    return out
 
 
 def c_chains_to_measure(chains, k=0, m=1):

@@ -91,3 +91,15 @@ def test_signed_measure_bit_exact(engine, oracle):
                 assert np.array_equal(a[key], b[key]), key
     with pytest.raises(Exception):
         engine.c_chains_to_measure(ch, k=5, m=3)            # k must be <= m
+
+
+def test_tv_upper_bounds_bit_exact(engine, oracle):
+    """L-lag TV upper bounds (vignettes/polyagammagibbs.Rmd:238-244) from C1 meeting times with lag 30."""
+    from tests import cases
+    from unbiasedmcmc_b200 import api
+    mt = engine.sample_meetingtime(cases.c1_model(), R.Draws(seed=5), lag=30, nrep=5000)["meetingtime"]
+    t = np.arange(0, 400, 3)
+    g, c = engine.tv_upper_bounds(mt, 30, t), oracle.tv_upper_bounds(mt, 30, t)
+    assert np.array_equal(g, c)
+    assert np.array_equal(g, np.array([api.tv_upper_bound(mt, 30, tj).mean() for tj in t]))
+    assert np.all(np.diff(g) <= 0) and g[0] > 1 and g[-1] < 0.2       # slow mixing between the two modes

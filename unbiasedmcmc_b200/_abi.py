@@ -132,6 +132,8 @@ def load_lib():
                               c_double_p, c_double_p, c_double_p, c_int64_p, c_double_p]
     lib.ubm_estimator_bins.argtypes = [vp, C.c_int32, C.POINTER(ubm_bins), C.c_int64, C.c_int64, C.c_int64,
                                        C.c_int64, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]
+    lib.ubm_tv_upper_bounds.argtypes = [vp, c_double_p, C.c_int64, C.c_int64, c_int64_p, C.c_int32, c_double_p]
+    lib.ubm_tv_upper_bounds.restype = C.c_int
     lib.ubm_measure_size.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_double]
     lib.ubm_measure_size.restype = C.c_int64
     lib.ubm_c_chains_to_measure.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,

@@ -252,6 +252,18 @@ def c_chains_to_dataframe(c_chains, k, m, dopar=False, prune=True):
     return {"rep": df[:, 0].astype(np.int64), "MCMC": df[:, 1] != 0, "weight": df[:, 2], "atom": df[:, 3:]}
 
 
+def tv_upper_bound(meetingtimes, lag, t):
+    """vignettes/polyagammagibbs.Rmd:238-240 — pmax(0, ceiling((meetingtimes - lag - t) / lag)), per meeting time."""
+    mt = np.asarray(meetingtimes, dtype=np.float64)
+    return np.maximum(0.0, np.ceil((mt - lag - t) / lag))
+
+
+def tv_upper_bounds(meetingtimes, lag, t):
+    """The curve the callers plot (polyagammagibbs.Rmd:243): mean(tv_upper_bound(meetingtimes, lag, t)) for each t of a
+    grid, reduced on the device in integer arithmetic."""
+    return _eng().tv_upper_bounds(meetingtimes, lag, t)
+
+
 def create_mids(breaks):
     """R/histogram_c_chains.R:77-83."""
     breaks = np.asarray(breaks, dtype=np.float64)

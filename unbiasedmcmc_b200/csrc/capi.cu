@@ -579,6 +579,25 @@ int ubm_h_bar(ubm_handle* h, int32_t dim, int32_t h_kind, int64_t k, int64_t m, 
   return UBM_OK;
 }
 
+int ubm_tv_upper_bounds(ubm_handle* h, const double* meetingtime, int64_t nrep, int64_t lag, const int64_t* t, int32_t nt,
+                        double* bound) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!meetingtime || !t || !bound || nrep < 1 || nt < 1 || lag < 1) return fail(h, UBM_ERR_INVALID, "tv_upper_bounds: invalid arguments");
+  for (int64_t r = 0; r < nrep; ++r)
+    if (!(meetingtime[r] < 9.0e18)) return fail(h, UBM_ERR_INVALID, "tv_upper_bounds: a meeting time is Inf (raise max_iterations)");
+  CU(cudaSetDevice(h->device));
+  DevBuf mt, dt, out;
+  CU(mt.alloc((size_t)nrep * 8)); CU(dt.alloc((size_t)nt * 8)); CU(out.alloc((size_t)nt * 8));
+  CU(cudaMemcpyAsync(mt.p, meetingtime, (size_t)nrep * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(dt.p, t, (size_t)nt * 8, cudaMemcpyHostToDevice, h->stream));
+  tv_bound_kernel<<<(unsigned)nt, 256, 0, h->stream>>>(mt.as<double>(), nrep, lag, reinterpret_cast<const int64_t*>(dt.p), out.as<double>());
+  h->launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(bound, out.p, (size_t)nt * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return UBM_OK;
+}
+
 int64_t ubm_measure_size(int64_t k, int64_t m, int64_t lag, double meetingtime) {
   if (!(meetingtime < 9.0e18)) return -1;                       // censored
   const int64_t T = (int64_t)meetingtime;

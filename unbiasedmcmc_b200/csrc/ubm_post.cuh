@@ -100,4 +100,23 @@ __global__ void measure_kernel(const double* __restrict__ s1, const double* __re
   if (c == 0) { weights[row_all] = w; part[row_all] = flag; }
 }
 
+// tv_upper_bound of vignettes/polyagammagibbs.Rmd:238-240, averaged over the meeting times: one block per t
+__global__ void tv_bound_kernel(const double* __restrict__ mt, int64_t nrep, int64_t lag, const int64_t* __restrict__ t,
+                                double* __restrict__ out) {
+  __shared__ long long part[256];
+  const int64_t tj = t[blockIdx.x];
+  long long acc = 0;
+  for (int64_t r = threadIdx.x; r < nrep; r += blockDim.x) {
+    const long long x = (long long)mt[r] - lag - tj;
+    if (x > 0) acc += (x + lag - 1) / lag;                       // ceiling of a positive ratio of integers
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) part[threadIdx.x] += part[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = (double)part[0] / (double)nrep;
+}
+
 }  // namespace ubm

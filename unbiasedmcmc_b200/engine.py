@@ -127,6 +127,14 @@ class Engine:
                                                 A.dptr(s2), A.dptr(chains["meetingtime"]), A.dptr(out)))
         return out
 
+    def tv_upper_bounds(self, meetingtimes, lag, t):
+        """mean over the meeting times of max(0, ceil((tau - lag - t) / lag)) for every t of the grid."""
+        mt = np.ascontiguousarray(meetingtimes, dtype=np.float64).reshape(-1)
+        tg = np.ascontiguousarray(np.atleast_1d(t), dtype=np.int64)
+        out = np.zeros(len(tg))
+        self._check(self.lib.ubm_tv_upper_bounds(self.h, A.dptr(mt), len(mt), int(lag), A.i64ptr(tg), len(tg), A.dptr(out)))
+        return out
+
     def c_chains_to_measure(self, chains, k=0, m=1):
         """src/c_chains_to_measure.cpp:38-84 for every replicate of a stored batch: list of dicts(atoms, weights, MCMC)."""
         s1, s2 = chains["samples1"], chains["samples2"]
