@@ -254,6 +254,13 @@ int ubm_c_chains_to_measure(ubm_handle* h, int32_t dim, int64_t k, int64_t m, in
                             double* weights /* [nrep][cap] */, int32_t* mcmc_part /* [nrep][cap] */,
                             int64_t* sizes /* [nrep] */);
 
+/* H_bar for a GRID of (k, m) pairs from one upload of the stored chains (the tuning sweeps of
+ * inst/reproducegermancredit/germancredit.run.R:171-186 and inst/reproducebimodal/bimodal.plots.R:43-46 call H_bar once
+ * per k).  hbar: [npairs][nrep][dim h]; every entry equals ubm_h_bar with that (k, m) bit for bit. */
+int ubm_h_bar_grid(ubm_handle* h, int32_t dim, int32_t h_kind, int32_t npairs, const int64_t* ks, const int64_t* ms,
+                   int64_t lag, int64_t stride, int64_t nrep, const double* samples1, const double* samples2,
+                   const double* meetingtime, const int64_t* iteration, double* hbar);
+
 /* L-lag total-variation upper bounds from meeting times (Biswas, Jacob & Vanetti 2019), as computed by the callers
  * directly above the path (vignettes/polyagammagibbs.Rmd:238-244, inst/reproducegermancredit/germancredit.run.R:171-186):
  *   bound[j] = mean_r max(0, ceil((tau_r - lag - t[j]) / lag)).

@@ -49,6 +49,10 @@ def test_readme_workflow():
     ref = np.array(ref)
     ref = ref[np.lexsort([ref[:, 1], ref[:, 0]])]
     assert np.array_equal(ref[:, 3], df["atom"][:, 0]) and np.allclose(ref[:, 2], df["weight"], rtol=1e-12, atol=1e-18)
+    # k sweep from one upload: every entry equals the single-pair H_bar
+    grid = api.H_bar_grid(chains[:20], [100, 500, 900], 2000)
+    for i, kk in enumerate((100, 500, 900)):
+        assert np.array_equal(grid[i], api.H_bar(chains[:20], h="identity", k=kk, m=2000))
     # on-the-fly estimator: same numbers without storing the chains
     u = api.sample_unbiasedestimator(single_kernel, coupled_kernel, rinit, k=500, m=2000, lag=500, nrep=nrep, seed=1)
     np.testing.assert_allclose(u["uestimator"][:, 0], est, rtol=1e-11, atol=1e-11)

@@ -132,6 +132,9 @@ def load_lib():
                               c_double_p, c_double_p, c_double_p, c_int64_p, c_double_p]
     lib.ubm_estimator_bins.argtypes = [vp, C.c_int32, C.POINTER(ubm_bins), C.c_int64, C.c_int64, C.c_int64,
                                        C.c_int64, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p]
+    lib.ubm_h_bar_grid.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, c_int64_p, c_int64_p, C.c_int64, C.c_int64,
+                                   C.c_int64, c_double_p, c_double_p, c_double_p, c_int64_p, c_double_p]
+    lib.ubm_h_bar_grid.restype = C.c_int
     lib.ubm_tv_upper_bounds.argtypes = [vp, c_double_p, C.c_int64, C.c_int64, c_int64_p, C.c_int32, c_double_p]
     lib.ubm_tv_upper_bounds.restype = C.c_int
     lib.ubm_measure_size.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_double]

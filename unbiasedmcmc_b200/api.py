@@ -252,6 +252,13 @@ def c_chains_to_dataframe(c_chains, k, m, dopar=False, prune=True):
     return {"rep": df[:, 0].astype(np.int64), "MCMC": df[:, 1] != 0, "weight": df[:, 2], "atom": df[:, 3:]}
 
 
+def H_bar_grid(c_chains, ks, ms, h="identity"):
+    """H_bar(c_chains, h, k, m) for a grid of k (and m, scalar or one per k) from one upload of the chains — the k / m tuning
+    sweeps of germancredit.run.R:171-186 and bimodal.plots.R:43-46; returns [len(ks)][nrep][dim h]."""
+    batch, n = _batch_of(c_chains)
+    return _eng().h_bar_grid(batch, ks, ms, _H[h])
+
+
 def tv_upper_bound(meetingtimes, lag, t):
     """vignettes/polyagammagibbs.Rmd:238-240 — pmax(0, ceiling((meetingtimes - lag - t) / lag)), per meeting time."""
     mt = np.asarray(meetingtimes, dtype=np.float64)

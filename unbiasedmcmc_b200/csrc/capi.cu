@@ -579,6 +579,36 @@ int ubm_h_bar(ubm_handle* h, int32_t dim, int32_t h_kind, int64_t k, int64_t m, 
   return UBM_OK;
 }
 
+int ubm_h_bar_grid(ubm_handle* h, int32_t dim, int32_t h_kind, int32_t npairs, const int64_t* ks, const int64_t* ms,
+                   int64_t lag, int64_t stride, int64_t nrep, const double* samples1, const double* samples2,
+                   const double* meetingtime, const int64_t* iteration, double* hbar) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!samples1 || !samples2 || !meetingtime || !iteration || !hbar || !ks || !ms || npairs < 1) return fail(h, UBM_ERR_INVALID, "null buffer");
+  if (h_kind < UBM_H_IDENTITY || h_kind > UBM_H_BOTH) return fail(h, UBM_ERR_UNSUPPORTED, "unknown test function h");
+  for (int32_t q = 0; q < npairs; ++q)
+    for (int64_t r = 0; r < nrep; ++r) {   // R/H_bar.R:21-28
+      if (ks[q] > iteration[r]) return fail(h, UBM_ERR_INVALID, "error: k has to be less than the horizon of the coupled chains");
+      if (ms[q] > iteration[r]) return fail(h, UBM_ERR_INVALID, "error: m has to be less than the horizon of the coupled chains");
+    }
+  CU(cudaSetDevice(h->device));
+  const int dimh = (h_kind == UBM_H_BOTH) ? 2 * dim : dim;
+  DevBuf s1, s2, mt, out;
+  const size_t sz = (size_t)nrep * stride * dim * 8, ob = (size_t)nrep * dimh * 8;
+  CU(s1.alloc(sz)); CU(s2.alloc(sz)); CU(mt.alloc((size_t)nrep * 8)); CU(out.alloc(ob * npairs));
+  CU(cudaMemcpyAsync(s1.p, samples1, sz, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(s2.p, samples2, sz, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(mt.p, meetingtime, (size_t)nrep * 8, cudaMemcpyHostToDevice, h->stream));
+  const int64_t total = nrep * dimh;
+  for (int32_t q = 0; q < npairs; ++q) {     // chains stay resident; one launch per pair on the same stream
+    hbar_kernel<<<(unsigned)((total + 127) / 128), 128, 0, h->stream>>>(s1.as<double>(), s2.as<double>(), mt.as<double>(), dim, h_kind, ks[q], ms[q], lag, stride, nrep, out.as<double>() + (size_t)q * nrep * dimh);
+    h->launches += 1;
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(hbar, out.p, ob * npairs, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return UBM_OK;
+}
+
 int ubm_tv_upper_bounds(ubm_handle* h, const double* meetingtime, int64_t nrep, int64_t lag, const int64_t* t, int32_t nt,
                         double* bound) {
   if (!h) return UBM_ERR_INVALID;

@@ -127,6 +127,19 @@ class Engine:
                                                 A.dptr(s2), A.dptr(chains["meetingtime"]), A.dptr(out)))
         return out
 
+    def h_bar_grid(self, chains, ks, ms, h_kind=A.UBM_H_IDENTITY):
+        """H_bar for every (k, m) pair from one upload of the stored chains: [npairs][nrep][dim h]."""
+        s1, s2 = chains["samples1"], chains["samples2"]
+        nrep, stride, d = s1.shape
+        dimh = 2 * d if h_kind == A.UBM_H_BOTH else d
+        ks = np.ascontiguousarray(np.atleast_1d(ks), dtype=np.int64)
+        ms = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(ms), ks.shape), dtype=np.int64)
+        out = np.zeros((len(ks), nrep, dimh))
+        self._check(self.lib.ubm_h_bar_grid(self.h, d, h_kind, len(ks), A.i64ptr(ks), A.i64ptr(ms), chains["lag"], stride,
+                                            nrep, A.dptr(s1), A.dptr(s2), A.dptr(chains["meetingtime"]),
+                                            A.i64ptr(chains["iteration"]), A.dptr(out)))
+        return out
+
     def tv_upper_bounds(self, meetingtimes, lag, t):
         """mean over the meeting times of max(0, ceil((tau - lag - t) / lag)) for every t of the grid."""
         mt = np.ascontiguousarray(meetingtimes, dtype=np.float64).reshape(-1)
