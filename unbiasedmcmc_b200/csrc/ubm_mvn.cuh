@@ -19,19 +19,22 @@
 // finishes (work stealing).  Reductions over a d-vector use the canonical order "fma chain inside each
 // 4-column group, xor-butterfly over the <= 32 groups" (oracle: sum_g4_*).
 //
-// Thread roles (384 threads, warp-specialised): warps 0-7 (two per SM sub-partition, so that one hides the other's
-// shared-memory latency) are CONSUMERS: they run the GEMM phases and the coupling algebra, synchronising among
-// themselves on a named barrier; warps 8-11 are PRODUCERS: while step t is computed they generate every draw of step t+1 (the d normals
-// per slot through Philox + AS241 with the rare tail branch handled in a separate lane-local pass, and the
-// log-uniforms, into a small ring), so no random-number work sits on the critical path.  All 8 warps share the short
-// per-slot section at the step boundary (accept/reject, state and estimator update, slot state machine), one warp
-// per slot.  Tiles are 1 row x 4+4 columns when a phase has at most 16 rows, 2 rows otherwise: one unit per thread.  Two CTA-wide barriers per step.
+// Thread roles (512 threads, warp-specialised): warps 0-7 (two per SM sub-partition, so that one fills the other's DFMA
+// issue gaps) are CONSUMERS: they run the GEMM phases and the coupling algebra, synchronising among themselves on a
+// named barrier; warps 8-15 are PRODUCERS: while step t is computed they generate every draw of step t+1 (the d normals
+// per slot through Philox + AS241, the rare tail branch compacted over the warp, and the log-uniforms, into a small
+// ring), so no random-number work sits on the critical path.  All 16 warps share the short per-slot section at the
+// step boundary (accept/reject, state and estimator update, slot state machine), one warp per slot.  Tiles are 2 rows x
+// 4 columns per thread over balanced half-units (see mvn_phase_compute); phases with more rows than one batch run in
+// batches.  Two CTA-wide barriers per step.
 //
-// Shared-memory layout notes (ncu, profiles/r01_mvn_*.md: the first version had 12.5e9 bank conflicts):
-//   - packed group g starts at 8 g (g+1) + 2 g doubles: the 16-byte pad per group spreads the
-//     per-thread LDS.128 of different groups over different banks (unpadded, every group starts on bank 0);
-//   - vectors use a row stride of DP + 2 doubles (== 2 mod 4), so rows of different slots read at the same k
-//     fall into different banks while staying 16-byte aligned;
+// Shared-memory layout notes (ncu and tools/lds_probe.cu, profiles/r01_mvn.md: the first version had 12.5e9 bank
+// conflicts; an LDS.128 is served per quarter-warp, one wavefront when its 16-byte words fall into distinct banks):
+//   - packed group g starts at 8 g (g+1) + 4 g (+2 for the long groups) doubles, so that the two streams of a
+//     quarter-warp (a short group and its long partner) read different banks;
+//   - vectors use a row stride of DPS doubles with DPS/2 == 2 (mod 8) words: four consecutive rows plus the same rows an
+//     odd number of words further on (the partner stream) cover the eight bank groups exactly once;
+//   - the canonical cut of the long columns is `half` == 2 (mod 4) rows from the end (mvn_half);
 //   - GEMM units are numbered row-group fastest, so a warp touches few column groups (matrix bytes dominate).
 #pragma once
 #include <algorithm>

@@ -12,11 +12,12 @@
 //      then runs the Devroye sampler and the per-observation max coupling with divergent rejection loops.  Draws are
 //      addressed by CELL (sweep, observation) in the replicate's typed Philox streams, so the sweep is parallel and
 //      independent of scheduling (oracle/oracle_pg.hpp states the same contract).
-//   2. Gram build A_c = X' diag(w_c) X + B^-1 for both chains at once: X is streamed once per sweep through shared
-//      memory in 32-row tiles; each thread owns entries (j1 <= j2) and accumulates sequentially over observations
-//      with fma, i.e. in the reference's order (src/logisticregression.cpp:40-48).
-//   3. p x p linear algebra (Cholesky, solves, triangular inverse, Sigma = Linv' Linv, Cholesky of Sigma) at warp
-//      level: warp 0 owns chain 1, warp 1 chain 2 (lane = row(s)); every sum runs in the oracle's order.
+//   2. Gram build A_c = X' diag(w_c) X + B^-1 for both chains at once, register-tiled: a thread owns a 4 x 4 block of
+//      entries for one of four interleaved observation classes (i mod 4), X is streamed through double-buffered 32-row
+//      tiles of a padded row-major copy; canonical order: four chains over i mod 4, added to B^-1 in turn
+//      (the reference: one chain over i, src/logisticregression.cpp:40-48).
+//   3. p x p linear algebra: Cholesky (right-looking, same per-entry fma sequence as the oracle) and Sigma = Linv' Linv by
+//      the whole CTA; solves and the triangular inverse at warp level (warp 0 chain 1, warp 1 chain 2).
 //   4. max-coupled multivariate Normal draw of (beta1, beta2) by warp 0.
 // Everything lives in shared memory; HBM sees X (392 KB, L2-resident) and the per-replicate results.
 #pragma once
@@ -216,36 +217,14 @@ __device__ inline double pg_logcosh(double x) {
 }
 
 // ---- warp-level p x p linear algebra on column-major shared-memory matrices (stride p) --------------------------
-// in place: lower triangle of A becomes L (A = L L'); strict upper part is zeroed.  Right-looking: after column k is
-// scaled, every remaining entry (i, c), k < c <= i, takes its k-th update A[i][c] = fma(-L[i][k], L[c][k], A[i][c]) —
+// In place: the lower triangle of A becomes L (A = L L'), the strict upper part is zeroed.  Right-looking: after column k
+// is scaled, every remaining entry (i, c), k < c <= i, takes its k-th update A[i][c] = fma(-L[i][k], L[c][k], A[i][c]) —
 // exactly the fma sequence k = 0, 1, ... of the oracle's left-looking chol_lower for that entry, but the updates of one
-// step are independent, so a lane keeps many in flight instead of walking one dependent load-fma chain per column.
-__device__ inline void pg_warp_chol(double* A, int p, int lane) {
-  for (int k = 0; k < p; ++k) {
-    const double lkk = sqrt(A[k * p + k]);
-    __syncwarp();
-    for (int i = k + lane; i < p; i += 32) A[k * p + i] = (i == k) ? lkk : A[k * p + i] / lkk;
-    for (int i = lane; i < k; i += 32) A[k * p + i] = 0.0;
-    __syncwarp();
-    for (int i = k + 1 + lane; i < p; i += 32) {
-      const double nl = -A[k * p + i];
-      int c = k + 1;
-      for (; c + 3 <= i; c += 4) {
-        const double b0 = A[k * p + c], b1 = A[k * p + c + 1], b2 = A[k * p + c + 2], b3 = A[k * p + c + 3];
-        const double a0 = A[c * p + i], a1 = A[(c + 1) * p + i], a2 = A[(c + 2) * p + i], a3 = A[(c + 3) * p + i];
-        A[c * p + i] = ubm_fma(nl, b0, a0); A[(c + 1) * p + i] = ubm_fma(nl, b1, a1);
-        A[(c + 2) * p + i] = ubm_fma(nl, b2, a2); A[(c + 3) * p + i] = ubm_fma(nl, b3, a3);
-      }
-      for (; c <= i; ++c) A[c * p + i] = ubm_fma(nl, A[k * p + c], A[c * p + i]);
-    }
-    __syncwarp();
-  }
-}
-// The same factorisation by the whole CTA, for one matrix (A2 == nullptr) or two at once (threads split in halves):
+// step are independent.  By the whole CTA, for one matrix (A2 == nullptr) or two at once (threads split in halves):
 // thread (ti, tc) updates entries (k+1+ti+.., k+1+tc+..) of the trailing block, so a column step costs the pivot chain
-// (sqrt, one division) plus two or three independent fma per thread and two CTA barriers, instead of a warp walking
-// ~40 entries per lane.  `dg` [2][PG_MAXP] keeps the new diagonal until the end, so that the pivot can be read and the
-// column scaled between the same two barriers.  Same per-entry fma sequence as pg_warp_chol / the oracle.
+// (sqrt, one division) plus two or three independent fma per thread and two CTA barriers (a single warp walking ~40
+// entries per lane took 2.3 K cycles per column).  `dg` [2][PG_MAXP] keeps the new diagonal until the end, so that the
+// pivot can be read and the column scaled between the same two barriers.
 __device__ inline void pg_cta_chol(double* A1, double* A2, double* dg, int p, int tid) {
   const bool two = (A2 != nullptr);
   const int nthr = two ? PG_T / 2 : PG_T;
@@ -479,17 +458,6 @@ __device__ inline void pg_gram(const PgDevice& M, const double* w1, const double
     }
   }
   __syncthreads();
-}
-
-// warp-level: from A (shared, p x p) compute L (in place), m (shared vector), Linv (second matrix)
-__device__ inline void pg_warp_m_sigma(const PgDevice& M, double* A, double* Linv, double* m, int lane) {
-  const int p = M.p;
-  pg_warp_chol(A, p, lane);                              // src/logisticregression.cpp:49-50
-  for (int i = lane; i < p; i += 32) m[i] = M.ktk[i];
-  __syncwarp();
-  pg_warp_forward(A, p, lane, m);                        // :51  L y = b
-  pg_warp_backward(A, p, lane, m);                       //      L' x = y
-  pg_warp_tri_inverse(A, Linv, p, lane);                 // :55
 }
 
 __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const RunParams P) {

@@ -6,11 +6,11 @@
 //   kernels   R/variableselection.R:8-16 (prior, rinit), :17-55 (single), :57-148 (coupled)
 //   numerics  src/vs_mlikelihood.cpp:5-28, src/sample_pairs01.cpp:12-42, R/coupled_pairs01.R:3-40
 //
-// Design (B200): one WARP per replicate.  gamma is a bitmap: lane w keeps bits 32w..32w+31 of both chains in two
+// Design (B200): one WARP per replicate (two per CTA, 14 per SM).  gamma is a bitmap: lane w keeps bits 32w..32w+31 of both chains in two
 // registers, so sums, equality tests and all index sampling are popcounts + warp scans (no O(p) loops, no memory).
 // G = X'X and X'Y are formed ONCE on the device (varsel_gram_kernel) and stay L2-resident (8 MB for p = 1000); a
 // marginal likelihood gathers the s x s block G[gamma, gamma] into shared memory (one L2 round trip), runs a
-// left-looking Cholesky with the right-hand side appended as an extra row (so the triangular solve comes for free)
+// right-looking reciprocal-scaled Cholesky with the right-hand side appended as an extra row (so the solve comes free)
 // and returns in a few thousand cycles — the reference instead re-reads the n x p design matrix, converts it to
 // float32 and inverts with Eigen on every call.  The estimator of the p inclusion probabilities is accumulated
 // lazily in exact integers: a coordinate's counter is only touched when that coordinate flips.
