@@ -74,11 +74,14 @@ def workload(name):
             return 25.0 * site_updates
         return mdl, kw, 2368, desc, flops, "int32"
     if name == "c3":
-        mdl = cases.c3_model()
+        mdl = cases.c3_credit_like_model()
         n, p_ = 1000, 49
         kw = dict(h_kind=A.UBM_H_IDENTITY, bins=None, k=110, m=1100, lag=1)
-        desc = ("C3: logistic regression n=1000, p=49 (synthetic X, prior N(0, 10 I)), coupled Polya-Gamma Gibbs "
-                "(per-observation max-coupled PG draws + max-coupled MVN beta), lag=1, k=110, m=1100, h = beta")
+        desc = ("C3: logistic regression n=1000, p=49, synthetic design with the structure of the German-credit model "
+                "matrix (intercept, 7 unscaled quantitative columns, 13 factors as dummies with the real level "
+                "frequencies; meeting times median 27 / q95 58 against 42 / 75 on the real data), prior N(0, 10 I), "
+                "coupled Polya-Gamma Gibbs (per-observation max-coupled PG draws + max-coupled MVN beta), lag=1, "
+                "k=110, m=1100, h = beta")
 
         def flops(S, nrep):
             # single step = X beta (n p fma) + Gram (n p (p+1)/2 fma) + Cholesky/solves (~p^3/2 fma)

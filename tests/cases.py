@@ -61,6 +61,46 @@ def c3_model(n=1000, p=49, seed=SEED, mode="max"):
     return R.PgLogistic(Y, X, np.zeros(p), 10.0 * np.eye(p), mode=mode)
 
 
+# marginal summaries of the German-credit columns (inst/reproducegermancredit/german_credit.csv): (mean, sd, min, max) of
+# the 7 quantitative columns and the level frequencies of the 13 factors — the data themselves are not shipped
+_CREDIT_QUANT = [(20.9, 12.05, 4, 72), (3271.25, 2821.34, 250, 18424), (2.97, 1.12, 1, 4), (2.84, 1.10, 1, 4),
+                 (35.54, 11.35, 19, 75), (1.41, 0.58, 1, 4), (1.16, 0.36, 1, 2)]
+_CREDIT_LEVELS = [[.274, .269, .063, .394], [.040, .049, .530, .088, .293],
+                  [.234, .103, .181, .280, .012, .022, .050, .009, .097, .012], [.603, .103, .063, .048, .183],
+                  [.062, .172, .339, .174, .253], [.050, .310, .548, .092], [.907, .041, .052],
+                  [.282, .232, .332, .154], [.139, .047, .814], [.179, .714, .107], [.022, .200, .630, .148],
+                  [.596, .404], [.963, .037]]
+
+
+def c3_credit_like_data(n=1000, seed=SEED):
+    """Synthetic design with the STRUCTURE of the German-credit model matrix (germancredit.preparedata.R:2-15): intercept,
+    7 unscaled quantitative columns with the real columns' location / scale / support, 13 independent factors with the
+    real level frequencies as treatment-coded dummies: p = 49; Y from a logistic model with P(Y = 1) ~ 0.7.  On the real
+    data the oracle's meeting times have median 42 and 95 % quantile 75 (lag 1), which is what k = 110 was chosen for."""
+    rng = np.random.default_rng(seed)
+    cols = [np.ones(n)]
+    for mean, sd, lo, hi in _CREDIT_QUANT:
+        shape = (mean / sd) ** 2                              # gamma with the column's mean and sd, rounded and clipped
+        cols.append(np.clip(np.round(rng.gamma(shape, mean / shape, size=n)), lo, hi))
+    for probs in _CREDIT_LEVELS:
+        pr = np.asarray(probs) / np.sum(probs)
+        lev = rng.choice(len(pr), size=n, p=pr)
+        for l in range(1, len(pr)):
+            cols.append((lev == l).astype(np.float64))
+    X = np.column_stack(cols)
+    beta = np.concatenate([[1.2], [-0.03, -1e-4, -0.25, 0.0, 0.012, -0.2, -0.1], rng.normal(0.0, 0.5, X.shape[1] - 8)])
+    eta = X @ beta
+    eta = eta - np.quantile(eta, 0.3)                         # about 70 % positive responses
+    Y = (rng.uniform(size=n) < 1.0 / (1.0 + np.exp(-eta))).astype(np.float64)
+    return Y, X
+
+
+def c3_credit_like_model(n=1000, seed=SEED):
+    """germancredit.run.R:16-19: prior b = 0, B = 10 I on the German-credit-shaped design."""
+    Y, X = c3_credit_like_data(n, seed)
+    return R.PgLogistic(Y, X, np.zeros(X.shape[1]), 10.0 * np.eye(X.shape[1]))
+
+
 def c5_data(n=500, p=1000, snr=1.0, seed=SEED):
     """inst/reproducevarselection/varselection.generatedata.run.R:7-18 (independent design, scaled X and Y)."""
     rng = np.random.default_rng(seed)
