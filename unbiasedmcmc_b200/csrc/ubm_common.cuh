@@ -61,7 +61,17 @@ __device__ inline int bin_of(double x, const double* __restrict__ breaks, int nb
 }
 
 // Sequential typed draws for one replicate held by ONE thread (C1 and the scalar parts of other models).
-template <bool TAPE>
+// Out-of-line copies of the numerics used at many call sites of the thread-per-replicate kernels: inlined everywhere
+// they made those kernels 13-27 K instructions long, and ncu showed `no_inst` (instruction fetch) as the top stall
+// (42 % of the samples of mix_driver_kernel).  Same arithmetic, one copy.
+__device__ __noinline__ double ool_log(double x) { return ubm_log(x); }
+__device__ __noinline__ double ool_exp(double x) { return ubm_exp(x); }
+__device__ __noinline__ double ool_qnorm(double p) { return ubm_qnorm(p); }
+__device__ __noinline__ ubm_u32x4 ool_stream_block(uint64_t seed, uint64_t rep, uint32_t type, uint64_t blk) {
+  return ubm_stream_block(seed, rep, type, blk);
+}
+
+template <bool TAPE, bool OOL = false>      // OOL: call the out-of-line copies (kernels with many draw sites)
 struct ScalarDraws {
   uint64_t seed, rep;
   uint64_t iu, in, ie;
@@ -82,7 +92,7 @@ struct ScalarDraws {
     uint64_t i = iu++;
     if (TAPE) { if ((int64_t)i >= lu) { bad = true; return 0.5; } return tu[i]; }
     uint32_t s = (uint32_t)i & 3u;
-    if (s == 0) bu = ubm_stream_block(seed, rep, UBM_STREAM_U, i >> 2);
+    if (s == 0) bu = OOL ? ool_stream_block(seed, rep, UBM_STREAM_U, i >> 2) : ubm_stream_block(seed, rep, UBM_STREAM_U, i >> 2);
     uint32_t w = (s == 0) ? bu.w[0] : (s == 1) ? bu.w[1] : (s == 2) ? bu.w[2] : bu.w[3];
     return ubm_u01_32(w);
   }
@@ -90,17 +100,17 @@ struct ScalarDraws {
     uint64_t i = in++;
     if (TAPE) { if ((int64_t)i >= ln) { bad = true; return 0.0; } return tn[i]; }
     uint32_t s = (uint32_t)i & 1u;
-    if (s == 0) bn = ubm_stream_block(seed, rep, UBM_STREAM_N, i >> 1);
+    if (s == 0) bn = OOL ? ool_stream_block(seed, rep, UBM_STREAM_N, i >> 1) : ubm_stream_block(seed, rep, UBM_STREAM_N, i >> 1);
     double p = s ? ubm_u01_53(bn.w[2], bn.w[3]) : ubm_u01_53(bn.w[0], bn.w[1]);
-    return ubm_qnorm(p);
+    return OOL ? ool_qnorm(p) : ubm_qnorm(p);
   }
   __device__ double e() {
     uint64_t i = ie++;
     if (TAPE) { if ((int64_t)i >= le) { bad = true; return 1.0; } return te[i]; }
     uint32_t s = (uint32_t)i & 1u;
-    if (s == 0) be = ubm_stream_block(seed, rep, UBM_STREAM_E, i >> 1);
+    if (s == 0) be = OOL ? ool_stream_block(seed, rep, UBM_STREAM_E, i >> 1) : ubm_stream_block(seed, rep, UBM_STREAM_E, i >> 1);
     double p = s ? ubm_u01_53(be.w[2], be.w[3]) : ubm_u01_53(be.w[0], be.w[1]);
-    return -ubm_log(p);
+    return OOL ? -ool_log(p) : -ubm_log(p);
   }
 };
 

@@ -50,10 +50,10 @@ struct MixModel {
     for (int i = 0; i < 8; ++i) {
       if (i < P.ncomp) {
         double a = ev[i] - mx;
-        s = s + ((a == 0.0) ? 1.0 : ubm_exp(a));   // ubm_exp(0) == 1 exactly: skipping it changes no bit
+        s = s + ((a == 0.0) ? 1.0 : ool_exp(a));   // ool_exp(0) == 1 exactly: skipping it changes no bit
       }
     }
-    return mx + ubm_log(s);
+    return mx + ool_log(s);
   }
   template <class D>
   __device__ void rinit(MixState& s, D& d) const {          // README.Rmd:80-84
@@ -64,7 +64,7 @@ struct MixModel {
   __device__ void single(MixState& s, D& d) const {         // R/get_mh_kernels.R:29-40
     double prop = d.n() * P.prop_sd + s.x;
     double ppdf = target(prop);
-    double logu = ubm_log(d.u());
+    double logu = ool_log(d.u());
     if (logu < ppdf - s.pdf) { s.x = prop; s.pdf = ppdf; }
   }
   template <class D>
@@ -78,7 +78,7 @@ struct MixModel {
       double e = z / normz;
       double utilde = d.u();
       double a = xdot + z;
-      ident = ubm_log(utilde) <
+      ident = ool_log(utilde) <
               (-((UBM_LN_SQRT_2PI + 0.5 * a * a) + 0.0)) - (-((UBM_LN_SQRT_2PI + 0.5 * xdot * xdot) + 0.0));
       double ydot = ident ? (xdot + z) : (xdot - 2 * (e * xdot) * e);
       p1 = s1.x + P.prop_sd * xdot;
@@ -86,7 +86,7 @@ struct MixModel {
     } else {                                                // R/get_max_coupling.R:24-39
       double sg = P.prop_sd, lsg = P.log_prop_sd;
       p1 = s1.x + sg * d.n();
-      if (dnorm_log(p1, s1.x, sg, lsg) + ubm_log(d.u()) < dnorm_log(p1, s2.x, sg, lsg)) {
+      if (dnorm_log(p1, s1.x, sg, lsg) + ool_log(d.u()) < dnorm_log(p1, s2.x, sg, lsg)) {
         ident = true; p2 = p1;
       } else {
         ident = false;
@@ -94,13 +94,13 @@ struct MixModel {
         p2 = 0.0;
         while (reject && !d.bad) {
           p2 = s2.x + sg * d.n();
-          reject = dnorm_log(p2, s2.x, sg, lsg) + ubm_log(d.u()) < dnorm_log(p2, s1.x, sg, lsg);
+          reject = dnorm_log(p2, s2.x, sg, lsg) + ool_log(d.u()) < dnorm_log(p2, s1.x, sg, lsg);
         }
       }
     }
     double pdf1 = target(p1), pdf2;
     if (ident) { p2 = p1; pdf2 = pdf1; } else pdf2 = target(p2);
-    double logu = ubm_log(d.u());
+    double logu = ool_log(d.u());
     bool acc1 = false, acc2 = false;
     if (isfinite(pdf1)) acc1 = logu < pdf1 - s1.pdf;
     if (isfinite(pdf2)) acc2 = logu < pdf2 - s2.pdf;
@@ -118,7 +118,10 @@ __device__ inline void h_eval1(int h_kind, double x, double* h) {
 
 // One thread per replicate.  Shared memory: int hist[nbins][blockDim.x] (bins on) + breaks.
 template <bool TAPE>
-__global__ void __launch_bounds__(128) mix_driver_kernel(const MixParams MP, const RunParams P) {
+#ifndef MIX_MINB
+#define MIX_MINB 5      // CTAs per SM asked of the register allocator (96 registers): 3 -> 5.5e6, 4 -> 6.1e6, 5 -> 6.6e6 est/s on C1
+#endif
+__global__ void __launch_bounds__(128, MIX_MINB) mix_driver_kernel(const MixParams MP, const RunParams P) {
   extern __shared__ unsigned char smem_raw[];
   const int nbins = (P.mode == MODE_ESTIMATOR && P.nbreaks >= 2) ? P.nbreaks - 1 : 0;
   double* s_breaks = reinterpret_cast<double*>(smem_raw);
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(128) mix_driver_kernel(const MixParams MP, con
     const bool active = r < P.nrep;
     bool done = !active;
 
-    ScalarDraws<TAPE> D;
+    ScalarDraws<TAPE, true> D;
     D.init(P, active ? r : 0);
     MixState s1, s2;
     double mc[2] = {0, 0}, co[2] = {0, 0}, h1[2], h2[2];
