@@ -251,7 +251,7 @@ __device__ inline void pg_cta_chol(double* A1, double* A2, double* dg, int p, in
 // solve L y = rhs (forward), y overwrites `v` (shared); terms taken in increasing column order.  The diagonal sits in
 // registers (lane k mod 32) and the column of the next step is requested one step ahead, so a step is one shuffle
 // pair, one division and one fma deep.
-__device__ inline void pg_warp_forward(const double* L, int p, int lane, double* v) {
+__device__ __noinline__ void pg_warp_forward(const double* L, int p, int lane, double* v) {
   double s[2], dg[2];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
@@ -275,7 +275,7 @@ __device__ inline void pg_warp_forward(const double* L, int p, int lane, double*
   __syncwarp();
 }
 // solve L' x = y (backward), in place in `v`; terms taken from the last row upwards (as the oracle)
-__device__ inline void pg_warp_backward(const double* L, int p, int lane, double* v) {
+__device__ __noinline__ void pg_warp_backward(const double* L, int p, int lane, double* v) {
   double s[2], dg[2];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
@@ -300,7 +300,7 @@ __device__ inline void pg_warp_backward(const double* L, int p, int lane, double
   __syncwarp();
 }
 // Li = L^-1 (lower): lane owns columns j = lane, lane + 32 and runs the oracle's forward substitution for each
-__device__ inline void pg_warp_tri_inverse(const double* L, double* Li, int p, int lane) {
+__device__ __noinline__ void pg_warp_tri_inverse(const double* L, double* Li, int p, int lane) {
   for (int q = 0; q < 2; ++q) {
     const int j = lane + 32 * q;
     if (j >= p) continue;
@@ -334,7 +334,7 @@ __device__ inline void pg_ltl(const double* Li, double* S, int p, int t, int nth
   }
 }
 // fast_dmvnorm_ (src/mvnorm.cpp:49-67) with the lower factor Ls of the covariance; tmp: shared scratch [p]
-__device__ inline double pg_warp_dmvnorm(const double* x, const double* mean, const double* Ls, int p, int lane, double* tmp) {
+__device__ __noinline__ double pg_warp_dmvnorm(const double* x, const double* mean, const double* Ls, int p, int lane, double* tmp) {
   for (int i = lane; i < p; i += 32) tmp[i] = x[i] - mean[i];
   __syncwarp();
   pg_warp_forward(Ls, p, lane, tmp);
