@@ -138,10 +138,19 @@ int run_chains(const M& model, const ubm_draws* draws, int64_t m, int64_t lag, i
 
 extern "C" {
 
+// R-emulated session stream (r_stream.hpp): create with set.seed(seed); draw typed values (runif / rnorm / rexp order)
+void* orc_rsession_create(uint32_t seed) { return new RStream(seed); }
+void orc_rsession_destroy(void* s) { delete reinterpret_cast<RStream*>(s); }
+void orc_rsession_draw(void* s, int32_t type, int64_t n, double* out) {
+  RStream* R = reinterpret_cast<RStream*>(s);
+  for (int64_t i = 0; i < n; ++i) out[i] = (type == 0) ? R->unif_rand() : (type == 1) ? R->norm_rand() : R->exp_rand();
+}
+
 int orc_sample_meetingtime(int32_t model_kind, const void* model, const ubm_draws* draws, int64_t lag,
                            int64_t max_iterations, int64_t nrep, int64_t rep_offset, double* meetingtime,
                            int32_t nthreads) {
   if (lag < 1) return UBM_ERR_INVALID;
+  if (draws->mode == ORC_DRAWS_RSTREAM) nthreads = 1;   // one sequential stream
   DISPATCH(run_meeting(M, draws, lag, max_iterations, nrep, rep_offset, meetingtime, nthreads))
 }
 
@@ -149,6 +158,7 @@ int orc_sample_unbiasedestimator(int32_t model_kind, const void* model, const ub
                                  const ubm_bins* bins, int64_t k, int64_t m, int64_t lag, int64_t max_iterations,
                                  int64_t nrep, int64_t rep_offset, const ubm_estimator_out* out, int32_t nthreads) {
   if (lag < 1 || k > m || lag > m || k < 0) return UBM_ERR_INVALID;   // R/unbiasedestimator.R:44-51
+  if (draws->mode == ORC_DRAWS_RSTREAM) nthreads = 1;
   DISPATCH(run_estimator(M, draws, h_kind, bins, k, m, lag, max_iterations, nrep, rep_offset, out, nthreads))
 }
 
@@ -157,6 +167,7 @@ int orc_sample_coupled_chains(int32_t model_kind, const void* model, const ubm_d
                               double* samples1, double* samples2, double* meetingtime, int64_t* iteration,
                               double* cost, int32_t nthreads) {
   if (lag < 1) return UBM_ERR_INVALID;
+  if (draws->mode == ORC_DRAWS_RSTREAM) nthreads = 1;
   DISPATCH(run_chains(M, draws, m, lag, max_iterations, stride, nrep, rep_offset, samples1, samples2, meetingtime,
                       iteration, cost, nthreads))
 }

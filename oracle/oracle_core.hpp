@@ -17,8 +17,15 @@
 #include <vector>
 #include "../include/ubm.h"
 #include "../include/ubm_numerics.h"
+#include "r_stream.hpp"
 
 namespace orc {
+
+// oracle-only third draw source: ONE sequential R-emulated stream (r_stream.hpp) shared by consecutive replicates, as in
+// an R session.  ubm_draws.seed carries the RStream pointer; if tapes are given they are RECORDING buffers of capacity
+// len_* per replicate: the typed draws each replicate consumed are written there (NaN beyond), so that the same draws
+// can be replayed through UBM_DRAWS_TAPE on the device.
+#define ORC_DRAWS_RSTREAM 2
 
 // ---------------------------------------------------------------------------------------------------
 // Draw source: typed sequential streams (U, N, E) of one replicate — Philox or replay tape.
@@ -34,9 +41,12 @@ struct Draws {
   // block caches
   uint64_t cbu = ~0ull, cbn = ~0ull, cbe = ~0ull;
   ubm_u32x4 bu{}, bn{}, be{};
+  RStream* rs = nullptr;                       // ORC_DRAWS_RSTREAM
+  double *ru = nullptr, *rn = nullptr, *re = nullptr;   // recording buffers (capacity lu / ln / le)
 
   double u() {
     uint64_t i = iu++;
+    if (mode == ORC_DRAWS_RSTREAM) { double v = rs->unif_rand(); if (ru && (int64_t)i < lu) ru[i] = v; return v; }
     if (mode == UBM_DRAWS_TAPE) {
       if ((int64_t)i >= lu) { exhausted = true; return 0.5; }
       return tu[i];
@@ -46,6 +56,7 @@ struct Draws {
   }
   double n() {
     uint64_t i = in++;
+    if (mode == ORC_DRAWS_RSTREAM) { double v = rs->norm_rand(); if (rn && (int64_t)i < ln) rn[i] = v; return v; }
     if (mode == UBM_DRAWS_TAPE) {
       if ((int64_t)i >= ln) { exhausted = true; return 0.0; }
       return tn[i];
@@ -55,6 +66,7 @@ struct Draws {
   }
   double e() {
     uint64_t i = ie++;
+    if (mode == ORC_DRAWS_RSTREAM) { double v = rs->exp_rand(); if (re && (int64_t)i < le) re[i] = v; return v; }
     if (mode == UBM_DRAWS_TAPE) {
       if ((int64_t)i >= le) { exhausted = true; return 1.0; }
       return te[i];
@@ -77,6 +89,13 @@ inline Draws make_draws(const ubm_draws* d, int64_t local_rep, int64_t rep_offse
     if (!r.tu) r.lu = 0;
     if (!r.tn) r.ln = 0;
     if (!r.te) r.le = 0;
+  }
+  if (d->mode == ORC_DRAWS_RSTREAM) {
+    r.rs = reinterpret_cast<RStream*>((uintptr_t)d->seed);
+    r.lu = d->len_u; r.ln = d->len_n; r.le = d->len_e;
+    r.ru = d->tape_u ? const_cast<double*>(d->tape_u) + local_rep * d->len_u : nullptr;
+    r.rn = d->tape_n ? const_cast<double*>(d->tape_n) + local_rep * d->len_n : nullptr;
+    r.re = d->tape_e ? const_cast<double*>(d->tape_e) + local_rep * d->len_e : nullptr;
   }
   return r;
 }

@@ -53,6 +53,12 @@ def lib():
         L.orc_philox.restype = None
         L.orc_stream.argtypes = [C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, A.c_double_p]
         L.orc_stream.restype = None
+        L.orc_rsession_create.restype = C.c_void_p
+        L.orc_rsession_create.argtypes = [C.c_uint32]
+        L.orc_rsession_destroy.argtypes = [C.c_void_p]
+        L.orc_rsession_destroy.restype = None
+        L.orc_rsession_draw.argtypes = [C.c_void_p, C.c_int32, C.c_int64, A.c_double_p]
+        L.orc_rsession_draw.restype = None
         _lib = L
     return _lib
 
@@ -91,6 +97,45 @@ def stream(seed, rep, type_, n):
     out = np.empty(n, dtype=np.float64)
     lib().orc_stream(int(seed), int(rep), int(type_), n, A.dptr(out))
     return out
+
+
+class RSession:
+    """One emulated R session stream (oracle/r_stream.hpp): `RSession(1)` is `set.seed(1)`.  Passed as `draws`, the
+    oracle's drivers run consecutive replicates on this single sequential stream, exactly as an R loop would (Mersenne-
+    Twister, inversion normals).  With `record=(len_u, len_n, len_e)` the typed draws each replicate consumed are
+    written to `tapes` ([nrep, len] arrays, NaN beyond the consumed prefix) for replay through UBM_DRAWS_TAPE."""
+    ORC_DRAWS_RSTREAM = 2
+
+    def __init__(self, seed, record=None):
+        self._s = lib().orc_rsession_create(int(seed))
+        self.record = record
+        self.tapes = None
+
+    def close(self):
+        if self._s:
+            lib().orc_rsession_destroy(self._s)
+            self._s = None
+
+    def _draw(self, type_, n):
+        out = np.empty(n, dtype=np.float64)
+        lib().orc_rsession_draw(self._s, type_, n, A.dptr(out))
+        return out
+
+    def runif(self, n):
+        return self._draw(0, n)
+
+    def rnorm(self, n):
+        return self._draw(1, n)
+
+    def rexp(self, n):
+        return self._draw(2, n)
+
+    def struct(self, nrep=None):
+        if self.record is None:
+            return A.ubm_draws(self.ORC_DRAWS_RSTREAM, 0, self._s, A.dptr(None), A.dptr(None), A.dptr(None), 0, 0, 0)
+        self.tapes = [np.full((nrep, max(int(n), 1)), np.nan) for n in self.record]
+        return A.ubm_draws(self.ORC_DRAWS_RSTREAM, 0, self._s, A.dptr(self.tapes[0]), A.dptr(self.tapes[1]),
+                           A.dptr(self.tapes[2]), self.tapes[0].shape[1], self.tapes[1].shape[1], self.tapes[2].shape[1])
 
 
 def sample_meetingtime(model, draws, lag=1, max_iterations=0, nrep=1, rep_offset=0, nthreads=1):
