@@ -1,4 +1,4 @@
-// oracle_capi.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see oracle_core.hpp header; parity unpinned).
+// oracle_capi.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see oracle_core.hpp header for the parity status).
 // extern "C" surface of the CPU oracle, loaded with ctypes by tests/, smoke() and bench.py's CPU legs.
 // Mirrors the product's C ABI (include/ubm.h) argument for argument so that a test can hand the same
 // structs to both sides.  `nthreads` > 1 runs replicates on a std::thread pool (the cpu_baseline leg).
@@ -398,6 +398,81 @@ void orc_pg_draws(uint64_t seed, double z, int64_t n, double* out) {
   for (int64_t i = 0; i < n; ++i) { CellDraws c(&D, (uint64_t)i); out[i] = pg_draw(z, c); }
 }
 void orc_vec_pnorm_log(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ubm_pnorm_log(x[i]); }
+
+// ---- probes of single reference functions, for the comparison with the reference's own compiled code (oracle/_ref) ----
+// lattices: 32 x 32 column-major int32 (R's IntegerMatrix), as passed to src/ising.cpp
+static void lattice_in(const IsingModel& M, IsingModel::State& s, const int32_t* a) {
+  s.x.assign((size_t)32 * 32, 0); s.sums.assign(1, 0.0);
+  for (int i = 0; i < 32; ++i) for (int j = 0; j < 32; ++j) M.at(s, 0, i, j) = (int8_t)a[j * 32 + i];
+}
+static void lattice_out(const IsingModel& M, const IsingModel::State& s, int32_t* a) {
+  for (int i = 0; i < 32; ++i) for (int j = 0; j < 32; ++j) a[j * 32 + i] = M.at(s, 0, i, j);
+}
+int32_t orc_ising_sum(const int32_t* state) {
+  double beta = 0.4; ubm_model_ising_pt m{32, 1, &beta, 0.0, 0, 0};
+  IsingModel M(&m); IsingModel::State s; lattice_in(M, s, state);
+  return M.ising_sum(s, 0);
+}
+// one (coupled, if state2 != NULL) sweep at inverse temperature beta with the uniforms of `u`; probas[5] out
+void orc_ising_sweep(double beta, int32_t* state1, int32_t* state2, const double* u, int64_t lu, double* probas) {
+  ubm_model_ising_pt m{32, 1, &beta, 0.0, 0, 0};
+  IsingModel M(&m); IsingModel::State s1, s2;
+  for (int q = 0; q < 5; ++q) probas[q] = M.probas[q];
+  Draws D; D.mode = UBM_DRAWS_TAPE; D.tu = u; D.lu = lu;
+  lattice_in(M, s1, state1);
+  if (state2) { lattice_in(M, s2, state2); M.coupled_sweep(s1, s2, 0, D); lattice_out(M, s2, state2); }
+  else M.sweep(s1, 0, D);
+  lattice_out(M, s1, state1);
+}
+// sample_pair01 (0-based indices: zero index, one index)
+void orc_sample_pair01(const ubm_model_varsel* mdl, const double* selection, double u0, double u1, int32_t* out2) {
+  VarselModel M(mdl);
+  VarselModel::State st; st.g.assign(M.p, 0);
+  for (int j = 0; j < M.p; ++j) st.g[j] = selection[j] != 0.0;
+  M.sync(st);
+  double tu[2] = {u0, u1};
+  Draws D; D.mode = UBM_DRAWS_TAPE; D.tu = tu; D.lu = 2;
+  int i0, i1; M.sample_pair01(st, D, &i0, &i1);
+  out2[0] = i0; out2[1] = i1;
+}
+double orc_varsel_ml(const ubm_model_varsel* mdl, const double* selection) {
+  VarselModel M(mdl);
+  std::vector<uint8_t> g(M.p);
+  for (int j = 0; j < M.p; ++j) g[j] = selection[j] != 0.0;
+  return M.ml(g);
+}
+// Polya-Gamma pieces under SEQUENTIAL (replay) draws of replicate 0 of `draws`; used[3] = draws consumed (u, n, e)
+static void used_out(const Draws& D, int64_t* used) { if (used) { used[0] = (int64_t)D.iu; used[1] = (int64_t)D.in; used[2] = (int64_t)D.ie; } }
+int orc_pg_rpg_seq(const ubm_draws* draws, const double* z, int64_t count, double* out, int64_t* used) {
+  Draws D = make_draws(draws, 0, 0); SeqDraws c(&D);
+  for (int64_t i = 0; i < count; ++i) out[i] = pg_draw(z[i], c);
+  used_out(D, used);
+  return D.exhausted ? UBM_ERR_TAPE : UBM_OK;
+}
+int orc_pg_w_seq(const ubm_model_pg_logistic* mdl, const ubm_draws* draws, const double* beta1, const double* beta2,
+                 double* w, int64_t* used) {
+  PgLogisticModel M(mdl);
+  std::vector<double> z1, z2;
+  M.xbeta(beta1, z1); M.xbeta(beta2, z2);
+  Draws D = make_draws(draws, 0, 0); SeqDraws c(&D);
+  for (int i = 0; i < M.n; ++i) M.w_pair(fabs(z1[i]), fabs(z2[i]), c, &w[2 * i], &w[2 * i + 1]);
+  used_out(D, used);
+  return D.exhausted ? UBM_ERR_TAPE : UBM_OK;
+}
+double orc_pg_logcosh(double x) { return pg_logcosh(x); }
+void orc_pg_xbeta(const ubm_model_pg_logistic* mdl, const double* beta, double* out) {
+  PgLogisticModel M(mdl); std::vector<double> z; M.xbeta(beta, z);
+  for (int i = 0; i < M.n; ++i) out[i] = z[i];
+}
+// m_sigma_function_: m [p], L (= Cholesky_inverse) and Linv (= Cholesky), p x p column-major; also invB and ktk
+void orc_pg_m_sigma(const ubm_model_pg_logistic* mdl, const double* omega, double* m, double* L, double* Linv,
+                    double* invB, double* ktk) {
+  PgLogisticModel M(mdl);
+  PgLogisticModel::MS r = M.m_sigma(std::vector<double>(omega, omega + M.n));
+  const int p = M.p;
+  for (int i = 0; i < p; ++i) { m[i] = r.m[i]; ktk[i] = M.ktk[i]; }
+  for (int q = 0; q < p * p; ++q) { L[q] = r.L[q]; Linv[q] = r.Linv[q]; invB[q] = M.invB[q]; }
+}
 
 // numerics probes (tests/test_numerics.py)
 void orc_vec_log(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ubm_log(x[i]); }

@@ -3,10 +3,17 @@
 // CPU restatement of the reference's three driver loops and two estimator routines.  Only tests/,
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may build or call this.
 //
-// PARITY STATUS: "parity unpinned" — the reference (an R package) cannot be built or run in this
-// image (no R, Rcpp, Eigen, Rmath) and ships no golden vectors or assertions.  The oracle
-// is therefore a line-by-line restatement, each function citing the reference lines it follows, pinned
-// only by the analytic identities and statistical anchors listed in SURVEY.md §8c (tests/test_oracle_*).
+// PARITY STATUS: pinned two ways.
+//  (1) Against R's own printed output: on the emulated R session stream of r_stream.hpp (set.seed(1)), the restatement of
+//      the R drivers and kernels reproduces the three literals of the reference's README (README.md:146, :171) digit for
+//      digit (tests/test_r_stream.py).  These are the only literal outputs in the reference tree.
+//  (2) Against the reference's own compiled code: oracle/_ref holds the UNMODIFIED src/*.cpp of the reference built against
+//      stand-in R / Rcpp / Eigen headers (oracle/ref_shim); fed identical draws, the functions restated here agree with it
+//      bit for bit on every integer / index / control-flow result and, where the reference fixes the operation order,
+//      on the FP64 values too (tests/test_ref_parity.py).
+//  What stays a restatement without a compiled counterpart: the interpreted R code that is not exercised by the README
+//  (R/ising.R, R/variableselection.R, R/coupled_pairs01.R, R/unbiasedestimator.R) — pinned by the identities of
+//  tests/test_oracle_*.py — and the arithmetic of R's nmath / Eigen, which are outside the reference tree.
 //
 // Randomness and transcendentals come from include/ubm_numerics.h (the engine's numerics contract, which
 // replaces the R runtime layer L0 that is absent from /root/reference).

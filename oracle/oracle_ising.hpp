@@ -1,4 +1,4 @@
-// oracle_ising.hpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see oracle_core.hpp header; parity unpinned).
+// oracle_ising.hpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see oracle_core.hpp header for the parity status).
 // CPU restatement of the reference's Ising parallel-tempering kernels (C4):
 //   src/ising.cpp:11-35 (ising_sum_), :43-62 (ising_gibbs_sweep_), :67-92 (ising_coupled_gibbs_sweep_)
 //   R/ising.R:4-8,30-36 (rinit), :45-77 (PT single kernel), :87-141 (PT coupled kernel)

@@ -1,4 +1,4 @@
-// oracle_models.hpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see oracle_core.hpp header).
+// oracle_models.hpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see oracle_core.hpp header for the parity status).
 // CPU restatement of the reference's kernels for C1 (Normal mixture RW-MH) and C2 (MVN RW-MH).
 #pragma once
 #include "oracle_core.hpp"

@@ -1,4 +1,4 @@
-// oracle_pg.hpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see oracle_core.hpp header; parity unpinned).
+// oracle_pg.hpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see oracle_core.hpp header for the parity status).
 // CPU restatement of the reference's Polya-Gamma Gibbs sampler for logistic regression (C3):
 //   src/PolyaGamma.cpp:65-79 (a), :89-104 (mass_texpon), :106-139 (rtigauss), :175-226 (draw_like_devroye),
 //   src/PolyaGamma.h:34-38 (constants), src/RRNG.cpp:50-95 (RNG facade: unif / expon_rate / norm / p_norm)
@@ -12,6 +12,11 @@
 // CELL: cell c = (sweep * n + observation) owns its own blocks of the replicate's typed streams (struct CellDraws
 // below gives the exact address); `sweep` = index of the kernel call (= time).
 // The multivariate-normal draws of the beta update (and rinit) use the ordinary sequential region from index 0.  Same distribution as the reference's order; this is the contract the CUDA kernel matches.
+// REPLAY (UBM_DRAWS_TAPE, and the oracle-only R-session stream): the reference's own order.  Every draw comes from the
+// replicate's typed tapes in the sequence the reference consumes them — observation after observation through
+// w_max_couplingC / w_rejsamplerC (src/logisticregressioncoupling.cpp:42-113), rejection loops included, then the
+// normals and uniforms of the beta update (struct SeqDraws).  The single kernel draws its n PG variables with the same
+// vendored Devroye sampler, in observation order (the reference calls BayesLogit::rpg there, a package outside the tree).
 //
 // Arithmetic pinned where the reference leaves it to the compiler / Eigen / BLAS: a + b * c is one fma;
 // Cholesky = left-looking column algorithm with sequential fma sums; triangular inverse by forward substitution;
@@ -66,6 +71,17 @@ struct CellDraws {
     if (blk != cbe || rep_eff != cre) { cbe = blk; cre = rep_eff; be = ubm_stream_block(seed, rep_eff, UBM_STREAM_E, blk); }
     return -ubm_log(ubm_block_u53(be, k & 1));
   }
+};
+
+// Sequential draws (replay): the replicate's own typed streams, in the reference's order.
+struct SeqDraws {
+  Draws* d;
+  bool overflow = false;        // tape exhausted: the samplers' loops stop
+  explicit SeqDraws(Draws* d_) : d(d_) {}
+  void set_attempt(uint64_t) {}
+  double u() { double v = d->u(); overflow = d->exhausted; return v; }
+  double n() { double v = d->n(); overflow = d->exhausted; return v; }
+  double e() { double v = d->e(); overflow = d->exhausted; return v; }
 };
 
 // PolyaGamma::a — src/PolyaGamma.cpp:65-79
@@ -313,10 +329,15 @@ struct PgLogisticModel {
     s.sweep += 1;
     std::vector<double> zs, w(n);
     xbeta(s.beta.data(), zs);
-    for (int i = 0; i < n; ++i) {
-      CellDraws c(&D, s.sweep * (uint64_t)n + i);
-      w[i] = pg_draw(fabs(zs[i]), c);
-      if (c.overflow) D.exhausted = true;
+    if (D.mode != UBM_DRAWS_PHILOX) {                  // replay: one sequential stream
+      SeqDraws c(&D);
+      for (int i = 0; i < n && !c.overflow; ++i) w[i] = pg_draw(fabs(zs[i]), c);
+    } else {
+      for (int i = 0; i < n; ++i) {
+        CellDraws c(&D, s.sweep * (uint64_t)n + i);
+        w[i] = pg_draw(fabs(zs[i]), c);
+        if (c.overflow) D.exhausted = true;
+      }
     }
     MS r = m_sigma(w);
     // fast_rmvnorm_chol(1, m, Cholesky): y = z Cholesky + m with Cholesky = L^{-1} (lower): y_j = sum_{i >= j} z_i Linv[i,j]
@@ -328,6 +349,41 @@ struct PgLogisticModel {
       s.beta[j] = acc + r.m[j];
     }
   }
+  // one observation of sample_w: w_max_couplingC (src/logisticregressioncoupling.cpp:87-113) or, for mode 'rej_samp',
+  // w_rejsamplerC (:50-74).  `c` is the draw source: the observation's cell (set_attempt moves to the cell's next
+  // attempt) or the sequential replay stream (set_attempt is a no-op).
+  template <class R>
+  void w_pair(double z1, double z2, R& c, double* w1, double* w2) const {
+    if (w_coupling == 1) {                                         // w_rejsamplerC
+      const double z_min = z1 < z2 ? z1 : z2, z_max = z1 < z2 ? z2 : z1;   // std::min / std::max (:54-55)
+      const double w_min = pg_draw(z_min, c);                      // :57
+      const double log_u = ubm_log(c.u());                         // :59
+      const double log_ratio = -0.5 * w_min * (z_max * z_max - z_min * z_min);   // :61 (pow(z, 2.) is exact)
+      double w_max;
+      if (log_u < log_ratio) w_max = w_min;                        // :62-63
+      else { c.set_attempt(1); w_max = pg_draw(z_max, c); }        // :65, second draw = attempt 1 of the cell
+      if (z1 < z2) { *w1 = w_min; *w2 = w_max; } else { *w1 = w_max; *w2 = w_min; }   // :67-73
+      return;
+    }
+    const double a1 = pg_draw(z1, c);                              // :90
+    double a2;
+    const double u1 = c.u();                                       // :94
+    const double logaccept1 = pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * a1 - (pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * a1);   // :96
+    if (ubm_log(u1) <= logaccept1) a2 = a1;                        // :97-98
+    else {
+      bool accept = false;
+      a2 = a1;
+      uint64_t attempt = 0;
+      while (!accept && !c.overflow) {                             // :100-110
+        c.set_attempt(++attempt);
+        a2 = pg_draw(z2, c);
+        const double u2 = c.u();
+        const double logaccept2 = pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * a2 - (pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * a2);
+        if (ubm_log(u2) > logaccept2) accept = true;
+      }
+    }
+    *w1 = a1; *w2 = a2;
+  }
   // coupled_kernel — germancredit.run.R:32-45: sample_w (w_max_couplingC) + sample_beta (rmvnorm_max)
   bool coupled(State& s1, State& s2, Draws& D) const {
     s1.sweep += 1;
@@ -335,42 +391,19 @@ struct PgLogisticModel {
     xbeta(s1.beta.data(), z1s);
     xbeta(s2.beta.data(), z2s);
     bool all_equal = true;
-    for (int i = 0; i < n; ++i) {                                    // src/logisticregressioncoupling.cpp:87-113
-      CellDraws c(&D, s1.sweep * (uint64_t)n + i);
-      const double z1 = fabs(z1s[i]), z2 = fabs(z2s[i]);
-      if (w_coupling == 1) {                                         // w_rejsamplerC — src/logisticregressioncoupling.cpp:42-75
-        const double z_min = z1 < z2 ? z1 : z2, z_max = z1 < z2 ? z2 : z1;   // std::min / std::max (:54-55)
-        const double w_min = pg_draw(z_min, c);                      // :57
-        const double log_u = ubm_log(c.u());                         // :59
-        const double log_ratio = -0.5 * w_min * (z_max * z_max - z_min * z_min);   // :61 (pow(z, 2.) is exact)
-        double w_max;
-        if (log_u < log_ratio) w_max = w_min;                        // :62-63
-        else { c.set_attempt(1); w_max = pg_draw(z_max, c); }        // :65, second draw = attempt 1 of the cell
-        if (z1 < z2) { w1[i] = w_min; w2[i] = w_max; } else { w1[i] = w_max; w2[i] = w_min; }   // :67-73
+    if (D.mode != UBM_DRAWS_PHILOX) {                                // replay: the reference's sequential order
+      SeqDraws c(&D);
+      for (int i = 0; i < n && !c.overflow; ++i) {
+        w_pair(fabs(z1s[i]), fabs(z2s[i]), c, &w1[i], &w2[i]);
+        if (w1[i] != w2[i]) all_equal = false;
+      }
+    } else {
+      for (int i = 0; i < n; ++i) {                                  // src/logisticregressioncoupling.cpp:87-113
+        CellDraws c(&D, s1.sweep * (uint64_t)n + i);
+        w_pair(fabs(z1s[i]), fabs(z2s[i]), c, &w1[i], &w2[i]);
         if (w1[i] != w2[i]) all_equal = false;
         if (c.overflow) D.exhausted = true;
-        continue;
       }
-      const double a1 = pg_draw(z1, c);
-      double a2;
-      const double u1 = c.u();
-      const double logaccept1 = pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * a1 - (pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * a1);
-      if (ubm_log(u1) <= logaccept1) a2 = a1;
-      else {
-        bool accept = false;
-        a2 = a1;
-        uint64_t attempt = 0;
-        while (!accept) {
-          c.set_attempt(++attempt);
-          a2 = pg_draw(z2, c);
-          const double u2 = c.u();
-          const double logaccept2 = pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * a2 - (pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * a2);
-          if (ubm_log(u2) > logaccept2) accept = true;
-        }
-      }
-      w1[i] = a1; w2[i] = a2;
-      if (a1 != a2) all_equal = false;
-      if (c.overflow) D.exhausted = true;
     }
     // sample_beta — R/logistic_regression.R:180-209: rmvnorm_max(m1, m2, t(C1) %*% C1, t(C2) %*% C2)
     MS r1 = m_sigma(w1), r2 = m_sigma(w2);

@@ -1,7 +1,7 @@
 """ctypes loader of the CPU oracle (oracle/_build/libubm_oracle.so).
 
 TEST INFRASTRUCTURE, NOT PRODUCT CODE: only tests/, __graft_entry__.smoke() and bench.py's CPU legs
-(cpu_baseline, --impl reference) may import this module.  Parity status: unpinned (see oracle_core.hpp).
+(cpu_baseline, --impl reference) may import this module.  Parity status: see oracle_core.hpp.
 """
 import ctypes as C
 import os
@@ -321,3 +321,91 @@ def fast_dmvnorm_chol_inverse(x, mean, chol_inverse):
     out = np.zeros(n)
     _check(_prim_lib().orc_dmvnorm_chol_inverse(n, d, A.dptr(x), A.dptr(mean), A.dptr(ci), A.dptr(out)))
     return out
+
+
+# ---- probes of single reference functions (compared with oracle/_ref in tests/test_ref_parity.py) -----------------
+def _probe_lib():
+    L = lib()
+    if not getattr(L, "_probes_bound", False):
+        vp, dpp = C.c_void_p, C.POINTER(A.ubm_draws)
+        L.orc_ising_sum.argtypes = [A.c_int32_p]
+        L.orc_ising_sum.restype = C.c_int32
+        L.orc_ising_sweep.argtypes = [C.c_double, A.c_int32_p, A.c_int32_p, A.c_double_p, C.c_int64, A.c_double_p]
+        L.orc_ising_sweep.restype = None
+        L.orc_sample_pair01.argtypes = [vp, A.c_double_p, C.c_double, C.c_double, A.c_int32_p]
+        L.orc_sample_pair01.restype = None
+        L.orc_varsel_ml.argtypes = [vp, A.c_double_p]
+        L.orc_varsel_ml.restype = C.c_double
+        L.orc_pg_rpg_seq.argtypes = [dpp, A.c_double_p, C.c_int64, A.c_double_p, A.c_int64_p]
+        L.orc_pg_w_seq.argtypes = [vp, dpp, A.c_double_p, A.c_double_p, A.c_double_p, A.c_int64_p]
+        L.orc_pg_logcosh.argtypes = [C.c_double]
+        L.orc_pg_logcosh.restype = C.c_double
+        L.orc_pg_xbeta.argtypes = [vp, A.c_double_p, A.c_double_p]
+        L.orc_pg_xbeta.restype = None
+        L.orc_pg_m_sigma.argtypes = [vp] + [A.c_double_p] * 6
+        L.orc_pg_m_sigma.restype = None
+        L._probes_bound = True
+    return L
+
+
+def ising_sum(state):
+    st = np.ascontiguousarray(state, dtype=np.int32)
+    return int(_probe_lib().orc_ising_sum(A.i32ptr(st)))
+
+
+def ising_sweep(beta, state1, u, state2=None):
+    """state*: flat column-major 32 x 32 int32 lattices (modified copies are returned)"""
+    s1 = np.array(state1, dtype=np.int32)
+    s2 = None if state2 is None else np.array(state2, dtype=np.int32)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    probas = np.zeros(5)
+    _probe_lib().orc_ising_sweep(float(beta), A.i32ptr(s1), A.i32ptr(s2), A.dptr(u), u.size, A.dptr(probas))
+    return s1, s2, probas
+
+
+def sample_pair01(model, selection, u0, u1):
+    sel = np.ascontiguousarray(selection, dtype=np.float64)
+    out = np.zeros(2, dtype=np.int32)
+    _probe_lib().orc_sample_pair01(model.ref(), A.dptr(sel), float(u0), float(u1), A.i32ptr(out))
+    return out
+
+
+def varsel_ml(model, selection):
+    sel = np.ascontiguousarray(selection, dtype=np.float64)
+    return float(_probe_lib().orc_varsel_ml(model.ref(), A.dptr(sel)))
+
+
+def pg_rpg_seq(draws, z):
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    out, used = np.zeros(z.size), np.zeros(3, dtype=np.int64)
+    ds = draws.struct(1)
+    _check(_probe_lib().orc_pg_rpg_seq(C.byref(ds), A.dptr(z), z.size, A.dptr(out), A.i64ptr(used)))
+    return out, used
+
+
+def pg_w_seq(model, draws, beta1, beta2):
+    b1, b2 = np.ascontiguousarray(beta1, dtype=np.float64), np.ascontiguousarray(beta2, dtype=np.float64)
+    w, used = np.zeros((model.n, 2)), np.zeros(3, dtype=np.int64)
+    ds = draws.struct(1)
+    _check(_probe_lib().orc_pg_w_seq(model.ref(), C.byref(ds), A.dptr(b1), A.dptr(b2), A.dptr(w), A.i64ptr(used)))
+    return w, used
+
+
+def pg_logcosh(x):
+    return float(_probe_lib().orc_pg_logcosh(float(x)))
+
+
+def pg_xbeta(model, beta):
+    b = np.ascontiguousarray(beta, dtype=np.float64)
+    out = np.zeros(model.n)
+    _probe_lib().orc_pg_xbeta(model.ref(), A.dptr(b), A.dptr(out))
+    return out
+
+
+def pg_m_sigma(model, omega):
+    om = np.ascontiguousarray(omega, dtype=np.float64)
+    p = model.p
+    m, L, Li, iB, ktk = np.zeros(p), np.zeros(p * p), np.zeros(p * p), np.zeros(p * p), np.zeros(p)
+    _probe_lib().orc_pg_m_sigma(model.ref(), A.dptr(om), A.dptr(m), A.dptr(L), A.dptr(Li), A.dptr(iB), A.dptr(ktk))
+    cmj = lambda a: a.reshape(p, p).T.copy()
+    return {"m": m, "Cholesky_inverse": cmj(L), "Cholesky": cmj(Li), "invB": cmj(iB), "ktk": ktk}

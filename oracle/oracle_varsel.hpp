@@ -1,4 +1,4 @@
-// oracle_varsel.hpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see oracle_core.hpp header; parity unpinned).
+// oracle_varsel.hpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE (see oracle_core.hpp header for the parity status).
 // CPU restatement of the reference's spike-and-slab variable selection sampler (C5):
 //   R/variableselection.R:3-16 (prior, rinit), :17-55 (single kernel), :57-148 (coupled kernel),
 //   :215-279 (unbiasedestimator_vs; same estimator as the generic lag-1 driver used here)
