@@ -4,7 +4,7 @@
 // COLUMN-major (R layout), as in include/ubm.h.
 #include <RcppEigen.h>
 #include "ref_runtime.h"
-#include "/root/reference/src/mvnorm.h"
+#include "mvnorm.h"   /* the reference's own header, found through -I$(REF)/src */
 using namespace Rcpp;
 
 NumericMatrix sigma_(const NumericMatrix& X, const NumericVector& w);                                            // src/logisticregression.cpp:5

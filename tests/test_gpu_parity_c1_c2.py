@@ -226,3 +226,49 @@ def test_invalid_arguments(engine):
         with pytest.raises(UbmError) as e:
             engine.sample_unbiasedestimator(mdl, R.Draws(seed=1), nrep=4, **kw)
         assert e.value.status == A.UBM_ERR_INVALID
+
+
+def test_c2_exact_length_tapes(engine, oracle):
+    """A tape that holds exactly the draws a replicate consumes is enough: the producer warps' prefetch past its end is
+    not an error (one draw fewer is)."""
+    from unbiasedmcmc_b200.engine import UbmError
+    d = 12
+    mdl = cases.c2_model(d)
+    rng = np.random.default_rng(5)
+    big = R.Draws(tape_u=rng.uniform(size=(1, 4000)), tape_n=rng.standard_normal((1, 40000)))
+    kw = dict(k=2, m=30, lag=1, nrep=1)
+    c = oracle.sample_unbiasedestimator(mdl, big, **kw)
+    it, tau = int(c["iteration"][0]), int(c["meetingtime"][0])
+    # normals: 2 d (rinit) + d per kernel call; uniforms: 1 per single step, 2 per coupled step (R/get_mh_kernels.R:32-57)
+    n_used = 2 * d + d * it
+    u_used = 1 + 2 * (tau - 1) + (it - tau)
+    exact = R.Draws(tape_u=big.tapes[0][:, :u_used].copy(), tape_n=big.tapes[1][:, :n_used].copy())
+    c2 = oracle.sample_unbiasedestimator(mdl, exact, **kw)
+    g = engine.sample_unbiasedestimator(mdl, exact, **kw)
+    assert_same(c2, c, EST_KEYS)
+    assert_same(g, c, EST_KEYS)
+    for short in (R.Draws(tape_u=exact.tapes[0][:, :-1].copy(), tape_n=exact.tapes[1]),
+                  R.Draws(tape_u=exact.tapes[0], tape_n=exact.tapes[1][:, :-1].copy())):
+        with pytest.raises(UbmError) as e:
+            engine.sample_unbiasedestimator(mdl, short, **kw)
+        assert e.value.status == A.UBM_ERR_TAPE
+
+
+def test_stored_chain_estimators_reject_censored_replicates(engine):
+    """H_bar / estimator_bin on a chain stopped by max_iterations (meetingtime = Inf): R's H_bar stops with an error
+    (R/H_bar.R:45); here UBM_ERR_INVALID instead of reading past the stored rows"""
+    from unbiasedmcmc_b200.engine import UbmError
+    mdl = cases.c1_model()
+    ch = engine.sample_coupled_chains(mdl, R.Draws(seed=3), m=10, lag=1, max_iterations=12, stride=64, nrep=400)
+    assert np.isinf(ch["meetingtime"]).any()
+    for call in (lambda: engine.h_bar(ch, A.UBM_H_IDENTITY, k=2, m=10),
+                 lambda: engine.h_bar_grid(ch, [1, 2], [10, 10], A.UBM_H_IDENTITY),
+                 lambda: engine.estimator_bins(ch, cases.c1_bins(), k=2, m=10)):
+        with pytest.raises(UbmError) as e:
+            call()
+        assert e.value.status == A.UBM_ERR_INVALID
+    ok = {k: (v[np.isfinite(ch["meetingtime"])] if isinstance(v, np.ndarray) else v) for k, v in ch.items()}
+    ok = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in ok.items()}
+    assert np.all(np.isfinite(engine.h_bar(ok, A.UBM_H_IDENTITY, k=2, m=10)))
+    with pytest.raises(UbmError):
+        engine.h_bar(ok, A.UBM_H_IDENTITY, k=11, m=10)          # k > m

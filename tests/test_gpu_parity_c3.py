@@ -1,5 +1,6 @@
 """GPU parity, C3 (Polya-Gamma Gibbs for logistic regression): CUDA kernel through the C ABI vs the oracle, bit-exact
-under Philox (draws are addressed by (sweep, observation) cell on both sides)."""
+under Philox (draws addressed by (sweep, observation) cell on both sides) and under replay tapes (the reference's
+sequential order on both sides)."""
 import numpy as np
 import pytest
 
@@ -53,9 +54,59 @@ def test_c3_rejsampler_coupling_bit_exact(engine, oracle):
     assert not np.array_equal(g0["meetingtime"], g1["meetingtime"])
 
 
-def test_c3_tape_mode_is_refused(engine):
+def _tapes(nrep, L, seed):
+    rng = np.random.default_rng(seed)
+    return R.Draws(tape_u=rng.uniform(size=(nrep, L)), tape_n=rng.standard_normal((nrep, L)),
+                   tape_e=rng.exponential(size=(nrep, L)))
+
+
+@pytest.mark.parametrize("mode", ["max", "rej_samp"])
+def test_c3_replay_tapes(engine, oracle, mode):
+    """Replay mode in the REFERENCE'S order: one sequential stream per replicate, observation after observation through
+    w_max_couplingC / w_rejsamplerC (src/logisticregressioncoupling.cpp:42-113) with their rejection loops, then the beta
+    update.  (The oracle's sequential w-coupling is itself checked against the reference's compiled code on the same
+    tapes: tests/test_ref_parity.py::test_w_coupling_sequential_order.)"""
+    mdl = cases.c3_model(80, 4, seed=3, mode=mode)
+    nrep = 6
+    draws = _tapes(nrep, 120000, 17)
+    g = engine.sample_meetingtime(mdl, draws, lag=1, nrep=nrep, max_iterations=150)
+    c = oracle.sample_meetingtime(mdl, draws, lag=1, nrep=nrep, max_iterations=150)
+    assert_same(g, c, ["meetingtime"])
+    assert np.isfinite(g["meetingtime"]).any()
+    kw = dict(h_kind=A.UBM_H_BOTH, k=3, m=25, lag=2, nrep=nrep, max_iterations=150)
+    g = engine.sample_unbiasedestimator(mdl, draws, **kw)
+    c = oracle.sample_unbiasedestimator(mdl, draws, **kw)
+    assert_same(g, c, KEYS)
+    kw = dict(m=20, lag=1, stride=160, nrep=nrep)
+    g = engine.sample_coupled_chains(mdl, draws, **kw)
+    c = oracle.sample_coupled_chains(mdl, draws, **kw)
+    assert_same(g, c, ["meetingtime", "iteration", "cost"])
+    for r in range(nrep):
+        nrow = int(c["iteration"][r]) + 1
+        assert np.array_equal(g["samples1"][r, :nrow], c["samples1"][r, :nrow])
+        assert np.array_equal(g["samples2"][r, :nrow - 1], c["samples2"][r, :nrow - 1])
+
+
+def test_c3_replay_differs_from_cell_addressing_only_in_the_draws(engine, oracle):
+    """a tape that records, in sequential order, nothing but fresh draws gives a valid run of the same sampler: the two
+    addressing modes are two orders of consumption of one algorithm (meeting times have the same law; here: finite)"""
+    mdl = cases.c3_model(60, 3, seed=1)
+    g = engine.sample_meetingtime(mdl, _tapes(16, 60000, 5), lag=1, nrep=16, max_iterations=200)
+    assert np.isfinite(g["meetingtime"]).all() and g["meetingtime"].min() >= 2
+
+
+def test_c3_tape_exhaustion_is_an_error(engine):
     from unbiasedmcmc_b200.engine import UbmError
     mdl = cases.c3_model(60, 3)
     with pytest.raises(UbmError) as e:
-        engine.sample_meetingtime(mdl, R.Draws(tape_u=np.full((2, 8), 0.5), tape_n=np.zeros((2, 8))), nrep=2)
-    assert e.value.status == A.UBM_ERR_UNSUPPORTED
+        engine.sample_meetingtime(mdl, _tapes(2, 50, 1), nrep=2)
+    assert e.value.status == A.UBM_ERR_TAPE
+
+
+def test_c3_credit_like_design_bit_exact(engine, oracle):
+    """the German-credit-shaped design of the bench workload (unscaled columns up to 18424; workloads.c3_credit_like_model)"""
+    mdl = cases.c3_credit_like_model()
+    kw = dict(h_kind=A.UBM_H_IDENTITY, k=4, m=16, lag=1, nrep=6, max_iterations=120)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=12), **kw)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=12), nthreads=6, **kw)
+    assert_same(g, c, KEYS)

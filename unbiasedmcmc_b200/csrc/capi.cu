@@ -199,6 +199,15 @@ static int plan_build(ubm_handle* h, int mode, int32_t model_kind, const void* m
   int st = register_model(p, model_kind, model);
   if (st != UBM_OK) { delete p; return st; }
   p->dimh = (h_kind == UBM_H_BOTH) ? 2 * p->dim : p->dim;
+  // combinations the device registry does not hold fail here, before anything is allocated or enqueued
+  if (mode == MODE_ESTIMATOR && h_kind != UBM_H_IDENTITY && (model_kind == UBM_MODEL_ISING_PT || model_kind == UBM_MODEL_VARSEL)) {
+    delete p;
+    return fail(h, UBM_ERR_UNSUPPORTED, "this model's state is integer valued (natural statistics / inclusion indicators): h must be the identity");
+  }
+  if (mode == MODE_ESTIMATOR && bins && bins->nbreaks >= 2 && model_kind != UBM_MODEL_NORMAL_MIXTURE) {
+    delete p;
+    return fail(h, UBM_ERR_UNSUPPORTED, "on-the-fly histogram bins are not available for this model (use ubm_sample_coupled_chains + ubm_estimator_bins)");
+  }
   if (mode == MODE_ESTIMATOR && bins && bins->nbreaks >= 2) {
     if (bins->nbreaks > 257) { delete p; return fail(h, UBM_ERR_INVALID, "at most 256 bins"); }
     if (bins->component < 0 || bins->component >= p->dim) { delete p; return fail(h, UBM_ERR_INVALID, "bins: component out of range"); }
@@ -220,7 +229,7 @@ static int plan_build(ubm_handle* h, int mode, int32_t model_kind, const void* m
     if (p->nbins) {
       if ((e = p->bin_acc.alloc((size_t)2 * p->nbins * 8)) != cudaSuccess) return e;
       if ((e = p->breaks.alloc((size_t)p->nbreaks * 8)) != cudaSuccess) return e;
-      if ((e = cudaMemcpy(p->breaks.p, bins->breaks, (size_t)p->nbreaks * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+      if ((e = cudaMemcpyAsync(p->breaks.p, bins->breaks, (size_t)p->nbreaks * 8, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return e;
     }
     if ((e = p->summary.alloc((size_t)ubm_summary_len(p->dimh, p->nbins) * 8)) != cudaSuccess) return e;
     if ((e = p->counter.alloc(8)) != cudaSuccess) return e;
@@ -247,7 +256,7 @@ static int plan_set_tapes(ubm_plan* p, const ubm_draws* d, int64_t nrep) {
     if (!src || len <= 0) return b.alloc(0);
     cudaError_t e = b.alloc((size_t)nrep * len * 8);
     if (e != cudaSuccess) return e;
-    return cudaMemcpy(b.p, src, (size_t)nrep * len * 8, cudaMemcpyHostToDevice);
+    return cudaMemcpyAsync(b.p, src, (size_t)nrep * len * 8, cudaMemcpyHostToDevice, h->stream);
   };
   CU(up(p->tape_u, d->tape_u, d->len_u));
   CU(up(p->tape_n, d->tape_n, d->len_n));
@@ -535,9 +544,10 @@ int ubm_sample_coupled_chains(ubm_handle* h, int32_t model_kind, const void* mod
   if (st != UBM_OK) return st;
   if (draws->mode == UBM_DRAWS_TAPE) st = plan_set_tapes(p, draws, nrep);
   if (st == UBM_OK) {
-    cudaMemsetAsync(p->samples1.p, 0xFF, p->samples1.bytes, h->stream);   // NaN fill: rows never written stay NaN
-    cudaMemsetAsync(p->samples2.p, 0xFF, p->samples2.bytes, h->stream);
-    st = plan_run(p, draws->mode, draws->seed, nrep, rep_offset);
+    cudaError_t e1 = cudaMemsetAsync(p->samples1.p, 0xFF, p->samples1.bytes, h->stream);   // NaN fill: rows never written stay NaN
+    cudaError_t e2 = cudaMemsetAsync(p->samples2.p, 0xFF, p->samples2.bytes, h->stream);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) st = fail(h, UBM_ERR_CUDA, "sample_coupled_chains: memset of the trajectory buffers failed");
+    else st = plan_run(p, draws->mode, draws->seed, nrep, rep_offset);
   }
   if (st == UBM_OK) {
     ubm_estimator_out o{};
@@ -545,11 +555,32 @@ int ubm_sample_coupled_chains(ubm_handle* h, int32_t model_kind, const void* mod
     st = plan_fetch(p, &o);
   }
   if (st == UBM_OK || st == UBM_ERR_TAPE) {
-    cudaMemcpy(samples1, p->samples1.p, p->samples1.bytes, cudaMemcpyDeviceToHost);
-    cudaMemcpy(samples2, p->samples2.p, p->samples2.bytes, cudaMemcpyDeviceToHost);
+    if (cudaMemcpy(samples1, p->samples1.p, p->samples1.bytes, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(samples2, p->samples2.p, p->samples2.bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+      st = fail(h, UBM_ERR_CUDA, "sample_coupled_chains: copy of the trajectories failed");
   }
   ubm_plan_destroy(p);
   return st;
+}
+
+// argument checks shared by the estimators that read stored chains.  R's H_bar stops on a chain that did not meet
+// ((k+lag):(Inf-1) is an error, R/H_bar.R:45) and estimator_bin_ converts meetingtime to int (src/estimator_bin.cpp:11):
+// a censored replicate (meetingtime = +Inf) is rejected here instead of indexing past the stored rows.
+static int check_stored_chains(ubm_handle* h, const char* who, int64_t k, int64_t m, int64_t lag, int64_t stride, int64_t nrep,
+                               const double* meetingtime, const int64_t* iteration) {
+  if (nrep < 1) return fail(h, UBM_ERR_INVALID, std::string(who) + ": nrep must be >= 1");
+  if (lag < 1) return fail(h, UBM_ERR_INVALID, std::string(who) + ": lag must be >= 1");
+  if (k < 0 || k > m) return fail(h, UBM_ERR_INVALID, std::string(who) + ": need 0 <= k <= m");
+  if (m >= stride) return fail(h, UBM_ERR_INVALID, std::string(who) + ": m is beyond the stored rows (stride)");
+  for (int64_t r = 0; r < nrep; ++r) {
+    if (!(meetingtime[r] < 9.0e18)) return fail(h, UBM_ERR_INVALID, std::string(who) + ": a replicate did not meet (meetingtime = Inf); raise max_iterations");
+    if (meetingtime[r] > (double)stride) return fail(h, UBM_ERR_INVALID, std::string(who) + ": a meeting time is beyond the stored rows (stride)");
+    if (iteration) {   // R/H_bar.R:21-28
+      if (k > iteration[r]) return fail(h, UBM_ERR_INVALID, "error: k has to be less than the horizon of the coupled chains");
+      if (m > iteration[r]) return fail(h, UBM_ERR_INVALID, "error: m has to be less than the horizon of the coupled chains");
+    }
+  }
+  return UBM_OK;
 }
 
 int ubm_h_bar(ubm_handle* h, int32_t dim, int32_t h_kind, int64_t k, int64_t m, int64_t lag, int64_t stride,
@@ -558,10 +589,7 @@ int ubm_h_bar(ubm_handle* h, int32_t dim, int32_t h_kind, int64_t k, int64_t m, 
   if (!h) return UBM_ERR_INVALID;
   if (!samples1 || !samples2 || !meetingtime || !iteration || !hbar) return fail(h, UBM_ERR_INVALID, "null buffer");
   if (h_kind < UBM_H_IDENTITY || h_kind > UBM_H_BOTH) return fail(h, UBM_ERR_UNSUPPORTED, "unknown test function h");
-  for (int64_t r = 0; r < nrep; ++r) {   // R/H_bar.R:21-28
-    if (k > iteration[r]) return fail(h, UBM_ERR_INVALID, "error: k has to be less than the horizon of the coupled chains");
-    if (m > iteration[r]) return fail(h, UBM_ERR_INVALID, "error: m has to be less than the horizon of the coupled chains");
-  }
+  if (int stc = check_stored_chains(h, "H_bar", k, m, lag, stride, nrep, meetingtime, iteration)) return stc;
   CU(cudaSetDevice(h->device));
   const int dimh = (h_kind == UBM_H_BOTH) ? 2 * dim : dim;
   DevBuf s1, s2, mt, out;
@@ -586,10 +614,7 @@ int ubm_h_bar_grid(ubm_handle* h, int32_t dim, int32_t h_kind, int32_t npairs, c
   if (!samples1 || !samples2 || !meetingtime || !iteration || !hbar || !ks || !ms || npairs < 1) return fail(h, UBM_ERR_INVALID, "null buffer");
   if (h_kind < UBM_H_IDENTITY || h_kind > UBM_H_BOTH) return fail(h, UBM_ERR_UNSUPPORTED, "unknown test function h");
   for (int32_t q = 0; q < npairs; ++q)
-    for (int64_t r = 0; r < nrep; ++r) {   // R/H_bar.R:21-28
-      if (ks[q] > iteration[r]) return fail(h, UBM_ERR_INVALID, "error: k has to be less than the horizon of the coupled chains");
-      if (ms[q] > iteration[r]) return fail(h, UBM_ERR_INVALID, "error: m has to be less than the horizon of the coupled chains");
-    }
+    if (int stc = check_stored_chains(h, "H_bar", ks[q], ms[q], lag, stride, nrep, meetingtime, iteration)) return stc;
   CU(cudaSetDevice(h->device));
   const int dimh = (h_kind == UBM_H_BOTH) ? 2 * dim : dim;
   DevBuf s1, s2, mt, out;
@@ -674,6 +699,7 @@ int ubm_estimator_bins(ubm_handle* h, int32_t dim, const ubm_bins* bins, int64_t
   if (!h) return UBM_ERR_INVALID;
   if (!bins || bins->nbreaks < 2 || !samples1 || !samples2 || !meetingtime || !binvals) return fail(h, UBM_ERR_INVALID, "null buffer / bins");
   if (bins->component < 0 || bins->component >= dim) return fail(h, UBM_ERR_INVALID, "bins: component out of range");
+  if (int stc = check_stored_chains(h, "estimator_bin", k, m, lag, stride, nrep, meetingtime, nullptr)) return stc;
   CU(cudaSetDevice(h->device));
   const int nbins = bins->nbreaks - 1;
   DevBuf s1, s2, mt, br, out;
@@ -706,17 +732,17 @@ static int prim_params(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t
   if (draws->mode == UBM_DRAWS_TAPE) {
     if (draws->tape_u && draws->len_u > 0) {
       CU(tu->alloc((size_t)n * draws->len_u * 8));
-      CU(cudaMemcpy(tu->p, draws->tape_u, (size_t)n * draws->len_u * 8, cudaMemcpyHostToDevice));
+      CU(cudaMemcpyAsync(tu->p, draws->tape_u, (size_t)n * draws->len_u * 8, cudaMemcpyHostToDevice, h->stream));
       P->tape_u = tu->as<double>(); P->len_u = draws->len_u;
     }
     if (draws->tape_n && draws->len_n > 0) {
       CU(tn->alloc((size_t)n * draws->len_n * 8));
-      CU(cudaMemcpy(tn->p, draws->tape_n, (size_t)n * draws->len_n * 8, cudaMemcpyHostToDevice));
+      CU(cudaMemcpyAsync(tn->p, draws->tape_n, (size_t)n * draws->len_n * 8, cudaMemcpyHostToDevice, h->stream));
       P->tape_n = tn->as<double>(); P->len_n = draws->len_n;
     }
   }
   CU(status->alloc(4));
-  CU(cudaMemset(status->p, 0, 4));
+  CU(cudaMemsetAsync(status->p, 0, 4, h->stream));
   P->status = status->as<int>();
   return UBM_OK;
 }
@@ -772,12 +798,12 @@ static int mvn_sample(ubm_handle* h, const ubm_draws* draws, int mode, int64_t n
   if (st != UBM_OK) return st;
   const size_t vb = (size_t)d * 8, mb = (size_t)d * d * 8, ob = (size_t)n * d * 8 * (mode == 1 ? 2 : 1);
   CU(dm1.alloc(vb)); CU(dc.alloc(mb)); CU(dout.alloc(ob)); CU(did.alloc((size_t)n * 4));
-  CU(cudaMemcpy(dm1.p, mu1, vb, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(dc.p, chol, mb, cudaMemcpyHostToDevice));
+  CU(cudaMemcpyAsync(dm1.p, mu1, vb, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(dc.p, chol, mb, cudaMemcpyHostToDevice, h->stream));
   if (mode == 1) {
     CU(dm2.alloc(vb)); CU(dci.alloc(mb));
-    CU(cudaMemcpy(dm2.p, mu2, vb, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(dci.p, chol_inv, mb, cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(dm2.p, mu2, vb, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dci.p, chol_inv, mb, cudaMemcpyHostToDevice, h->stream));
   }
   const unsigned grid = (unsigned)((n + 63) / 64);
   if (draws->mode == UBM_DRAWS_TAPE)
@@ -819,9 +845,9 @@ static int mvn_max(ubm_handle* h, const ubm_draws* draws, int variant, int64_t n
   if (st != UBM_OK) return st;
   CU(dm1.alloc(vb)); CU(dm2.alloc(vb)); CU(da1.alloc(mb)); CU(da2.alloc(mb)); CU(db1.alloc(mb)); CU(db2.alloc(mb));
   CU(dout.alloc((size_t)n * 2 * d * 8)); CU(did.alloc((size_t)n * 4)); CU(dna.alloc((size_t)n * 4));
-  CU(cudaMemcpy(dm1.p, mu1, vb, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dm2.p, mu2, vb, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(da1.p, A1, mb, cudaMemcpyHostToDevice)); CU(cudaMemcpy(da2.p, A2, mb, cudaMemcpyHostToDevice));
-  if (variant == 0) { CU(cudaMemcpy(db1.p, B1, mb, cudaMemcpyHostToDevice)); CU(cudaMemcpy(db2.p, B2, mb, cudaMemcpyHostToDevice)); }
+  CU(cudaMemcpyAsync(dm1.p, mu1, vb, cudaMemcpyHostToDevice, h->stream)); CU(cudaMemcpyAsync(dm2.p, mu2, vb, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(da1.p, A1, mb, cudaMemcpyHostToDevice, h->stream)); CU(cudaMemcpyAsync(da2.p, A2, mb, cudaMemcpyHostToDevice, h->stream));
+  if (variant == 0) { CU(cudaMemcpyAsync(db1.p, B1, mb, cudaMemcpyHostToDevice, h->stream)); CU(cudaMemcpyAsync(db2.p, B2, mb, cudaMemcpyHostToDevice, h->stream)); }
   const unsigned grid = (unsigned)((n + 63) / 64);
   if (draws->mode == UBM_DRAWS_TAPE)
     prim_mvn_max_kernel<true><<<grid, 64, 0, h->stream>>>(P, variant, d, dm1.as<double>(), dm2.as<double>(), da1.as<double>(), da2.as<double>(), db1.as<double>(), db2.as<double>(), cst1, cst2, dout.as<double>(), did.as<int>(), dna.as<int>());
@@ -866,9 +892,9 @@ int ubm_fast_dmvnorm_chol_inverse(ubm_handle* h, int64_t n, int32_t d, const dou
   const double cst = -(-halflogdet) - (d * 0.9189385);      // src/mvnorm.cpp:74-75
   DevBuf dx, dm, dci, dout;
   CU(dx.alloc((size_t)n * d * 8)); CU(dm.alloc((size_t)d * 8)); CU(dci.alloc((size_t)d * d * 8)); CU(dout.alloc((size_t)n * 8));
-  CU(cudaMemcpy(dx.p, x, (size_t)n * d * 8, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(dm.p, mean, (size_t)d * 8, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(dci.p, chol_inv, (size_t)d * d * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpyAsync(dx.p, x, (size_t)n * d * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(dm.p, mean, (size_t)d * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(dci.p, chol_inv, (size_t)d * d * 8, cudaMemcpyHostToDevice, h->stream));
   prim_dmvnorm_kernel<<<(unsigned)((n + 63) / 64), 64, 0, h->stream>>>(n, d, dx.as<double>(), dm.as<double>(), dci.as<double>(), cst, dout.as<double>());
   h->launches += 1;
   CU(cudaGetLastError());

@@ -494,7 +494,16 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
         __syncwarp();
         // ---- slot state machine
         bool finished;
-        const bool capped = (P.max_it > 0 && time >= P.max_it) || S.bad[s];
+        // replay: a tape is exhausted when the step just finished CONSUMED a draw past its end (the producers only
+        // prefetch, and reading ahead of the consumer is not an error)
+        bool tape_bad = false;
+        if (TAPE) {
+          const long long n_used = (long long)S.in[s] + ((ph == SL_INIT) ? 2 * d : d);
+          const long long len_n = P.tape_n ? P.len_n : 0, len_u = P.tape_u ? P.len_u : 0;
+          tape_bad = n_used > len_n || (long long)S.iu[s] > len_u;
+          if (tape_bad && lane == 0) S.bad[s] = 1;
+        }
+        const bool capped = (P.max_it > 0 && time >= P.max_it) || tape_bad;
         if (P.mode == MODE_MEETING) finished = met || (time >= P.lag && capped);
         else {
           const long long tt = met ? S.tau[s] : 0;
@@ -514,7 +523,7 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
             if (P.tau) P.tau[rep] = met ? (double)tt : dinf();
             if (P.cost) P.cost[rep] = cost;
             if (P.iter) P.iter[rep] = time;
-            if (S.bad[s]) atomicExch(P.status, UBM_ERR_TAPE);
+            if (tape_bad) atomicExch(P.status, UBM_ERR_TAPE);
           }
           if (P.mode == MODE_ESTIMATOR) {
             const double* a = sm.ACC + s * acc_per_slot;
@@ -711,12 +720,11 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
         if (ph == SL_IDLE) continue;
         const long long rep = S.rep[s];
         const unsigned long long base = (ph == SL_WAIT) ? 0ull : ((ph == SL_INIT) ? (unsigned long long)(2 * d) : S.in[s] + d);
-        bool bad = false;
+        bool past_end = false;    // prefetch past the end of a tape yields a dummy value; only consumption is an error
         const int nvalid = (lane < nCG) ? d - 4 * lane : 0;
-        draw_n4_warp<TAPE>(P, rep, base + 4 * lane, nvalid, XIn + s * DPS, lane, &bad);
+        draw_n4_warp<TAPE>(P, rep, base + 4 * lane, nvalid, XIn + s * DPS, lane, &past_end);
         if (ph == SL_WAIT)        // rinit of chain 2 (draw order: chain 1's d normals, then chain 2's)
-          draw_n4_warp<TAPE>(P, rep, base + d + 4 * lane, nvalid, sm.V2 + s * DPS, lane, &bad);
-        if (bad) S.bad[s] = 1;
+          draw_n4_warp<TAPE>(P, rep, base + d + 4 * lane, nvalid, sm.V2 + s * DPS, lane, &past_end);
       }
       // log-uniform rings of this warp's slots (8 lanes per slot): keep them at least 4 draws ahead of the consumers
       // (they use at most 2 per step)
@@ -724,15 +732,14 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
         const int s = pw + (lane >> 3) * MVN_PW, l8 = lane & 7;
         const bool on = s < R && S.phase[s] != SL_IDLE;
         unsigned long long pu = 0, target = 0;
-        bool bad = false;
+        bool past_end = false;
         if (on) {
           pu = S.pu[s]; target = S.iu[s] + 6;
           const unsigned long long idx = pu + l8;
-          if (idx < target) sm.LU[s * 8 + (int)(idx & 7ull)] = ubm_log(draw_u_at<TAPE>(P, S.rep[s], idx, &bad));
+          if (idx < target) sm.LU[s * 8 + (int)(idx & 7ull)] = ubm_log(draw_u_at<TAPE>(P, S.rep[s], idx, &past_end));
         }
         __syncwarp();
         if (on && l8 == 0 && target > pu) S.pu[s] = target;
-        if (bad) S.bad[s] = 1;
       }
     }
     __syncthreads();      // CTA barrier 2: step computed, draws of the next step in place

@@ -20,6 +20,11 @@
 //      the whole CTA; solves and the triangular inverse at warp level (warp 0 chain 1, warp 1 chain 2).
 //   4. max-coupled multivariate Normal draw of (beta1, beta2) by warp 0.
 // Everything lives in shared memory; HBM sees X (392 KB, L2-resident) and the per-replicate results.
+//
+// Replay (UBM_DRAWS_TAPE): the reference's own order of consumption — ONE sequential stream per replicate, observation
+// after observation through w_max_couplingC / w_rejsamplerC with their rejection loops (src/logisticregressioncoupling.cpp:
+// 42-113), then the normals and uniforms of the beta update.  How many draws an observation takes is data dependent, so
+// thread 0 walks the observations (struct PgSeq); this is a parity path like sample_coupled_chains, not a fast one.
 #pragma once
 #include <string>
 #include <vector>
@@ -134,6 +139,19 @@ struct PgCell {   // a cell = (sweep, observation); an attempt = 32 blocks of ea
   __device__ __forceinline__ double u() { return pg_cell_u(seed, rep_eff, base, (ku++) & 127u); }
   __device__ __forceinline__ double n() { return pg_qnorm(pg_cell_u53(seed, rep_eff, base, (kn++) & 63u, UBM_STREAM_N)); }
   __device__ __forceinline__ double e() { return -pg_log(pg_cell_u53(seed, rep_eff, base, (ke++) & 63u, UBM_STREAM_E)); }
+  __device__ __forceinline__ bool overflow() const { return false; }
+};
+// replay: the replicate's typed tapes, consumed sequentially (oracle/oracle_pg.hpp: SeqDraws over Draws)
+struct PgSeq {
+  const double *tu, *tn, *te;
+  long long lu, ln, le;
+  unsigned long long iu, in, ie;
+  bool bad;
+  __device__ __forceinline__ void set_attempt(uint64_t) {}
+  __device__ double u() { const unsigned long long i = iu++; if ((long long)i >= lu) { bad = true; return 0.5; } return tu[i]; }
+  __device__ double n() { const unsigned long long i = in++; if ((long long)i >= ln) { bad = true; return 0.0; } return tn[i]; }
+  __device__ double e() { const unsigned long long i = ie++; if ((long long)i >= le) { bad = true; return 1.0; } return te[i]; }
+  __device__ __forceinline__ bool overflow() const { return bad; }
 };
 
 // PolyaGamma::a — src/PolyaGamma.cpp:65-79
@@ -160,7 +178,8 @@ __device__ inline double pg_mass_texpon(double Z) {
   return 1.0 / (1.0 + qdivp);
 }
 // PolyaGamma::rtigauss — src/PolyaGamma.cpp:106-139
-__device__ inline double pg_rtigauss(double Z, PgCell& r) {
+template <class R>
+__device__ inline double pg_rtigauss(double Z, R& r) {
   Z = fabs(Z);
   const double t = PG_TRUNC_D;
   double X = t + 1.0;
@@ -168,10 +187,11 @@ __device__ inline double pg_rtigauss(double Z, PgCell& r) {
     double alpha = 0.0;
     while (r.u() > alpha) {
       double E1 = r.e(); double E2 = r.e();
-      while (E1 * E1 > 2 * E2 / t) { E1 = r.e(); E2 = r.e(); }
+      while (E1 * E1 > 2 * E2 / t) { E1 = r.e(); E2 = r.e(); if (r.overflow()) break; }
       X = 1 + E1 * t;
       X = t / (X * X);
       alpha = pg_exp(-0.5 * Z * Z * X);
+      if (r.overflow()) break;
     }
   } else {
     const double mu = 1.0 / Z;
@@ -181,12 +201,14 @@ __device__ inline double pg_rtigauss(double Z, PgCell& r) {
       const double mu_Y = mu * Y;
       X = mu + half_mu * mu_Y - half_mu * sqrt(4 * mu_Y + mu_Y * mu_Y);
       if (r.u() > mu / (mu + X)) X = mu * mu / X;
+      if (r.overflow()) break;
     }
   }
   return X;
 }
 // PolyaGamma::draw_like_devroye — src/PolyaGamma.cpp:175-226
-__device__ inline double pg_draw(double Zin, PgCell& r) {
+template <class R>
+__device__ inline double pg_draw(double Zin, R& r) {
   const double Z = fabs(Zin) * 0.5;
   const double fz = 0.125 * PG_PI_D * PG_PI_D + 0.5 * Z * Z;
   double X = 0.0, S = 1.0, Y = 0.0;
@@ -208,6 +230,7 @@ __device__ inline double pg_draw(double Zin, PgCell& r) {
         if (Y > S) go = false;
       }
     }
+    if (r.overflow()) return 0.25 * X;
   }
 }
 // logcosh — src/logisticregressioncoupling.cpp:9-17
@@ -360,8 +383,10 @@ __device__ __noinline__ double pg_warp_dmvnorm(const double* x, const double* me
 
 struct PgShared {   // scalars
   long long rep;
-  unsigned long long in, iu;   // sequential region of the N / U streams (beta updates)
+  unsigned long long in, iu, ie;   // sequential region of the N / U (/ E: replay) streams
   int flag;
+  int bad;                         // replay tape exhausted
+  int eq;                          // replay: all w pairs equal
 };
 
 // Gram build for one or two chains: A_c[j2, j1] (lower) = invB[j1, j2] + sum_i X(i,j1) X(i,j2) w_c[i].
@@ -460,6 +485,7 @@ __device__ inline void pg_gram(const PgDevice& M, const double* w1, const double
   __syncthreads();
 }
 
+template <bool TAPE>
 __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const RunParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -490,7 +516,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
     if (tid == 0) {
       const unsigned long long got = atomicAdd(P.work_counter, 1ull);
       sh.rep = (got < (unsigned long long)P.nrep) ? (long long)got : -1;
-      sh.in = 0; sh.iu = 0;
+      sh.in = 0; sh.iu = 0; sh.ie = 0; sh.bad = 0;
     }
     __syncthreads();
     const long long rep = sh.rep;
@@ -499,7 +525,9 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
     // ---- rinit (germancredit.run.R:47-49): beta ~ N(b, B) via fast_rmvnorm (src/mvnorm.cpp:9-26), chain 1 then chain 2
     if (warp == 0) {
       for (int c = 0; c < 2; ++c) {
-        for (int j = lane; j < p; j += 32) zz[j] = ubm_philox_n(P.seed, grep, (uint64_t)(c * p + j));
+        bool badr = false;
+        for (int j = lane; j < p; j += 32) zz[j] = draw_n_at<TAPE>(P, rep, (uint64_t)(c * p + j), &badr);
+        if (TAPE && __any_sync(0xffffffffu, badr) && lane == 0) sh.bad = 1;
         __syncwarp();
         for (int j = lane; j < p; j += 32) {
           double a = 0.0;
@@ -535,10 +563,11 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
       bool go;
       if (time < P.lag) go = true;
       else {
-        const bool capped = (P.max_it > 0 && time >= P.max_it);
+        const bool capped = (P.max_it > 0 && time >= P.max_it) || (TAPE && sh.bad);
         if (P.mode == MODE_MEETING) go = !met && !capped;
         else go = (!met || time < (tau > P.m ? tau : P.m)) && !capped;
       }
+      if (TAPE && sh.bad) go = false;
       if (!go) break;
       time += 1;
       const bool coupled_step = (time > P.lag) && !met;
@@ -552,7 +581,63 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
       int all_equal = 1;
       if (tid == 0) sh.flag = 0;
       __syncthreads();
-      for (int i = tid; i < n; i += PG_T) {
+      if (TAPE) {
+        // replay: z_i for both chains by all threads, then thread 0 walks the observations on the sequential stream
+        for (int i = tid; i < n; i += PG_T) {
+          double xb1 = 0.0, xb2 = 0.0;
+          for (int j = 0; j < p; ++j) {
+            const double xv = M.X[(size_t)j * n + i];
+            xb1 = ubm_fma(xv, beta1[j], xb1);
+            if (coupled_step) xb2 = ubm_fma(xv, beta2[j], xb2);
+          }
+          w1[i] = fabs(xb1); w2[i] = fabs(xb2);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          PgSeq r;
+          r.tu = P.tape_u + rep * P.len_u; r.tn = P.tape_n + rep * P.len_n; r.te = P.tape_e + rep * P.len_e;
+          r.lu = P.tape_u ? P.len_u : 0; r.ln = P.tape_n ? P.len_n : 0; r.le = P.tape_e ? P.len_e : 0;
+          r.iu = sh.iu; r.in = sh.in; r.ie = sh.ie; r.bad = false;
+          int eq = 1;
+          for (int i = 0; i < n && !r.bad; ++i) {
+            const double z1 = w1[i], z2 = w2[i];
+            if (!coupled_step) { w1[i] = pg_draw(z1, r); continue; }
+            double wa, wb;
+            if (M.w_coupling == 1) {                                      // w_rejsamplerC (:50-74)
+              const double z_min = z1 < z2 ? z1 : z2, z_max = z1 < z2 ? z2 : z1;
+              const double w_min = pg_draw(z_min, r);
+              const double log_u = pg_log(r.u());
+              const double log_ratio = -0.5 * w_min * (z_max * z_max - z_min * z_min);
+              double w_max;
+              if (log_u < log_ratio) w_max = w_min;
+              else w_max = pg_draw(z_max, r);
+              wa = (z1 < z2) ? w_min : w_max; wb = (z1 < z2) ? w_max : w_min;
+            } else {                                                      // w_max_couplingC (:87-113)
+              wa = pg_draw(z1, r);
+              const double u1 = r.u();
+              const double la1 = pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * wa - (pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * wa);
+              if (pg_log(u1) <= la1) wb = wa;
+              else {
+                bool accept = false;
+                wb = wa;
+                while (!accept && !r.bad) {
+                  wb = pg_draw(z2, r);
+                  const double u2 = r.u();
+                  const double la2 = pg_logcosh(z1 / 2.) - 0.5 * z1 * z1 * wb - (pg_logcosh(z2 / 2.) - 0.5 * z2 * z2 * wb);
+                  if (pg_log(u2) > la2) accept = true;
+                }
+              }
+            }
+            w1[i] = wa; w2[i] = wb;
+            if (wa != wb) eq = 0;
+          }
+          sh.iu = r.iu; sh.in = r.in; sh.ie = r.ie; sh.eq = eq;
+          if (r.bad) sh.bad = 1;
+        }
+        __syncthreads();
+        all_equal = sh.eq;
+      }
+      for (int i = tid; i < n && !TAPE; i += PG_T) {
         double xb1 = 0.0, xb2 = 0.0;
         for (int j = 0; j < p; ++j) {                                     // xbeta_ (logisticregressioncoupling.cpp:22-32)
           const double xv = M.X[(size_t)j * n + i];
@@ -588,7 +673,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
       __syncthreads();
       // Phase 2: the rejection loop of the max coupling (:99-110), one warp per listed observation, 32 attempts at a
       // time (attempt a draws from its own region of the cell, so the first accepted attempt is the sequential answer)
-      if (coupled_step) {
+      if (coupled_step && !TAPE) {
         const int nlist = sh.flag;
         for (int q = warp; q < nlist; q += PG_T / 32) {
           const int i = plist[q];
@@ -640,7 +725,9 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
         // single kernel: beta = fast_rmvnorm_chol(1, m, Linv) (germancredit.run.R:27-28): y_j = sum_{i >= j} z_i Linv(i, j)
         if (warp == 0) {
           const unsigned long long in0 = sh.in;
-          for (int j = lane; j < p; j += 32) zz[j] = ubm_philox_n(P.seed, grep, in0 + j);
+          bool badr = false;
+          for (int j = lane; j < p; j += 32) zz[j] = draw_n_at<TAPE>(P, rep, in0 + j, &badr);
+          if (TAPE && __any_sync(0xffffffffu, badr) && lane == 0) sh.bad = 1;
           __syncwarp();
           for (int j = lane; j < p; j += 32) {
             double a = 0.0;
@@ -657,8 +744,9 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
         pg_cta_chol(MA1, MA2, tmp, p, tid);
         if (warp == 0) {                                                  // rmvnorm_max_coupling_ (src/mvnorm.cpp:91-129)
           unsigned long long in0 = sh.in, iu0 = sh.iu;
+          bool badr = false;
           // x1 = z U1 + m1, U1 = Ls1': y_j = sum_{i <= j} z_i Ls1(j, i)
-          for (int j = lane; j < p; j += 32) zz[j] = ubm_philox_n(P.seed, grep, in0 + j);
+          for (int j = lane; j < p; j += 32) zz[j] = draw_n_at<TAPE>(P, rep, in0 + j, &badr);
           in0 += p;
           __syncwarp();
           for (int j = lane; j < p; j += 32) {
@@ -667,7 +755,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
             x1[j] = a + m1[j];
           }
           __syncwarp();
-          const double logu = ubm_log(ubm_philox_u(P.seed, grep, iu0));   // :103-106
+          const double logu = ubm_log(draw_u_at<TAPE>(P, rep, iu0, &badr));   // :103-106
           iu0 += 1;
           const double d11 = pg_warp_dmvnorm(x1, m1, MA1, p, lane, tmp);
           const double d12 = pg_warp_dmvnorm(x1, m2, MA2, p, lane, tmp);
@@ -675,8 +763,8 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
             for (int j = lane; j < p; j += 32) x2[j] = x1[j];
           } else {
             bool accept = false;
-            while (!accept) {                                             // :113-123
-              for (int j = lane; j < p; j += 32) zz[j] = ubm_philox_n(P.seed, grep, in0 + j);
+            while (!accept && !(TAPE && __any_sync(0xffffffffu, badr))) {   // :113-123
+              for (int j = lane; j < p; j += 32) zz[j] = draw_n_at<TAPE>(P, rep, in0 + j, &badr);
               in0 += p;
               __syncwarp();
               for (int j = lane; j < p; j += 32) {
@@ -685,7 +773,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
                 x2[j] = a + m2[j];
               }
               __syncwarp();
-              const double lu = ubm_log(ubm_philox_u(P.seed, grep, iu0));
+              const double lu = ubm_log(draw_u_at<TAPE>(P, rep, iu0, &badr));
               iu0 += 1;
               const double d22 = pg_warp_dmvnorm(x2, m2, MA2, p, lane, tmp);
               const double d21 = pg_warp_dmvnorm(x2, m1, MA1, p, lane, tmp);
@@ -698,6 +786,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
             beta2[j] = all_equal ? x1[j] : x2[j];                         // germancredit.run.R:38-41
           }
           if (lane == 0) { sh.in = in0; sh.iu = iu0; }
+          if (TAPE && __any_sync(0xffffffffu, badr) && lane == 0) sh.bad = 1;
         }
         if (all_equal) { met = true; tau = time; }
       }
@@ -733,6 +822,7 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
              (double)tacc[5] / tsteps, (double)tacc[2] / tsteps);
 #endif
     // ---- results
+    if (TAPE && sh.bad) { met = false; if (tid == 0) atomicExch(P.status, UBM_ERR_TAPE); }
     if (tid == 0) {
       double cost = dinf();
       if (met) {
@@ -760,17 +850,17 @@ inline size_t pg_smem_bytes(int n, int p) {
 
 inline int pg_launch(const PgDevice& M, const RunParams& P, bool tape, int nsm, cudaStream_t st, int64_t* launches,
                      std::string* err) {
-  if (tape) { *err = "pg logistic: replay tapes are not available for this model (draws are addressed by cell)"; return UBM_ERR_UNSUPPORTED; }
   if (P.nbreaks >= 2) { *err = "pg logistic: histogram bins are not available for this model yet"; return UBM_ERR_UNSUPPORTED; }
   const size_t smem = pg_smem_bytes(M.n, M.p);
   if (smem > 227 * 1024) { *err = "pg logistic: n / p too large for shared memory"; return UBM_ERR_UNSUPPORTED; }
-  cudaError_t e = cudaFuncSetAttribute(pg_driver_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = tape ? pg_driver_kernel<true> : pg_driver_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { *err = std::string("pg logistic: smem attribute: ") + cudaGetErrorString(e); return UBM_ERR_CUDA; }
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pg_driver_kernel, PG_T, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PG_T, smem);
   if (e != cudaSuccess || per_sm < 1) { *err = "pg logistic: occupancy query failed"; return UBM_ERR_CUDA; }
   const int grid = (int)std::min<int64_t>((int64_t)nsm * per_sm, P.nrep);
-  pg_driver_kernel<<<grid, PG_T, smem, st>>>(M, P);
+  kern<<<grid, PG_T, smem, st>>>(M, P);
   *launches += 1;
   return UBM_OK;
 }
