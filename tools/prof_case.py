@@ -3,7 +3,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tests import cases
+from unbiasedmcmc_b200 import workloads as cases
 from unbiasedmcmc_b200 import _abi as A
 from unbiasedmcmc_b200 import registry as R
 from unbiasedmcmc_b200.engine import Engine

@@ -2,7 +2,7 @@
 Usage: python tools/time_case_c5.py [nrep] [k m]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from tests import cases
+from unbiasedmcmc_b200 import workloads as cases
 from unbiasedmcmc_b200 import registry as R
 from unbiasedmcmc_b200.engine import Engine
 eng = Engine(0)
