@@ -132,19 +132,14 @@ struct MvnModel {
   const double* chain_state(const State& s) const { return s.x.data(); }
   void copy(State& dst, const State& src) const { dst = src; }
 
-  // Canonical summation order of y_j = sum_{i<=j} v_i U[i,j] (the reference leaves it to Eigen): sequential fma in i,
-  // except that for the long columns the range is cut once — columns of the 4-column group g with K_g = 4g+4 rows
-  // longer than half = 4 floor((ceil(d/4) + 1) / 2) + 2 are summed as (sum over i < K_g - half) + (sum over i >= K_g - half).
-  // This lets the device split every long column between two threads of equal work (ubm_mvn.cuh).
+  // Summation order of y_j = sum_{i<=j} v_i U[i,j] (the reference leaves it to Eigen): one fma chain, sequential in i from
+  // 0.0.  This is also, bit for bit, what a chain of FP64 tensor-core MMAs computes (DMMA m8n8k4 accumulates its four
+  // products in k order with one rounding each — tools/dmma_probe.cu), which is how the device evaluates it (ubm_mvn.cuh).
   void vec_times_upper(const double* v, const std::vector<double>& U, double* out) const {
-    const int nCG = (d + 3) / 4, half = 4 * ((nCG + 1) / 2) + 2;
     for (int j = 0; j < d; ++j) {
-      const int Kg = 4 * (j / 4) + 4;
-      const int ks = (Kg > half) ? Kg - half : 0;
-      double lo = 0.0, hi = 0.0;
-      for (int i = 0; i < ks && i <= j; ++i) lo = ubm_fma(v[i], U[(size_t)j * d + i], lo);
-      for (int i = ks; i <= j; ++i) hi = ubm_fma(v[i], U[(size_t)j * d + i], hi);
-      out[j] = (ks > 0) ? (lo + hi) : hi;
+      double acc = 0.0;
+      for (int i = 0; i <= j; ++i) acc = ubm_fma(v[i], U[(size_t)j * d + i], acc);
+      out[j] = acc;
     }
   }
   // fast_dmvnorm_cholesky_inverse_ — src/mvnorm.cpp:71-86

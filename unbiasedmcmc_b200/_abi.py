@@ -101,11 +101,12 @@ def load_lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("UBM_LIB_PATH", LIB_PATH)      # debug builds (per-phase cycle counters) live beside the product library
+    if not os.path.exists(path):
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(the engine has no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp = C.c_void_p
     lib.ubm_create.argtypes = [C.c_int, C.POINTER(vp)]
     lib.ubm_destroy.argtypes = [vp]

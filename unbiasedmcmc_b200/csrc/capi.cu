@@ -67,7 +67,7 @@ struct ubm_plan {
   VarselDevice varsel{};
   DevBuf model_blob;
   // results
-  DevBuf uest, mcmc, corr, tau, cost, iter, bins_out, bin_acc, breaks, summary, counter, status, scratch;
+  DevBuf uest, mcmc, corr, tau, cost, iter, bins_out, bin_acc, bin_num, breaks, summary, counter, status, scratch;
   DevBuf tape_u, tape_n, tape_e, samples1, samples2;
   int64_t len_u = 0, len_n = 0, len_e = 0;
   bool want_bins_out = false, want_parts = false;
@@ -204,7 +204,8 @@ static int plan_build(ubm_handle* h, int mode, int32_t model_kind, const void* m
     delete p;
     return fail(h, UBM_ERR_UNSUPPORTED, "this model's state is integer valued (natural statistics / inclusion indicators): h must be the identity");
   }
-  if (mode == MODE_ESTIMATOR && bins && bins->nbreaks >= 2 && model_kind != UBM_MODEL_NORMAL_MIXTURE) {
+  if (mode == MODE_ESTIMATOR && bins && bins->nbreaks >= 2 && model_kind != UBM_MODEL_NORMAL_MIXTURE &&
+      model_kind != UBM_MODEL_MVN) {
     delete p;
     return fail(h, UBM_ERR_UNSUPPORTED, "on-the-fly histogram bins are not available for this model (use ubm_sample_coupled_chains + ubm_estimator_bins)");
   }
@@ -229,6 +230,7 @@ static int plan_build(ubm_handle* h, int mode, int32_t model_kind, const void* m
     if (p->nbins) {
       if ((e = p->bin_acc.alloc((size_t)2 * p->nbins * 8)) != cudaSuccess) return e;
       if ((e = p->breaks.alloc((size_t)p->nbreaks * 8)) != cudaSuccess) return e;
+      if (model_kind != UBM_MODEL_NORMAL_MIXTURE && (e = p->bin_num.alloc(n * p->nbins * 8)) != cudaSuccess) return e;
       if ((e = cudaMemcpyAsync(p->breaks.p, bins->breaks, (size_t)p->nbreaks * 8, cudaMemcpyHostToDevice, h->stream)) != cudaSuccess) return e;
     }
     if ((e = p->summary.alloc((size_t)ubm_summary_len(p->dimh, p->nbins) * 8)) != cudaSuccess) return e;
@@ -285,12 +287,14 @@ static int plan_run(ubm_plan* p, int draws_mode, uint64_t seed, int64_t nrep, in
   P.tau = p->tau.as<double>(); P.cost = p->cost.as<double>(); P.iter = p->iter.as<int64_t>();
   P.bins_out = p->want_bins_out ? p->bins_out.as<double>() : nullptr;
   P.bin_acc = p->bin_acc.as<long long>();
+  P.bin_num = p->bin_num.as<long long>();
   P.samples1 = p->samples1.as<double>(); P.samples2 = p->samples2.as<double>(); P.stride = p->stride;
   P.work_counter = p->counter.as<unsigned long long>(); P.status = p->status.as<int>();
   cudaStream_t st = h->stream;
   CU(cudaMemsetAsync(p->counter.p, 0, 8, st));
   CU(cudaMemsetAsync(p->status.p, 0, 4, st));
   if (p->nbins) CU(cudaMemsetAsync(p->bin_acc.p, 0, p->bin_acc.bytes, st));
+  if (p->nbins && p->bin_num.p) CU(cudaMemsetAsync(p->bin_num.p, 0, (size_t)nrep * p->nbins * 8, st));
   const bool tape = draws_mode == UBM_DRAWS_TAPE;
   const int nsm = h->prop.multiProcessorCount;
   CU(cudaEventRecord(p->e0, st));
@@ -323,6 +327,11 @@ static int plan_run(ubm_plan* p, int draws_mode, uint64_t seed, int64_t nrep, in
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(p->e1, st));
+  if (p->nbins && p->bin_num.p) {
+    bins_finalize_kernel<<<p->nbins, 256, 0, st>>>(nrep, p->nbins, P.tau, P.bin_num, (double)(p->m - p->k + 1), P.bins_out, P.bin_acc);
+    h->launches += 1;
+    CU(cudaGetLastError());
+  }
   SummaryArgs A{};
   A.nrep = nrep; A.dimh = (p->mode == MODE_ESTIMATOR) ? p->dimh : 0; A.nbins = p->nbins;
   A.tau = P.tau; A.cost = P.cost; A.iter = P.iter; A.uest = (p->mode == MODE_ESTIMATOR) ? P.uest : nullptr;

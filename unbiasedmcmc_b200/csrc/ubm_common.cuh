@@ -29,6 +29,8 @@ struct RunParams {
   int64_t* iter;                 // [nrep]
   double* bins_out;              // [nrep][nbins]
   long long* bin_acc;            // [2][nbins] integer sums over uncensored replicates: numerators, squares
+  long long* bin_num;            // [nrep][nbins] per-replicate integer numerators (block-per-replicate kernels: global
+                                 // reductions, turned into bins_out / bin_acc by bins_finalize_kernel); null for C1
   // chains mode
   double *samples1, *samples2;   // [nrep][stride][dim]
   int64_t stride;

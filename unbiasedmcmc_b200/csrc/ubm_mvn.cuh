@@ -4,38 +4,32 @@
 //   drivers    R/meetingtime.R:24-48, R/coupled_chains.R:39-87, R/unbiasedestimator.R:43-104
 //   kernels    R/get_mh_kernels.R:29-77 (d > 1 branch)
 //   numerics   src/mvnorm.cpp:30-46 (fast_rmvnorm_cholesky_), :71-86 (fast_dmvnorm_cholesky_inverse_),
-//              :185-236 (rmvnorm_reflection_max_coupling_)
+//              :185-236 (rmvnorm_reflection_max_coupling_), src/estimator_bin.cpp:10-42 (on the fly)
 //
-// Design (B200): the three upper-triangular factors (proposal Cholesky, its inverse, the target's Cholesky
-// inverse) are block-packed and stay in SHARED MEMORY for the life of the kernel; a CTA runs R replicate
-// "slots" in lock step so that the five vector x triangular-matrix products of a coupled step become three
-// small register-tiled GEMM phases ([rows x d] . [d x d]) on the FP64 pipe:
+// Design (B200): a CTA runs R = 16 replicate "slots" in lock step, so that the five vector x triangular-matrix products of
+// a coupled step become three small GEMM phases ([rows x d] . [d x d]) — and those run on the FP64 TENSOR pipe:
 //   phase A  z = -(x2 - x1)^T Cinv_prop            (coupled slots)
 //   phase B  prop = x + xi^T C_prop  (and eta)     (all active rows)
 //   phase C  w = Cinv_pi^T (prop - mean_pi)        (all proposals) -> log-density
-// Every output element is accumulated by ONE thread, sequentially in k with fma, so results are bit-identical
-// to the oracle's plain loops (structural zeros only ever add exact zeros).  Triangular work is balanced by
-// pairing column group g with nCG-1-g.  Slots are refilled from a global counter as soon as a replicate
-// finishes (work stealing).  Reductions over a d-vector use the canonical order "fma chain inside each
-// 4-column group, xor-butterfly over the <= 32 groups" (oracle: sum_g4_*).
+// One DMMA (mma.sync m8n8k4 f64) multiplies 8 slot rows x 4 k-values into an 8-column output tile.  It accumulates its
+// four products as a chain of fused multiply-adds in k order, one rounding each (measured: tools/dmma_probe.cu, 128000 of
+// 128000 outputs equal the fma chain), so a column sum evaluated by a chain of DMMAs over k = 0, 4, 8, ... is bit for bit
+// the sequential fma loop of the oracle (oracle_models.hpp: vec_times_upper) — replay parity survives the tensor cores.
+// The three upper-triangular factors are packed as ready-made B fragments (tile (jt, ks): 32 doubles, lane l holds
+// U[4 ks + l%4][8 jt + l/4]) and stay in SHARED MEMORY for the life of the kernel (140 KB at d = 100); slot rows are read
+// as A fragments (row stride == 4 mod 16 doubles: conflict-free).  Row tiles are static: tile q = chain (q >> 1), slots
+// 8 (q & 1) .. + 7; a tile is skipped when none of its rows takes part in the phase, rows that do not are masked at the
+// write.  Output tiles jt (2 jt + 2 k-steps each) are handed to the eight consumer warps by a longest-first table built
+// on the host and balanced per SM sub-partition (the tensor pipe is per sub-partition).
 //
-// Thread roles (512 threads, warp-specialised): warps 0-7 (two per SM sub-partition, so that one fills the other's DFMA
-// issue gaps) are CONSUMERS: they run the GEMM phases and the coupling algebra, synchronising among themselves on a
-// named barrier; warps 8-15 are PRODUCERS: while step t is computed they generate every draw of step t+1 (the d normals
-// per slot through Philox + AS241, the rare tail branch compacted over the warp, and the log-uniforms, into a small
-// ring), so no random-number work sits on the critical path.  All 16 warps share the short per-slot section at the
-// step boundary (accept/reject, state and estimator update, slot state machine), one warp per slot.  Tiles are 2 rows x
-// 4 columns per thread over balanced half-units (see mvn_phase_compute); phases with more rows than one batch run in
-// batches.  Two CTA-wide barriers per step.
-//
-// Shared-memory layout notes (ncu and tools/lds_probe.cu, profiles/r01_mvn.md: the first version had 12.5e9 bank
-// conflicts; an LDS.128 is served per quarter-warp, one wavefront when its 16-byte words fall into distinct banks):
-//   - packed group g starts at 8 g (g+1) + 4 g (+2 for the long groups) doubles, so that the two streams of a
-//     quarter-warp (a short group and its long partner) read different banks;
-//   - vectors use a row stride of DPS doubles with DPS/2 == 2 (mod 8) words: four consecutive rows plus the same rows an
-//     odd number of words further on (the partner stream) cover the eight bank groups exactly once;
-//   - the canonical cut of the long columns is `half` == 2 (mod 4) rows from the end (mvn_half);
-//   - GEMM units are numbered row-group fastest, so a warp touches few column groups (matrix bytes dominate).
+// Thread roles (512 threads, warp-specialised): warps 0-7 (two per SM sub-partition) are CONSUMERS: they run the GEMM
+// phases and the coupling algebra, synchronising among themselves on a named barrier; warps 8-15 are PRODUCERS: while
+// step t is computed they generate every draw of step t+1 (the d normals per slot through Philox + AS241, the rare tail
+// branch compacted over the warp, and the log-uniforms, into a small ring), so no random-number work sits on the critical
+// path.  All 16 warps share the short per-slot section at the step boundary (accept/reject, state and estimator update,
+// slot state machine): warp s owns slot s and keeps its estimator sums in registers.  Slots are refilled from a global
+// counter as soon as a replicate finishes (work stealing).  Reductions over a d-vector use the canonical order "fma chain
+// inside each 4-column group, xor-butterfly over the <= 32 groups" (oracle: sum_g4_*).  Two CTA-wide barriers per step.
 #pragma once
 #include <algorithm>
 #include <string>
@@ -44,57 +38,66 @@
 
 namespace ubm {
 
+#define MVN_MAXR 16
+#define MVN_CW 8       // consumer warps: warps 0-7 (two per SM sub-partition)
+#define MVN_PW 8       // producer warps: warps 8-15 produce the draws of the next step
+#define MVN_GT (32 * MVN_CW)               // consumer (GEMM) threads
+#define MVN_T (32 * (MVN_CW + MVN_PW))     // threads per CTA
+#define MVN_JMAX 2     // output tiles per consumer warp (d <= 128: 16 tiles over 8 warps)
+
 struct MvnDevice {
-  int d, DP, DPS, nCG, nPairs, zero_mean;
+  int d, DPS, nNT, nCG, zero_mean;
   int packLen;                 // doubles per packed matrix
   double cst;                  // src/mvnorm.cpp:74-75
   const double *mean_pi, *init_mean, *packA, *packB, *packC, *packI;   // device
   size_t offs[6];              // host-side: offsets inside the blob
+  unsigned char jobs[MVN_CW][MVN_JMAX];    // output tiles of consumer warp w (255: none), the longer one first
 };
 
-// column group g holds rows k = 0 .. 4g+3 (rows >= d and entries below the diagonal are zero), 4 doubles per row.
-// Pads: group g starts 4 g (+2 for the long groups g >= nPairs) doubles late, so that the 16-byte words read by one
-// quarter-warp (a short group gA = pr and its partner gB = nCG-1-pr, at the same loop step) fall into different banks.
-__host__ __device__ __forceinline__ int mvn_group_off(int g, int nPairs) { return 8 * g * (g + 1) + 4 * g + (g >= nPairs ? 2 : 0); }
-__host__ __device__ __forceinline__ int mvn_pack_len(int nCG, int nPairs) { return mvn_group_off(nCG - 1, nPairs) + 16 * nCG + 16; }
-// The canonical cut of the long columns (oracle: vec_times_upper): K_g > half is summed as [0, K_g - half) + [K_g - half, K_g).
-// half == 2 (mod 4) keeps the two streams of a column group, `half` rows apart, in different banks.
-__host__ __device__ __forceinline__ int mvn_half(int nCG) { return 4 * ((nCG + 1) / 2) + 2; }
+// packed B fragments: tile (jt, ks), ks = 0 .. 2 jt + 1, at index jt (jt + 1) + ks; lane l of the tile holds
+// U[k = 4 ks + (l & 3)][n = 8 jt + (l >> 2)], zero below the diagonal and past d.
+__host__ __device__ __forceinline__ int mvn_tile_base(int jt) { return jt * (jt + 1); }
+__host__ __device__ __forceinline__ int mvn_pack_len(int nNT) { return 32 * nNT * (nNT + 1); }
 
-inline void mvn_pack_matrix(const double* Ucm, int d, int nCG, std::vector<double>* blob) {
-  size_t base = blob->size();
-  const int nPairs = (nCG + 1) / 2;
-  blob->resize(base + mvn_pack_len(nCG, nPairs), 0.0);
-  for (int g = 0; g < nCG; ++g) {
-    double* p = blob->data() + base + mvn_group_off(g, nPairs);
-    for (int k = 0; k < 4 * g + 4; ++k)
-      for (int c = 0; c < 4; ++c) {
-        int j = 4 * g + c;
-        p[4 * k + c] = (j < d && k <= j) ? Ucm[(size_t)j * d + k] : 0.0;
+inline void mvn_pack_matrix(const double* Ucm, int d, int nNT, std::vector<double>* blob) {
+  const size_t base = blob->size();
+  blob->resize(base + mvn_pack_len(nNT), 0.0);
+  for (int jt = 0; jt < nNT; ++jt)
+    for (int ks = 0; ks < 2 * jt + 2; ++ks)
+      for (int l = 0; l < 32; ++l) {
+        const int k = 4 * ks + (l & 3), n = 8 * jt + (l >> 2);
+        (*blob)[base + (size_t)(mvn_tile_base(jt) + ks) * 32 + l] = (n < d && k <= n) ? Ucm[(size_t)n * d + k] : 0.0;
       }
-  }
 }
 
 inline void mvn_pack_host(const ubm_model_mvn* s, MvnDevice* M, std::vector<double>* blob) {
   const int d = s->d;
-  M->d = d; M->nCG = (d + 3) / 4; M->DP = 4 * M->nCG; M->nPairs = (M->nCG + 1) / 2;
-  // row stride (in 16-byte words) == 2 (mod 8): four consecutive rows plus the same rows an odd number of words further
-  // on (the partner stream) cover the eight bank groups exactly once.  Reads of the GEMM prefetch may run 16 bytes past a
-  // row: that is the next row or the next array, never used.
-  M->DPS = M->DP + 2 * ((((2 - 2 * M->nCG) % 8) + 8) % 8);
+  M->d = d; M->nNT = (d + 7) / 8; M->nCG = (d + 3) / 4;
+  // row stride: >= 8 nNT (an A fragment of the last tile reads up to column 8 nNT - 1) and == 4 (mod 16) doubles, so that
+  // the 4 rows x 4 consecutive doubles read by a half-warp fall into 16 distinct bank pairs
+  M->DPS = 8 * M->nNT;
+  while (M->DPS % 16 != 4) M->DPS += 4;
   M->zero_mean = 1;
   for (int j = 0; j < d; ++j) if (s->mean_pi[j] != 0.0) M->zero_mean = 0;
   double halflogdet = 0.0;
   for (int j = 0; j < d; ++j) halflogdet = halflogdet + ubm_log(s->chol_inv_pi[(size_t)j * d + j]);
   M->cst = -(-halflogdet) - (d * 0.9189385);     // truncated constant kept verbatim (src/mvnorm.cpp:75)
-  M->packLen = mvn_pack_len(M->nCG, M->nPairs);
+  M->packLen = mvn_pack_len(M->nNT);
   blob->clear();
   M->offs[0] = blob->size(); for (int j = 0; j < M->DPS; ++j) blob->push_back(j < d ? s->mean_pi[j] : 0.0);
   M->offs[1] = blob->size(); for (int j = 0; j < M->DPS; ++j) blob->push_back(j < d ? s->init_mean[j] : 0.0);
-  M->offs[2] = blob->size(); mvn_pack_matrix(s->chol_inv_prop, d, M->nCG, blob);
-  M->offs[3] = blob->size(); mvn_pack_matrix(s->chol_prop, d, M->nCG, blob);
-  M->offs[4] = blob->size(); mvn_pack_matrix(s->chol_inv_pi, d, M->nCG, blob);
-  M->offs[5] = blob->size(); mvn_pack_matrix(s->init_chol, d, M->nCG, blob);
+  M->offs[2] = blob->size(); mvn_pack_matrix(s->chol_inv_prop, d, M->nNT, blob);
+  M->offs[3] = blob->size(); mvn_pack_matrix(s->chol_prop, d, M->nNT, blob);
+  M->offs[4] = blob->size(); mvn_pack_matrix(s->chol_inv_pi, d, M->nNT, blob);
+  M->offs[5] = blob->size(); mvn_pack_matrix(s->init_chol, d, M->nNT, blob);
+  // output tiles -> consumer warps, folded longest-first: warp w takes the (w+1)-th longest tile and the (16-w)-th, so that
+  // every warp runs about the same number of k-steps (a warp's K loop is a dependent chain of loads and DMMAs; the longest
+  // warp sets the length of a phase)
+  for (int w = 0; w < MVN_CW; ++w) {
+    const int j0 = M->nNT - 1 - w, j1 = M->nNT - 1 - (2 * MVN_CW - 1 - w);
+    M->jobs[w][0] = (j0 >= 0) ? (unsigned char)j0 : 255;
+    M->jobs[w][1] = (j1 >= 0) ? (unsigned char)j1 : 255;
+  }
 }
 inline void mvn_bind_device(MvnDevice* M, const double* dev) {
   M->mean_pi = dev + M->offs[0]; M->init_mean = dev + M->offs[1];
@@ -102,121 +105,21 @@ inline void mvn_bind_device(MvnDevice* M, const double* dev) {
 }
 
 enum { SL_IDLE = 0, SL_WAIT = 1, SL_INIT = 2, SL_SINGLE = 3, SL_COUPLED = 4 };
-#define MVN_MAXR 16
-#ifndef MVN_RT
-#define MVN_RT 2       // rows per GEMM register tile (x 4 columns)
-#endif
-#ifndef MVN_CW
-#define MVN_CW 8       // consumer warps: warps 0-7 (two per SM sub-partition, so that one fills the other's DFMA issue gaps)
-#endif
-#ifndef MVN_PW
-#define MVN_PW 8       // producer warps: warps 8-15 produce the draws of the next step
-#endif
-#define MVN_GT (32 * MVN_CW)               // consumer (GEMM) threads
-#define MVN_T (32 * (MVN_CW + MVN_PW))     // threads per CTA
 
 struct MvnSlots {   // per-slot scalars, in shared memory
   long long rep[MVN_MAXR], time[MVN_MAXR], tau[MVN_MAXR];
   unsigned long long iu[MVN_MAXR], in[MVN_MAXR], pu[MVN_MAXR];
   double pdf1[MVN_MAXR], pdf2[MVN_MAXR];
   int phase[MVN_MAXR], met[MVN_MAXR], ident[MVN_MAXR], bad[MVN_MAXR];
-  int rowsA[MVN_MAXR], rowsB[2 * MVN_MAXR], rowsI[2 * MVN_MAXR], rowsC[2 * MVN_MAXR];
-  int nA, nB, nI, nC;
   int exhausted;
 };
 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(MVN_GT) : "memory"); }
 
-// Operands of one two-row step of a half-unit: 8 matrix entries (rows k, k+1 of a 4-column group) and the RT row pairs.
-template <int RT, int MODE>
-struct MvnOperands {
-  double2 m0, m1, m2, m3, v[RT], w[RT], mu;
-  __device__ __forceinline__ void load(const double* __restrict__ mp, const double* const* in, const double* const* in2,
-                                       const double* __restrict__ aux, int k) {
-    m0 = *reinterpret_cast<const double2*>(mp); m1 = *reinterpret_cast<const double2*>(mp + 2);
-    m2 = *reinterpret_cast<const double2*>(mp + 4); m3 = *reinterpret_cast<const double2*>(mp + 6);
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      v[r] = *reinterpret_cast<const double2*>(in[r] + k);
-      if (MODE == 2) w[r] = *reinterpret_cast<const double2*>(in2[r] + k);
-    }
-    if (MODE == 1) mu = *reinterpret_cast<const double2*>(aux + k);
-  }
-  __device__ __forceinline__ void fma_into(double (&acc)[RT][4]) const {
-    double2 x[RT];
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      x[r] = v[r];
-      if (MODE == 1) { x[r].x = x[r].x - mu.x; x[r].y = x[r].y - mu.y; }
-      if (MODE == 2) { x[r].x = w[r].x - x[r].x; x[r].y = w[r].y - x[r].y; }
-    }
-    // row k for all accumulators, then row k+1: dependent fma pairs are 4 RT instructions apart
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      acc[r][0] = ubm_fma(x[r].x, m0.x, acc[r][0]);
-      acc[r][1] = ubm_fma(x[r].x, m0.y, acc[r][1]);
-      acc[r][2] = ubm_fma(x[r].x, m1.x, acc[r][2]);
-      acc[r][3] = ubm_fma(x[r].x, m1.y, acc[r][3]);
-    }
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      acc[r][0] = ubm_fma(x[r].y, m2.x, acc[r][0]);
-      acc[r][1] = ubm_fma(x[r].y, m2.y, acc[r][1]);
-      acc[r][2] = ubm_fma(x[r].y, m3.x, acc[r][2]);
-      acc[r][3] = ubm_fma(x[r].y, m3.y, acc[r][3]);
-    }
-  }
-};
-
-// One GEMM half-unit: RT input rows (smem, 16-byte aligned) against two consecutive row segments of a packed matrix,
-// executed as ONE loop so that the lanes of a warp — whose segments differ — run the same instruction stream:
-//   segment 1: n1 (even) two-row steps of column group g1 from k = 0   -> first[r][c]
-//   segment 2: n2 two-row steps of column group g2 from k = k2 (even)  -> acc[r][c]
-// each sum sequential in k.  The loop is unrolled by two steps with two operand sets (ping-pong): the operands of the
-// next step are requested while this one is computed, without register copies (reads run at most 32 bytes past a
-// group / row: padding, the next row or the next array, never used).
-// MODE 0: plain input; 1: input minus `aux` vector (the target mean); 2: input = in2_r[k] - in_r[k] (x2 - x1).
-template <int RT, int MODE>
-__device__ __forceinline__ void mvn_unit(const double* __restrict__ pack, int nPairs, int g1, int n1, int g2, int k2, int n2,
-                                         const double* const* in, const double* const* in2,
-                                         const double* __restrict__ aux, double (&first)[RT][4], double (&acc)[RT][4]) {
-  const int n = n1 + n2;
-  const double* const mp2 = pack + mvn_group_off(g2, nPairs) + 4 * k2;
-  const double* mp = (n1 > 0) ? pack + mvn_group_off(g1, nPairs) : mp2;
-  int k = (n1 > 0) ? 0 : k2;
-  MvnOperands<RT, MODE> A, B;
-  A.load(mp, in, in2, aux, k);
-  int it = 0;
-  for (; it + 1 < n; it += 2) {
-    if (it == n1 && it > 0) {      // segment 1 is complete (a few lanes, once per unit)
-#pragma unroll
-      for (int r = 0; r < RT; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { first[r][c] = acc[r][c]; acc[r][c] = 0.0; }
-    }
-    B.load(mp + 8, in, in2, aux, k + 2);                 // step it + 1 (odd: never the first of segment 2)
-    A.fma_into(acc);
-    const bool jump = (it + 2 == n1);
-    mp = jump ? mp2 : mp + 16;
-    k = jump ? k2 : k + 4;
-    A.load(mp, in, in2, aux, k);                         // step it + 2
-    B.fma_into(acc);
-  }
-  if (it < n) {                                          // odd number of steps: the last one is in A
-    if (it == n1 && it > 0) {
-#pragma unroll
-      for (int r = 0; r < RT; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { first[r][c] = acc[r][c]; acc[r][c] = 0.0; }
-    }
-    A.fma_into(acc);
-  }
-  if (n1 > 0 && n2 == 0) {
-#pragma unroll
-    for (int r = 0; r < RT; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) { first[r][c] = acc[r][c]; acc[r][c] = 0.0; }
-  }
+// D(8 x 8) += A(8 x 4) B(4 x 8): a = A[l / 4][l % 4], b = B[l % 4][l / 4], d0 / d1 = D[l / 4][2 (l % 4) + {0, 1}].
+// The four products of an output are accumulated as an fma chain in k order (tools/dmma_probe.cu).
+__device__ __forceinline__ void mvn_dmma(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
 __device__ __forceinline__ double warp_butterfly(double v) {
@@ -285,95 +188,108 @@ struct MvnSmem {
   double *X1, *X2;                // [R][DPS]
   double *XI;                     // [2][R][DPS]  double-buffered chain-1 row: normals of this step -> proposal 1 (in place)
   double *V2;                     // [R][DPS]     chain-2 row: z -> e -> eta -> proposal 2 (in place)
-  double *ACC;                    // [R][2][dimh] mcmc sums, correction sums (estimator mode)
-  double *TG;                     // [2R][32]
+  double *TG;                     // [2R][32]     per 4-column group partial sums of squares
   double *ZERO;                   // [DPS]
   double *LU;                     // [R][8] ring of log-uniforms produced ahead
   MvnSlots* S;
 };
 
-__host__ __device__ inline size_t mvn_smem_bytes(int packLen, int DPS, int R, int acc_per_slot) {
-  return (size_t)(3 * packLen + DPS + 5 * R * DPS + R * acc_per_slot + 2 * R * 32 + DPS + 8 * R) * sizeof(double) +
-         sizeof(MvnSlots) + 16;
+__host__ __device__ inline size_t mvn_smem_bytes(int packLen, int DPS, int R) {
+  return (size_t)(3 * packLen + DPS + 5 * R * DPS + 2 * R * 32 + DPS + 8 * R) * sizeof(double) + sizeof(MvnSlots) + 16;
 }
 
 #ifdef UBM_MVN_TIMING
-static __device__ long long g_mvn_tloop;      // debug builds only: cycles thread (0,0) spent inside the GEMM loops
+static __device__ long long g_mvn_tk[4];      // debug builds only: thread (0,0): cycles in K loops, k-steps, DMMAs, calls
 #endif
-// GEMM phase over a compact row list (row code = slot * 2 + which).  Work is cut into BALANCED HALF-UNITS: column
-// group gA = pr (K_A = 4 pr + 4 rows) is paired with gB = nCG-1-pr (K_B rows, K_A + K_B = 2 half), and the long
-// column group is summed in two segments [0, K_B - half) and [K_B - half, K_B) — the engine's canonical order
-// (oracle: vec_times_upper).  Lane 2i (h = 0) computes gA completely plus the first segment of gB, lane 2i+1 (h = 1)
-// the second segment of gB: both stream exactly `half` matrix rows.  The partner's first-segment sums arrive by
-// shuffle, so h = 0 owns the outputs of gA and h = 1 those of gB.  Unit index u = ((pr * nRG) + rg) * 2 + h.
-// Must be called by all 32 lanes of every consumer warp (shuffles); every thread owns at most one output group.
-template <int RT, int MODE>
-__device__ __forceinline__ void mvn_phase_compute(const double* __restrict__ pack, const MvnSmem& sm, const double* V1,
-                                                  const int* rows, int nrows, int DPS, int nCG, int nPairs,
-                                                  const double* aux, int u, int (&code)[RT], int& g_out, bool& has_out,
-                                                  double (&out)[RT][4]) {
-  const int nRG = (nrows + RT - 1) / RT;
-  const bool active = u < nRG * nPairs * 2;
-  const int h = u & 1, ur = u >> 1;
-  const int pr = active ? ur / nRG : 0, rg = active ? ur - pr * nRG : 0;
-  const int gA = pr, gB = nCG - 1 - pr;
-  const int KA = 4 * gA + 4, KB = 4 * gB + 4, half = mvn_half(nCG);
-  const bool middle = (gA == gB);
-  const int ks = (KB > half) ? KB - half : 0;
-  const double* in[RT];
-  const double* in2[RT];
+// The K loop of one output tile jt for this consumer warp: acc[i] = rows of the i-th ACTIVE row tile times the packed
+// factor, k-steps in increasing order.  MODE 0: a = r0[k]; 1: a = r0[k] - mean[k]; 2: a = r1[k] - r0[k].
+// NT (compile time) row tiles, no predication: a DMMA that is predicated off still occupies its issue slot of the tensor
+// pipe (measured: the first version ran every k-step at the cost of four DMMAs whatever the mask).
+template <int MODE, bool GLOBAL, int NT>
+__device__ __forceinline__ void mvn_kloop(const double* __restrict__ bp, int nk, int kq, const double* const (&p0)[4],
+                                          const double* const (&p1)[4], const double* __restrict__ mean, double (&acc)[4][2]) {
+  // fragments of k-step ks + 1 are requested before the DMMAs of k-step ks are issued (register double buffer)
+  double b = GLOBAL ? __ldg(bp) : bp[0];
+  double a[NT], a1[NT], mu = 0.0;
 #pragma unroll
-  for (int r = 0; r < RT; ++r) {
-    const int idx = r * nRG + rg;      // the rows read by one load instruction are consecutive: distinct banks
-    code[r] = (active && idx < nrows) ? rows[idx] : -1;
-    if (MODE == 2) {
-      in[r] = (code[r] < 0) ? sm.ZERO : sm.X1 + (code[r] >> 1) * DPS;
-      in2[r] = (code[r] < 0) ? sm.ZERO : sm.X2 + (code[r] >> 1) * DPS;
-    } else {
-      in[r] = (code[r] < 0) ? sm.ZERO : ((code[r] & 1) ? sm.V2 : V1) + (code[r] >> 1) * DPS;
-      in2[r] = in[r];
+  for (int i = 0; i < NT; ++i) { a[i] = p0[i][kq]; if (MODE == 2) a1[i] = p1[i][kq]; }
+  if (MODE == 1) mu = mean[kq];
+  for (int ks = 0; ks < nk; ++ks) {
+    const int kn = (ks + 1 < nk) ? ks + 1 : ks;        // the last trip re-reads its own fragments (never used)
+    const double bn = GLOBAL ? __ldg(bp + 32 * kn) : bp[32 * kn];
+    const int ko = 4 * kn + kq;
+    double an[NT], a1n[NT], mun = 0.0;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) { an[i] = p0[i][ko]; if (MODE == 2) a1n[i] = p1[i][ko]; }
+    if (MODE == 1) mun = mean[ko];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      double x = a[i];
+      if (MODE == 1) x = x - mu;
+      if (MODE == 2) x = a1[i] - x;
+      mvn_dmma(acc[i][0], acc[i][1], x, b);
     }
+    b = bn; mu = mun;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) { a[i] = an[i]; if (MODE == 2) a1[i] = a1n[i]; }
   }
-  double accA[RT][4], accB[RT][4];
+}
+// r0 / r1: per row tile q (chain q >> 1, slots 8 (q & 1) ..), this lane's row (row l / 4 of the tile; the ZERO row where the
+// slot does not exist).  The active tiles of `tmask` are compacted: acc[i] belongs to tile qmap[i], i < popc(tmask).
+template <int MODE, bool GLOBAL>
+__device__ __forceinline__ void mvn_gemm(const double* __restrict__ pack, int d, int jt, int lane, unsigned tmask,
+                                         const double* const (&r0)[4], const double* const (&r1)[4],
+                                         const double* __restrict__ mean, double (&acc)[4][2], int (&qmap)[4]) {
+  const int kq = lane & 3;
+  const double* p0[4];
+  const double* p1[4];
+  unsigned rest = tmask;
 #pragma unroll
-  for (int r = 0; r < RT; ++r) { accA[r][0] = accA[r][1] = accA[r][2] = accA[r][3] = 0.0; accB[r][0] = accB[r][1] = accB[r][2] = accB[r][3] = 0.0; }
+  for (int i = 0; i < 4; ++i) {
+    acc[i][0] = 0.0; acc[i][1] = 0.0;
+    const int q = (__ffs(rest) - 1) & 3;                     // i-th set bit (3 past the count: never used)
+    rest &= rest - 1;
+    qmap[i] = q;
+    p0[i] = (q == 0) ? r0[0] : (q == 1) ? r0[1] : (q == 2) ? r0[2] : r0[3];
+    p1[i] = (q == 0) ? r1[0] : (q == 1) ? r1[1] : (q == 2) ? r1[2] : r1[3];
+  }
+  const int nk = min(2 * jt + 2, (d + 3) >> 2);
+  const double* bp = pack + (size_t)mvn_tile_base(jt) * 32 + lane;
 #ifdef UBM_MVN_TIMING
-  const long long tl0_ = clock64();
+  const long long tk0_ = clock64();
 #endif
-  {
-    // h = 0: all of gA, then the first segment [0, ks) of gB; h = 1: the second segment [ks, KB) of gB
-    const int n1 = (active && h == 0 && !middle) ? KA / 2 : 0;
-    const int n2 = !active ? 0 : (h == 0 ? ks / 2 : (KB - ks) / 2);
-    mvn_unit<RT, MODE>(pack, nPairs, gA, n1, gB, h ? ks : 0, n2, in, in2, aux, accA, accB);
+  switch (__popc(tmask)) {
+    case 1: mvn_kloop<MODE, GLOBAL, 1>(bp, nk, kq, p0, p1, mean, acc); break;
+    case 2: mvn_kloop<MODE, GLOBAL, 2>(bp, nk, kq, p0, p1, mean, acc); break;
+    case 3: mvn_kloop<MODE, GLOBAL, 3>(bp, nk, kq, p0, p1, mean, acc); break;
+    case 4: mvn_kloop<MODE, GLOBAL, 4>(bp, nk, kq, p0, p1, mean, acc); break;
+    default: break;
   }
 #ifdef UBM_MVN_TIMING
-  if (threadIdx.x == 0 && blockIdx.x == 0) g_mvn_tloop += clock64() - tl0_;
+  if (threadIdx.x == 0 && blockIdx.x == 0) { g_mvn_tk[0] += clock64() - tk0_; g_mvn_tk[1] += nk; g_mvn_tk[2] += (long long)nk * __popc(tmask); g_mvn_tk[3] += 1; }
 #endif
-#pragma unroll
-  for (int r = 0; r < RT; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const double lo = __shfl_xor_sync(0xffffffffu, accB[r][c], 1);
-      if (h == 1 && ks > 0) accB[r][c] = lo + accB[r][c];
-      out[r][c] = h ? accB[r][c] : accA[r][c];
-    }
-  g_out = h ? gB : gA;
-  has_out = active && !(h == 0 && middle);
 }
 
-template <bool TAPE, bool ZERO_MEAN>
-__global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, const RunParams P, const int R,
-                                                           const int acc_per_slot) {
+// per 4-column group sum of squares of a fragment pair, in the canonical order fma(v3,v3,fma(v2,v2,fma(v1,v1,fma(v0,v0,0)))):
+// lanes with even l % 4 hold columns 0,1 of the group, the next lane columns 2,3.  Returns the group sum on odd lanes.
+__device__ __forceinline__ double mvn_group_sq(double v0, double v1, int lane) {
+  const double lo = ubm_fma(v1, v1, ubm_fma(v0, v0, 0.0));
+  const double prev = __shfl_up_sync(0xffffffffu, lo, 1);
+  return ubm_fma(v1, v1, ubm_fma(v0, v0, prev));
+}
+
+// NH: number of test-function blocks accumulated per coordinate (1: identity or square, 2: both)
+template <bool TAPE, bool ZERO_MEAN, int NH>
+__global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, const RunParams P, const int R) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, T = MVN_T, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
-  const int d = M.d, DPS = M.DPS, nCG = M.nCG, nPairs = M.nPairs;
+  const int tid = threadIdx.x, T = MVN_T, lane = tid & 31, warp = tid >> 5;
+  const int d = M.d, DPS = M.DPS, nCG = M.nCG;
   MvnSmem sm;
   {
     double* p = reinterpret_cast<double*>(smem_raw);
     sm.packA = p; p += M.packLen; sm.packB = p; p += M.packLen; sm.packC = p; p += M.packLen;
     sm.MEAN = p; p += DPS;
     sm.X1 = p; p += R * DPS; sm.X2 = p; p += R * DPS; sm.XI = p; p += 2 * R * DPS; sm.V2 = p; p += R * DPS;
-    sm.ACC = p; p += R * acc_per_slot;
     sm.TG = p; p += 2 * R * 32;
     sm.ZERO = p; p += DPS;
     sm.LU = p; p += 8 * R;
@@ -382,22 +298,33 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
   MvnSlots& S = *sm.S;
   for (int i = tid; i < M.packLen; i += T) { sm.packA[i] = M.packA[i]; sm.packB[i] = M.packB[i]; sm.packC[i] = M.packC[i]; }
   for (int i = tid; i < DPS; i += T) sm.MEAN[i] = M.mean_pi[i];
-  for (int i = tid; i < 5 * R * DPS + R * acc_per_slot + 2 * R * 32 + DPS + 8 * R; i += T) sm.X1[i] = 0.0;
+  for (int i = tid; i < 5 * R * DPS + 2 * R * 32 + DPS + 8 * R; i += T) sm.X1[i] = 0.0;
   if (tid < MVN_MAXR) {
     S.rep[tid] = -1; S.phase[tid] = SL_IDLE; S.time[tid] = 0; S.tau[tid] = 0; S.met[tid] = 0;
     S.iu[tid] = 0; S.in[tid] = 0; S.pu[tid] = 0; S.bad[tid] = 0; S.ident[tid] = 0;
   }
-  if (tid == 0) { S.exhausted = 0; S.nA = S.nB = S.nI = S.nC = 0; }
+  if (tid == 0) S.exhausted = 0;
   __syncthreads();
 
-  const int dimh = (P.h_kind == UBM_H_BOTH) ? 2 * d : d;
+  const int dimh = NH * d;
   const double denom = (double)(P.m - P.k + 1);
   const unsigned FULL = 0xffffffffu;
+  const int nbins = (P.mode == MODE_ESTIMATOR && P.nbreaks >= 2) ? P.nbreaks - 1 : 0;
+  double bin_b0 = 0.0, bin_iw = 0.0;
+  if (nbins) { bin_b0 = P.breaks[0]; bin_iw = (double)nbins / (P.breaks[nbins] - P.breaks[0]); }
   int cur = 0;
-  const int RB = min(2 * MVN_MAXR, MVN_RT * ((MVN_GT / 2) / nPairs));   // rows per GEMM batch: one half-unit per consumer thread
+  // estimator sums of this warp's slot (slot s = warp): coordinate j = lane + 32 i, test-function block hh
+  double am[NH][4], ac[NH][4];
+#pragma unroll
+  for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { am[hh][i] = 0.0; ac[hh][i] = 0.0; }
+  // this lane's rows of the four static row tiles (chain q >> 1, slots 8 (q & 1) + lane / 4), per input array
+  const int myrow[2] = {lane >> 2, 8 + (lane >> 2)};
+  const int kq = lane & 3;
 
 #ifdef UBM_MVN_TIMING
-  long long tacc[5] = {0, 0, 0, 0, 0}, tsteps = 0;
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tsteps = 0;
 #define TMARK(i) do { long long now_ = clock64(); tacc[i] += now_ - tprev; tprev = now_; } while (0)
 #else
 #define TMARK(i) do { } while (0)
@@ -409,12 +336,12 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
     double* XIc = sm.XI + cur * R * DPS;          // this step's chain-1 rows (normals -> proposals)
     double* XIn = sm.XI + (cur ^ 1) * R * DPS;    // filled by the producers for the next step ...
     const double* XIp = XIn;                      // ... and, until barrier 1, still holding the proposals of the step just computed
-    // ================================================================ per-slot section (all 8 warps, one warp per slot)
+    // ================================================================ per-slot section (warp s owns slot s)
     // finishes the step just computed (densities -> accept/reject -> state/estimator update) and runs the slot state
     // machine (finish / write-out / fetch the next replicate).  No random-number work: uniforms come from the ring.
     int my_active = 0;
-    // one slot per warp; slots beyond the warp count go to the producer warps (they are not on the critical path)
-    for (int s = warp; s < R; s = (s < nwarp && warp >= MVN_CW) ? nwarp + warp - MVN_CW : R) {
+    if (warp < R) {
+      const int s = warp;
       int ph = S.phase[s];
       long long rep = S.rep[s];
       long long time = S.time[s];
@@ -427,7 +354,7 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
         const int ident = S.ident[s];
         const double pp2 = (ph == SL_COUPLED && ident) ? pp1 : (-0.5 * ss2 + M.cst);
         int a1 = 0, a2 = 0, add_mcmc = 0, add_corr = 0;
-        double wgt = 0.0;
+        long long wgt_i = 0;
         if (ph == SL_INIT) {
           a1 = 1; a2 = 1;
           if (lane == 0) { S.pdf1[s] = pp1; S.pdf2[s] = pp2; }
@@ -453,41 +380,57 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
           // what the estimator adds after this step (R/unbiasedestimator.R:66, :70-72, :80, :90, :93-95)
           add_mcmc = (time <= P.lag) ? (time >= P.k) : (P.k <= time && time <= P.m);
           add_corr = ((time >= P.k + P.lag) && (ph == SL_COUPLED || time == P.lag)) ? 1 : 0;
-          if (add_corr && P.mode == MODE_ESTIMATOR) wgt = (double)corr_weight(time, P.k, P.m, P.lag);
+          if (add_corr && P.mode == MODE_ESTIMATOR) wgt_i = corr_weight(time, P.k, P.m, P.lag);
         }
+        const double wgt = (double)wgt_i;
         // ---- state update, estimator sums, trajectories
         const bool coupled_step = (ph == SL_COUPLED);
-        for (int j = lane; j < d; j += 32) {
-          const int o = s * DPS + j;
-          if (a1) sm.X1[o] = XIp[o];
-          if (a2) sm.X2[o] = (coupled_step && ident) ? XIp[o] : sm.V2[o];
-          const double x1 = sm.X1[o];
-          const double x2 = sm.X2[o];
-          if (P.mode == MODE_ESTIMATOR) {
-            double* a = sm.ACC + s * acc_per_slot;
-            const int nh = (P.h_kind == UBM_H_BOTH) ? 2 : 1;
-            for (int hh = 0; hh < nh; ++hh) {
-              const bool sq = (P.h_kind == UBM_H_SQUARE) || hh == 1;
-              const int e = hh * d + j;
-              const double h1 = sq ? x1 * x1 : x1;
-              if (ph == SL_INIT) {
-                a[e] = (P.k == 0) ? h1 : 0.0;                        // R/unbiasedestimator.R:55-59
-                a[dimh + e] = 0.0;
-              } else {
-                if (add_mcmc) a[e] = a[e] + h1;
-                if (add_corr) {
-                  const double h2 = sq ? x2 * x2 : x2;
-                  a[dimh + e] = a[dimh + e] + wgt * (h1 - h2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int j = lane + 32 * i;
+          if (j < d) {
+            const int o = s * DPS + j;
+            if (a1) sm.X1[o] = XIp[o];
+            if (a2) sm.X2[o] = (coupled_step && ident) ? XIp[o] : sm.V2[o];
+            const double x1 = sm.X1[o];
+            const double x2 = sm.X2[o];
+            if (P.mode == MODE_ESTIMATOR) {
+#pragma unroll
+              for (int hh = 0; hh < NH; ++hh) {
+                const bool sq = (P.h_kind == UBM_H_SQUARE) || hh == 1;
+                const double h1 = sq ? x1 * x1 : x1;
+                if (ph == SL_INIT) {
+                  am[hh][i] = (P.k == 0) ? h1 : 0.0;                        // R/unbiasedestimator.R:55-59
+                  ac[hh][i] = 0.0;
+                } else {
+                  if (add_mcmc) am[hh][i] = am[hh][i] + h1;
+                  if (add_corr) {
+                    const double h2 = sq ? x2 * x2 : x2;
+                    ac[hh][i] = ac[hh][i] + wgt * (h1 - h2);
+                  }
                 }
               }
-            }
-          } else if (P.mode == MODE_CHAINS) {
-            double* S1 = P.samples1 + (rep * P.stride) * d;
-            double* S2 = P.samples2 + (rep * P.stride) * d;
-            if (ph == SL_INIT) { S1[j] = x1; S2[j] = x2; }
-            else {
-              S1[time * d + j] = x1;
-              if (time > P.lag) S2[(time - P.lag) * d + j] = (coupled_step ? x2 : x1);   // R/coupled_chains.R:60-62,77-78
+              if (nbins && j == P.component) {      // estimator_bin_ numerators on the fly (src/estimator_bin.cpp:15-38)
+                long long* bn = P.bin_num + rep * nbins;
+                if ((ph == SL_INIT) ? (P.k == 0) : (add_mcmc != 0)) {
+                  const int b = bin_of(x1, P.breaks, P.nbreaks, bin_b0, bin_iw);
+                  if (b >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(bn + b), 1ull);
+                }
+                if (ph != SL_INIT && add_corr) {
+                  const int b1 = bin_of(x1, P.breaks, P.nbreaks, bin_b0, bin_iw);
+                  const int b2 = bin_of(x2, P.breaks, P.nbreaks, bin_b0, bin_iw);
+                  if (b1 >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(bn + b1), (unsigned long long)wgt_i);
+                  if (b2 >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(bn + b2), (unsigned long long)(-wgt_i));
+                }
+              }
+            } else if (P.mode == MODE_CHAINS) {
+              double* S1 = P.samples1 + (rep * P.stride) * d;
+              double* S2 = P.samples2 + (rep * P.stride) * d;
+              if (ph == SL_INIT) { S1[j] = x1; S2[j] = x2; }
+              else {
+                S1[time * d + j] = x1;
+                if (time > P.lag) S2[(time - P.lag) * d + j] = (coupled_step ? x2 : x1);   // R/coupled_chains.R:60-62,77-78
+              }
             }
           }
         }
@@ -526,17 +469,21 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
             if (tape_bad) atomicExch(P.status, UBM_ERR_TAPE);
           }
           if (P.mode == MODE_ESTIMATOR) {
-            const double* a = sm.ACC + s * acc_per_slot;
-            const int nh = (P.h_kind == UBM_H_BOTH) ? 2 : 1;
-            for (int j = lane; j < d; j += 32)
-              for (int hh = 0; hh < nh; ++hh) {
-                const int e = hh * d + j;
-                const double mc = a[e], co = a[dimh + e];
-                const double ue = mc + co;
-                P.uest[rep * dimh + e] = ue / denom;
-                if (P.mcmc) P.mcmc[rep * dimh + e] = mc / denom;
-                if (P.corr) P.corr[rep * dimh + e] = co / denom;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = lane + 32 * i;
+              if (j < d) {
+#pragma unroll
+                for (int hh = 0; hh < NH; ++hh) {
+                  const int e = hh * d + j;
+                  const double mc = am[hh][i], co = ac[hh][i];
+                  const double ue = mc + co;
+                  P.uest[rep * dimh + e] = ue / denom;
+                  if (P.mcmc) P.mcmc[rep * dimh + e] = mc / denom;
+                  if (P.corr) P.corr[rep * dimh + e] = co / denom;
+                }
               }
+            }
           }
           ph = SL_IDLE;
         } else if (time < P.lag) ph = SL_SINGLE;
@@ -569,51 +516,47 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
 
     if (warp < MVN_CW) {
       // ================================================================ CONSUMERS (warps 0-7)
-      if (warp == 0) {      // row tables from ballots
+      const int cw = warp;
+      // slot masks of this step (every consumer warp computes them: no table, no barrier)
+      unsigned mA, mS, mI;
+      {
         const int ph = (lane < R) ? S.phase[lane] : SL_IDLE;
-        const unsigned mA = __ballot_sync(FULL, ph == SL_COUPLED), mS = __ballot_sync(FULL, ph == SL_SINGLE);
-        const unsigned mI = __ballot_sync(FULL, ph == SL_INIT);
-        const unsigned below = (1u << lane) - 1u;
-        if (ph == SL_COUPLED) S.rowsA[__popc(mA & below)] = 2 * lane;
-        if (ph == SL_INIT) { const int q = 2 * __popc(mI & below); S.rowsI[q] = 2 * lane; S.rowsI[q + 1] = 2 * lane + 1; }
-        if (lane == 0) { S.nA = __popc(mA); S.nI = 2 * __popc(mI); }
-        if (mA == 0) {      // no coupled slot: the B / C lists are known already
-          const unsigned mBS = mS;
-          if (ph == SL_SINGLE) { const int q = __popc(mBS & below); S.rowsB[q] = 2 * lane; S.rowsC[q] = 2 * lane; }
-          const int nb = __popc(mBS);
-          if (ph == SL_INIT) { const int q = nb + 2 * __popc(mI & below); S.rowsC[q] = 2 * lane; S.rowsC[q + 1] = 2 * lane + 1; }
-          if (lane == 0) { S.nB = nb; S.nC = nb + 2 * __popc(mI); }
-        }
+        mA = __ballot_sync(FULL, ph == SL_COUPLED); mS = __ballot_sync(FULL, ph == SL_SINGLE); mI = __ballot_sync(FULL, ph == SL_INIT);
       }
-      consumer_bar();
-      const int nA = S.nA;
+      const int sl0 = myrow[0], sl1 = myrow[1];                 // the two slots this lane's fragment rows belong to
+      const bool ex0 = sl0 < R, ex1 = sl1 < R;
+      double acc[4][2];
+      int qmap[4];
+      unsigned mD = 0;       // coupled slots whose proposals differ (chain-2 rows of phases B and C)
       // ---------------------------------------------------------------- phase A: z = -((x2 - x1)^T Cinv_prop) -> V2, |z|^2
-      if (nA > 0) {
-        for (int r0 = 0; r0 < nA; r0 += RB) {
-          int code[MVN_RT], g;
-          bool has;
-          double acc[MVN_RT][4];
-          mvn_phase_compute<MVN_RT, 2>(sm.packA, sm, XIc, S.rowsA + r0, min(RB, nA - r0), DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
-          if (has) {
+      if (mA) {
+        const unsigned tm = ((mA & 0xffu) ? 1u : 0u) | ((mA >> 8) ? 2u : 0u);
+        const double* const r0[4] = {ex0 ? sm.X1 + sl0 * DPS : sm.ZERO, ex1 ? sm.X1 + sl1 * DPS : sm.ZERO, sm.ZERO, sm.ZERO};
+        const double* const r1[4] = {ex0 ? sm.X2 + sl0 * DPS : sm.ZERO, ex1 ? sm.X2 + sl1 * DPS : sm.ZERO, sm.ZERO, sm.ZERO};
+        for (int jb = 0; jb < MVN_JMAX; ++jb) {
+          const int jt = M.jobs[cw][jb];
+          if (jt == 255) continue;
+          mvn_gemm<2, false>(sm.packA, d, jt, lane, tm, r0, r1, nullptr, acc, qmap);
+          const int n0 = 8 * jt + 2 * kq, g = 2 * jt + (kq >> 1);
+          const int ntl = __popc(tm);
 #pragma unroll
-            for (int r = 0; r < MVN_RT; ++r) {
-              if (code[r] < 0) continue;
-              const int s = code[r] >> 1;
-              double t = 0.0;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const double z = -acc[r][c];                           // :198
-                sm.V2[s * DPS + 4 * g + c] = z;
-                t = ubm_fma(z, z, t);
+          for (int i = 0; i < 2; ++i) {
+            if (i < ntl) {
+              const int q = qmap[i];
+              const int s = q ? sl1 : sl0;
+              const double z0 = -acc[i][0], z1 = -acc[i][1];        // :198
+              const double t = mvn_group_sq(z0, z1, lane);
+              if ((mA >> s) & 1u) {
+                *reinterpret_cast<double2*>(sm.V2 + s * DPS + n0) = make_double2(z0, z1);
+                if (kq & 1) sm.TG[(2 * s) * 32 + g] = t;
               }
-              sm.TG[(2 * s) * 32 + g] = t;
             }
           }
         }
         consumer_bar();
         // -------------------------------------------------------------- coupling algebra, one warp per coupled slot
-        for (int i = warp; i < nA; i += MVN_CW) {
-          const int s = S.rowsA[i] >> 1;
+        for (int s = cw; s < R; s += MVN_CW) {
+          if (!((mA >> s) & 1u)) continue;
           const double nz = sqrt(warp_butterfly(sm.TG[(2 * s) * 32 + lane]));   // :199
           double z[4] = {0, 0, 0, 0}, e[4] = {0, 0, 0, 0};
           double t = 0.0;
@@ -645,68 +588,76 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
           }
         }
         consumer_bar();
-        if (warp == 0) {      // B / C row lists: chain-1 rows of all stepping slots, chain-2 rows where proposals differ
-          const int ph = (lane < R) ? S.phase[lane] : SL_IDLE;
-          const int differ = (ph == SL_COUPLED) && !S.ident[lane < R ? lane : 0];
-          const unsigned m1 = __ballot_sync(FULL, ph == SL_COUPLED || ph == SL_SINGLE);
-          const unsigned m2 = __ballot_sync(FULL, differ);
-          const unsigned mI = __ballot_sync(FULL, ph == SL_INIT);
-          const unsigned below = (1u << lane) - 1u;
-          const int n1 = __popc(m1), n2 = __popc(m2);
-          if (ph == SL_COUPLED || ph == SL_SINGLE) { const int q = __popc(m1 & below); S.rowsB[q] = 2 * lane; S.rowsC[q] = 2 * lane; }
-          if (differ) { const int q = n1 + __popc(m2 & below); S.rowsB[q] = 2 * lane + 1; S.rowsC[q] = 2 * lane + 1; }
-          if (ph == SL_INIT) { const int q = n1 + n2 + 2 * __popc(mI & below); S.rowsC[q] = 2 * lane; S.rowsC[q + 1] = 2 * lane + 1; }
-          if (lane == 0) { S.nB = n1 + n2; S.nC = n1 + n2 + 2 * __popc(mI); }
-        }
-        consumer_bar();
+        mD = __ballot_sync(FULL, lane < R && ((mA >> lane) & 1u) && !S.ident[lane < R ? lane : 0]);
       }
       TMARK(1);
       // ---------------------------------------------------------------- phase B: proposals = x + in^T C_prop (in place)
-      // and, for freshly fetched slots, x0 = init_mean + in^T init_chol (matrix read from global memory / L2)
+      // and, for freshly fetched slots, x0 = init_mean + in^T init_chol (matrix read from global memory / L2).
+      // Outputs overwrite their inputs: both K loops of every warp first, then a barrier, then the writes.
+      const double* const rc[4] = {ex0 ? XIc + sl0 * DPS : sm.ZERO, ex1 ? XIc + sl1 * DPS : sm.ZERO,
+                                   ex0 ? sm.V2 + sl0 * DPS : sm.ZERO, ex1 ? sm.V2 + sl1 * DPS : sm.ZERO};
       for (int pass = 0; pass < 2; ++pass) {
-        const int ntot = pass ? S.nI : S.nB;
-        const int* rows_all = pass ? S.rowsI : S.rowsB;
-        for (int r0 = 0; r0 < ntot; r0 += RB) {     // uniform over the consumer group; one batch unless 2R rows are live
-          const int nrows = min(RB, ntot - r0);
-          int code[MVN_RT], g;
-          bool has;
-          double acc[MVN_RT][4];
-          // two call sites so that the matrix loads are LDS (shared) resp. LDG (global), not generic loads
-          if (pass == 0) mvn_phase_compute<MVN_RT, 0>(sm.packB, sm, XIc, rows_all + r0, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
-          else mvn_phase_compute<MVN_RT, 0>(M.packI, sm, XIc, rows_all + r0, nrows, DPS, nCG, nPairs, nullptr, tid, code, g, has, acc);
-          consumer_bar();   // every read of this batch's input rows is done: overwrite them with the outputs
-          if (has) {
+        const unsigned m1 = pass ? mI : (mA | mS), m2 = pass ? mI : mD;      // chain-1 rows, chain-2 rows
+        if (!(m1 | m2)) continue;                                            // uniform over the consumer group
+        const unsigned tm = ((m1 & 0xffu) ? 1u : 0u) | ((m1 >> 8) ? 2u : 0u) | ((m2 & 0xffu) ? 4u : 0u) | ((m2 >> 8) ? 8u : 0u);
+        double accB[4][2];
+        const int jt0 = M.jobs[cw][0], jt1 = M.jobs[cw][1];
+        // two call sites each so that the matrix loads are LDS (shared) resp. LDG (global), not generic loads
+        if (jt0 != 255) {
+          if (pass == 0) mvn_gemm<0, false>(sm.packB, d, jt0, lane, tm, rc, rc, nullptr, acc, qmap);
+          else mvn_gemm<0, true>(M.packI, d, jt0, lane, tm, rc, rc, nullptr, acc, qmap);
+        }
+        if (jt1 != 255) {
+          if (pass == 0) mvn_gemm<0, false>(sm.packB, d, jt1, lane, tm, rc, rc, nullptr, accB, qmap);
+          else mvn_gemm<0, true>(M.packI, d, jt1, lane, tm, rc, rc, nullptr, accB, qmap);
+        }
+        consumer_bar();   // every read of the input rows is done: overwrite them with the outputs
+        const int ntl = __popc(tm);
 #pragma unroll
-            for (int r = 0; r < MVN_RT; ++r) {
-              if (code[r] < 0) continue;
-              const int s = code[r] >> 1, which = code[r] & 1;
-              const double* base = pass ? (M.init_mean + 4 * g) : ((which ? sm.X2 : sm.X1) + s * DPS + 4 * g);
-              double* outp = (which ? sm.V2 : XIc) + s * DPS + 4 * g;
+        for (int jb = 0; jb < MVN_JMAX; ++jb) {
+          const int jt = jb ? jt1 : jt0;
+          if (jt != 255) {
+            const int n0 = 8 * jt + 2 * kq;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) outp[c] = (4 * g + c < d) ? (base[c] + acc[r][c]) : 0.0;   // :40-44, :224-225
+            for (int i = 0; i < 4; ++i) {
+              if (i < ntl) {
+                const int q = qmap[i];
+                const int s = (q & 1) ? sl1 : sl0, which = q >> 1;
+                if (((which ? m2 : m1) >> s) & 1u) {
+                  const double* base = pass ? (M.init_mean + n0) : ((which ? sm.X2 : sm.X1) + s * DPS + n0);
+                  const double v0 = jb ? accB[i][0] : acc[i][0], v1 = jb ? accB[i][1] : acc[i][1];
+                  double2 o;
+                  o.x = (n0 < d) ? (base[0] + v0) : 0.0;          // :40-44, :224-225
+                  o.y = (n0 + 1 < d) ? (base[1] + v1) : 0.0;
+                  *reinterpret_cast<double2*>((which ? sm.V2 : XIc) + s * DPS + n0) = o;
+                }
+              }
             }
           }
         }
+        if (pass == 0 && mI) consumer_bar();   // the init pass must not start before every write of this pass has landed in ITS rows' neighbours' reads
       }
       consumer_bar();
       TMARK(2);
       // ---------------------------------------------------------------- phase C: w = Cinv_pi^T (prop - mean), |w|^2
       {
-        const int ntot = S.nC;
-        for (int r0 = 0; r0 < ntot; r0 += RB) {
-          const int nrows = min(RB, ntot - r0);
-          int code[MVN_RT], g;
-          bool has;
-          double acc[MVN_RT][4];
-          mvn_phase_compute<MVN_RT, ZERO_MEAN ? 0 : 1>(sm.packC, sm, XIc, S.rowsC + r0, nrows, DPS, nCG, nPairs, sm.MEAN, tid, code, g, has, acc);
-          if (has) {
+        const unsigned m1 = mA | mS | mI, m2 = mD | mI;
+        const unsigned tm = ((m1 & 0xffu) ? 1u : 0u) | ((m1 >> 8) ? 2u : 0u) | ((m2 & 0xffu) ? 4u : 0u) | ((m2 >> 8) ? 8u : 0u);
+        for (int jb = 0; jb < MVN_JMAX; ++jb) {
+          const int jt = M.jobs[cw][jb];
+          if (jt == 255) continue;
+          TMARK(5);
+          mvn_gemm<ZERO_MEAN ? 0 : 1, false>(sm.packC, d, jt, lane, tm, rc, rc, sm.MEAN, acc, qmap);
+          TMARK(6);
+          const int g = 2 * jt + (kq >> 1);
+          const int ntl = __popc(tm);
 #pragma unroll
-            for (int r = 0; r < MVN_RT; ++r) {
-              if (code[r] < 0) continue;
-              double t = 0.0;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) t = ubm_fma(acc[r][c], acc[r][c], t);
-              sm.TG[code[r] * 32 + g] = t;
+          for (int i = 0; i < 4; ++i) {
+            if (i < ntl) {
+              const int q = qmap[i];
+              const int s = (q & 1) ? sl1 : sl0, which = q >> 1;
+              const double t = mvn_group_sq(acc[i][0], acc[i][1], lane);
+              if ((((which ? m2 : m1) >> s) & 1u) && (kq & 1)) sm.TG[(2 * s + which) * 32 + g] = t;
             }
           }
         }
@@ -748,9 +699,10 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
   }
 #ifdef UBM_MVN_TIMING
   if (tid == 0 && blockIdx.x == 0)
-    printf("mvn timing (cycles/step, block 0, thread 0): steps %lld slot %.0f A+coupling %.0f B %.0f C %.0f wait-for-producers %.0f | GEMM loops %.0f\n", tsteps,
+    printf("mvn timing (cycles/step, block 0, thread 0): steps %lld slot %.0f A+coupling %.0f B %.0f C %.0f wait-for-producers %.0f | K loops of warp 0: %.0f cycles/step, %.1f k-steps/step, %.1f DMMA/step, %.1f calls/step\n", tsteps,
            (double)tacc[0] / tsteps, (double)tacc[1] / tsteps, (double)tacc[2] / tsteps, (double)tacc[3] / tsteps,
-           (double)tacc[4] / tsteps, (double)g_mvn_tloop / tsteps);
+           (double)tacc[4] / tsteps, (double)g_mvn_tk[0] / tsteps, (double)g_mvn_tk[1] / tsteps, (double)g_mvn_tk[2] / tsteps, (double)g_mvn_tk[3] / tsteps);
+  if (tid == 0 && blockIdx.x == 0) printf("   phase C split: before gemm %.0f, gemm call %.0f, after (epilogue + loop) %.0f\n", (double)tacc[5] / tsteps, (double)tacc[6] / tsteps, (double)tacc[3] / tsteps);
 #endif
 }
 
@@ -758,22 +710,29 @@ template <class Buf>
 inline int mvn_launch(const MvnDevice& M, const RunParams& P, bool tape, int nsm, cudaStream_t st, Buf& scratch,
                       int64_t* launches, std::string* err) {
   (void)scratch;
-  if (P.nbreaks >= 2) { *err = "mvn: histogram bins are not available for this model yet"; return UBM_ERR_UNSUPPORTED; }
   const size_t budget = 227 * 1024;
-  const int dimh = (P.h_kind == UBM_H_BOTH) ? 2 * M.d : M.d;
-  const int acc_per_slot = (P.mode == MODE_ESTIMATOR) ? 2 * dimh : 0;
+  const int nh = (P.mode == MODE_ESTIMATOR && P.h_kind == UBM_H_BOTH) ? 2 : 1;
   int R = MVN_MAXR;
-  while (R > 1 && mvn_smem_bytes(M.packLen, M.DPS, R, acc_per_slot) > budget) --R;
-  size_t smem = mvn_smem_bytes(M.packLen, M.DPS, R, acc_per_slot);
-  if (smem > budget || M.nPairs > MVN_GT / 2) { *err = "mvn: d too large for shared memory"; return UBM_ERR_UNSUPPORTED; }
+  while (R > 1 && mvn_smem_bytes(M.packLen, M.DPS, R) > budget) --R;
+  size_t smem = mvn_smem_bytes(M.packLen, M.DPS, R);
+  if (smem > budget) { *err = "mvn: d too large for shared memory"; return UBM_ERR_UNSUPPORTED; }
   int64_t need = (P.nrep + R - 1) / R;
   int grid = (int)std::min<int64_t>(nsm, need);
-  void (*kern)(const MvnDevice, const RunParams, const int, const int);
-  if (tape) kern = M.zero_mean ? mvn_driver_kernel<true, true> : mvn_driver_kernel<true, false>;
-  else kern = M.zero_mean ? mvn_driver_kernel<false, true> : mvn_driver_kernel<false, false>;
+  void (*kern)(const MvnDevice, const RunParams, const int);
+  const int variant = (tape ? 4 : 0) | (M.zero_mean ? 2 : 0) | (nh == 2 ? 1 : 0);
+  switch (variant) {
+    case 0: kern = mvn_driver_kernel<false, false, 1>; break;
+    case 1: kern = mvn_driver_kernel<false, false, 2>; break;
+    case 2: kern = mvn_driver_kernel<false, true, 1>; break;
+    case 3: kern = mvn_driver_kernel<false, true, 2>; break;
+    case 4: kern = mvn_driver_kernel<true, false, 1>; break;
+    case 5: kern = mvn_driver_kernel<true, false, 2>; break;
+    case 6: kern = mvn_driver_kernel<true, true, 1>; break;
+    default: kern = mvn_driver_kernel<true, true, 2>; break;
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { *err = std::string("mvn: smem attribute: ") + cudaGetErrorString(e); return UBM_ERR_CUDA; }
-  kern<<<grid, MVN_T, smem, st>>>(M, P, R, acc_per_slot);
+  kern<<<grid, MVN_T, smem, st>>>(M, P, R);
   *launches += 1;
   return UBM_OK;
 }

@@ -49,17 +49,13 @@ __global__ void prim_scalar_coupling_kernel(const RunParams P, int mode, double 
   if (D.bad) atomicExch(P.status, UBM_ERR_TAPE);
 }
 
-// y_j = sum_{i <= j} v_i U[i, j], U column-major upper triangular, in the engine's canonical order (sequential fma,
-// long columns cut once at K_g - half; see ubm_mvn.cuh / oracle_models.hpp: vec_times_upper)
+// y_j = sum_{i <= j} v_i U[i, j], U column-major upper triangular: one fma chain, sequential in i (the engine's order;
+// see ubm_mvn.cuh / oracle_models.hpp: vec_times_upper)
 __device__ inline void prim_vec_times_upper(const double* v, const double* __restrict__ U, int d, double* out) {
-  const int nCG = (d + 3) / 4, half = 4 * ((nCG + 1) / 2) + 2;
   for (int j = 0; j < d; ++j) {
-    const int Kg = 4 * (j / 4) + 4;
-    const int ks = (Kg > half) ? Kg - half : 0;
-    double lo = 0.0, hi = 0.0;
-    for (int i = 0; i < ks && i <= j; ++i) lo = ubm_fma(v[i], U[(size_t)j * d + i], lo);
-    for (int i = ks; i <= j; ++i) hi = ubm_fma(v[i], U[(size_t)j * d + i], hi);
-    out[j] = (ks > 0) ? (lo + hi) : hi;
+    double acc = 0.0;
+    for (int i = 0; i <= j; ++i) acc = ubm_fma(v[i], U[(size_t)j * d + i], acc);
+    out[j] = acc;
   }
 }
 __device__ inline double prim_sum_g4(const double* a, const double* b, int d) {   // canonical reduction order

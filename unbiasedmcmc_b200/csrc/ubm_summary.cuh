@@ -60,4 +60,26 @@ __global__ void __launch_bounds__(1024) summary_kernel(const SummaryArgs A) {
   if (q == 0) A.summary[col] = cur[0];
 }
 
+// estimator_bin_ values of every replicate and their sums over the uncensored replicates, from the integer numerators the
+// driver kernels accumulated with global reductions (P.bin_num).  One block per bin; integer sums: order-independent.
+__global__ void __launch_bounds__(256) bins_finalize_kernel(int64_t nrep, int nbins, const double* __restrict__ tau,
+                                                            const long long* __restrict__ bin_num, double denom,
+                                                            double* __restrict__ bins_out, long long* __restrict__ bin_acc) {
+  __shared__ long long s1[256], s2[256];
+  const int b = blockIdx.x, q = threadIdx.x;
+  long long c1 = 0, c2 = 0;
+  for (int64_t r = q; r < nrep; r += 256) {
+    const long long c = bin_num[r * nbins + b];
+    if (bins_out) bins_out[r * nbins + b] = (double)c / denom;
+    if (isfinite(tau[r])) { c1 += c; c2 += c * c; }
+  }
+  s1[q] = c1; s2[q] = c2;
+  __syncthreads();
+  for (int off = 128; off >= 1; off >>= 1) {
+    if (q < off) { s1[q] += s1[q + off]; s2[q] += s2[q + off]; }
+    __syncthreads();
+  }
+  if (q == 0) { bin_acc[b] = s1[0]; bin_acc[nbins + b] = s2[0]; }
+}
+
 }  // namespace ubm
