@@ -1,7 +1,9 @@
 """Regenerates tests/golden/oracle_r01.json: small outputs of the oracle under the engine's numerics contract, stored as
 hex floats.  They pin OUR canonical arithmetic (Philox streams, summation orders, Cholesky variants) against accidental
-drift between rounds; they do NOT pin parity with the R reference (none can be produced here: no R, no reference tests
-— DESIGN.md section 2).  Run from the repo root:  python tests/golden/make_golden.py"""
+drift between rounds (parity with the reference itself is pinned elsewhere: tests/test_r_stream.py against R's printed
+README output, tests/test_ref_parity.py against the reference's compiled C++).  Regenerated in round 2 for the C2 entry: the
+column sums of the triangular products are now one fma chain in k order (what a chain of DMMAs computes), without the
+round-1 cut of the long columns.  Run from the repo root:  python tests/golden/make_golden.py"""
 import json
 import os
 import sys

@@ -1,6 +1,6 @@
 """Golden regression vectors (tests/golden/oracle_r01.json, made by tests/golden/make_golden.py from the oracle): the
 oracle (CPU) and the CUDA engine (GPU) must both reproduce them bit for bit.  They pin the engine's own canonical
-arithmetic between rounds — not parity with the R reference, which cannot run here."""
+arithmetic between rounds (parity with the reference is pinned by tests/test_r_stream.py and tests/test_ref_parity.py)."""
 import importlib.util
 import json
 import os
