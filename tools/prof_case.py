@@ -28,4 +28,9 @@ elif which == "c1":
     nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 18
     res = eng.sample_unbiasedestimator(cases.c1_model(), R.Draws(seed=1), bins=cases.c1_bins(), k=500, m=2000, lag=500,
                                        nrep=nrep, want_bins=False, per_replicate=False)
-print(which, "ok", res["meetingtime"][:4] if res.get("meetingtime") is not None else res["summary"][:6])
+if which != "c5":
+    print(which, "ok", res["meetingtime"][:4] if res.get("meetingtime") is not None else res["summary"][:6])
+if which == "c5":
+    nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 16
+    res = eng.sample_unbiasedestimator(cases.c5_model(), R.Draws(seed=1), k=1500, m=3000, lag=1, nrep=nrep, want_bins=False)
+    print("c5 ok", res["meetingtime"][:4])
