@@ -61,6 +61,9 @@ struct Draws {
     if ((i >> 2) != cbu) { cbu = i >> 2; bu = ubm_stream_block(seed, rep, UBM_STREAM_U, cbu); }
     return ubm_u01_32(bu.w[i & 3]);
   }
+  // Philox streams only: skip to the next block boundary of the U stream (the Ising sweeps start on one, so that a
+  // row's 32 uniforms are 8 whole blocks — include/ubm_numerics.h); tapes and the R stream are dense
+  void align_u4() { if (mode == UBM_DRAWS_PHILOX) iu = (iu + 3ull) & ~3ull; }
   double n() {
     uint64_t i = in++;
     if (mode == ORC_DRAWS_RSTREAM) { double v = rs->norm_rand(); if (rn && (int64_t)i < ln) rn[i] = v; return v; }

@@ -101,6 +101,7 @@ struct IsingModel {
         if (ubm_log(u) < logprob) swap_lattices(s, c);
       }
     } else {
+      D.align_u4();
       for (int c = 0; c < N; ++c) sweep(s, c, D);
     }
     refresh_sums(s);
@@ -118,6 +119,7 @@ struct IsingModel {
         if (logu < lp2) swap_lattices(s2, c);
       }
     } else {
+      D.align_u4();
       for (int c = 0; c < N; ++c) coupled_sweep(s1, s2, c, D);
     }
     refresh_sums(s1);

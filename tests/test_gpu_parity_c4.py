@@ -1,4 +1,5 @@
-"""GPU parity, C4 (Ising parallel tempering): CUDA wavefront sweeps vs the oracle's sequential scan, bit-exact."""
+"""GPU parity, C4 (Ising parallel tempering): the CUDA row-at-a-time sweeps (carry-chain scan, one lane per lattice
+pair) vs the oracle's site-by-site sequential scan, bit-exact."""
 import numpy as np
 import pytest
 
@@ -57,4 +58,48 @@ def test_c4_replay_tape(engine, oracle):
     draws = R.Draws(tape_u=rng.uniform(size=(nrep, 2 * 2 * 1024 + (steps + 2) * (1 + 2 * 1024))))
     g = engine.sample_unbiasedestimator(mdl, draws, k=2, m=10, lag=1, max_iterations=steps, nrep=nrep)
     c = oracle.sample_unbiasedestimator(mdl, draws, k=2, m=10, lag=1, max_iterations=steps, nrep=nrep)
+    assert_same(g, c, KEYS)
+
+
+@pytest.mark.parametrize("nchains,nrep", [(12, 7), (32, 3), (5, 13), (2, 33)])
+def test_c4_ragged_groups(engine, oracle, nchains, nrep):
+    """Ladders that do not divide the warp (idle lanes), a full-warp ladder, replicate counts that leave the last group
+    of a warp part empty."""
+    mdl = cases.c4_model(nchains, 0.15, 0.25, 0.4)
+    kw = dict(k=3, m=25, lag=2, nrep=nrep, max_iterations=60)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=21), **kw)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=21), nthreads=8, **kw)
+    assert_same(g, c, KEYS)
+
+
+def test_c4_negative_and_extreme_betas(engine, oracle):
+    """Antiferromagnetic temperatures (acceptance thresholds decrease with the neighbour count: the serial recurrence
+    instead of the carry chain) and inverse temperatures so large that probabilities round to 0 / 1 in 32 bits."""
+    for betas in ([-0.3, -0.1, 0.2], [0.0, 3.0, 6.0]):
+        mdl = R.IsingPT(np.array(betas), 0.1)
+        kw = dict(k=2, m=20, lag=1, nrep=9, max_iterations=40)
+        g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=3), **kw)
+        c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=3), nthreads=8, **kw)
+        assert_same(g, c, KEYS)
+
+
+def test_c4_bins_on_the_fly(engine, oracle):
+    """histogram of one temperature's natural statistic (estimator_bin_, src/estimator_bin.cpp:15-38) inside the kernel"""
+    mdl = cases.c4_model(4, 0.1, 0.3, 0.4)
+    bins = R.Bins(2, np.linspace(-100.0, 1500.0, 33))
+    kw = dict(k=5, m=40, lag=1, nrep=20, max_iterations=300)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=8), bins=bins, **kw)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=8), bins=bins, nthreads=8, **kw)
+    assert_same(g, c, KEYS + ["bins"])
+    assert g["bins"].sum() > 0
+
+
+def test_c4_replay_tape_two_replicates_per_warp(engine, oracle):
+    """tape mode with several replicates per warp, tapes of exactly the needed length for some replicates only"""
+    mdl = cases.c4_model(3, 0.2, 0.3, 0.35)
+    nrep, steps = 11, 12
+    rng = np.random.default_rng(9)
+    draws = R.Draws(tape_u=rng.uniform(size=(nrep, 2 * 3 * 1024 + steps * (1 + 3 * 1024))))
+    g = engine.sample_unbiasedestimator(mdl, draws, k=2, m=8, lag=1, max_iterations=steps, nrep=nrep)
+    c = oracle.sample_unbiasedestimator(mdl, draws, k=2, m=8, lag=1, max_iterations=steps, nrep=nrep)
     assert_same(g, c, KEYS)

@@ -18,7 +18,7 @@ elif which == "c2bench":      # the bench workload's k, m on one wave of replica
     res = eng.sample_unbiasedestimator(cases.c2_model(100), R.Draws(seed=1), k=2000, m=10000, lag=1, nrep=nrep, want_bins=False)
 elif which == "c4":
     # keep it tiny: under `ncu --set full` (about 40 replays) 296 replicates with m = 400 did not finish in 10 minutes
-    nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 148
+    nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 2368
     res = eng.sample_unbiasedestimator(cases.c4_model(), R.Draws(seed=1), k=20, m=40, lag=1, nrep=nrep, want_bins=False,
                                        max_iterations=80)
 elif which == "c2meet":

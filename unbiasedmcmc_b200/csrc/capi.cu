@@ -205,7 +205,7 @@ static int plan_build(ubm_handle* h, int mode, int32_t model_kind, const void* m
     return fail(h, UBM_ERR_UNSUPPORTED, "this model's state is integer valued (natural statistics / inclusion indicators): h must be the identity");
   }
   if (mode == MODE_ESTIMATOR && bins && bins->nbreaks >= 2 && model_kind != UBM_MODEL_NORMAL_MIXTURE &&
-      model_kind != UBM_MODEL_MVN) {
+      model_kind != UBM_MODEL_MVN && model_kind != UBM_MODEL_ISING_PT) {
     delete p;
     return fail(h, UBM_ERR_UNSUPPORTED, "on-the-fly histogram bins are not available for this model (use ubm_sample_coupled_chains + ubm_estimator_bins)");
   }

@@ -6,15 +6,22 @@
 //   kernels   R/ising.R:45-77 (PT single), :87-141 (PT coupled), :30-36 (rinit)
 //   numerics  src/ising.cpp:43-62 / :67-92 (systematic-scan sweeps), :11-35 (natural statistic)
 //
-// Design (B200): one CTA per replicate, ONE WARP PER TEMPERATURE.  A lattice is 32 x 32 spins = 32 words: lane i
-// keeps row i of chain 1 and of chain 2 in two registers for the whole replicate (no shared memory, no HBM).
-// The reference sweep is an in-place sequential scan, not a checkerboard; it is reproduced EXACTLY by an
-// anti-diagonal wavefront: site (i, j) is updated at step i + j, when rows i-1 / column j-1 already hold new
-// values and row i+1 / column j+1 still hold old ones (periodic wrap-arounds fall on the right side too) —
-// 63 warp steps per sweep, neighbour rows through warp shuffles.  The uniform of site (i, j) is draw number
-// 32 i + j of the sweep, shared by both chains; `U < p` is evaluated as an exact integer compare of the 32-bit
-// Philox word against ceil(p 2^32 - 1/2).  Natural statistics are popcounts; estimator sums are exact integers.
-// The 16 warps only meet at a CTA barrier for the meeting test, and for the (rare) swap moves.
+// Design (B200): ONE LANE PER LATTICE PAIR.  Lane l of a warp owns temperature l % N of replicate l / N of the warp's
+// group of 32 / N replicates; its two lattices (chain 1, chain 2) are 2 x 32 row words in shared memory, laid out
+// [row][lane] so that every access is conflict free and no lane ever touches another lane's words.  The reference
+// sweep is an in-place sequential scan, and it is reproduced EXACTLY, but a whole row at a time:
+//   * the 32 uniforms of a row are 8 Philox blocks; comparing each word with the 5 acceptance thresholds of the
+//     lane's temperature gives five bit planes G_q (bit j: "site j becomes +1 if q of its neighbours are +1") that
+//     both chains share;
+//   * the vertical neighbours (new row above, old row below) are fixed during the row, so P_m = G_{up + down + m}
+//     (m = left + right) are three more planes by bitwise multiplexing; the right neighbour is old (except for
+//     the last column), which folds P into M0 / M1 = the new spin when the left neighbour is -1 / +1;
+//   * what remains, new_j = new_{j-1} ? M1_j : M0_j, is a carry chain: with M0 a subset of M1 (thresholds increase
+//     with the neighbour count, i.e. beta >= 0) the 32 new spins are the carries of ONE integer addition M1 + M0 +
+//     carry-in.  (Negative beta: a 32-step serial recurrence on the same two planes.)
+// A sweep of a lattice pair is therefore 32 x (8 Philox blocks + 160 compares + about 60 logic operations) with
+// no shuffles, no idle lanes and no sequential dependence inside a row; the cost is the random numbers.
+// Natural statistics are popcounts; estimator sums are exact integers; swap moves permute shared-memory columns.
 #pragma once
 #include <string>
 #include <vector>
@@ -23,17 +30,25 @@
 namespace ubm {
 
 #define ISING_MAXN 32
+#ifndef ISING_WPB
+#define ISING_WPB 2          // warps per CTA (independent of each other)
+#endif
+#ifndef ISING_MINB
+#define ISING_MINB 8         // CTAs per SM asked of the register allocator
+#endif
 
 struct IsingDevice {
-  int N;
+  int N, monotone;                         // monotone: thresholds / probabilities nondecreasing in the neighbour count
   double pswap;
   double betas[ISING_MAXN];
-  double probas[ISING_MAXN][5];            // for the tape path (FP64 compare, as the reference)
+  double probas[ISING_MAXN][5];            // tape path (FP64 compare, as the reference)
   unsigned long long thr[ISING_MAXN][5];   // Philox path: U < p  <=>  word < thr
 };
 
+struct IsingKeys { uint32_t k0[10], k1[10]; };   // Philox round keys of the run's seed (kernel-uniform: constant-bank operands)
+
 inline void ising_pack_host(const ubm_model_ising_pt* s, IsingDevice* M) {
-  M->N = s->nchains; M->pswap = s->proba_swapmove;
+  M->N = s->nchains; M->pswap = s->proba_swapmove; M->monotone = 1;
   for (int c = 0; c < s->nchains; ++c) {
     M->betas[c] = s->betas[c];
     for (int q = 0; q < 5; ++q) {                       // R/ising.R:151-152
@@ -44,29 +59,35 @@ inline void ising_pack_host(const ubm_model_ising_pt* s, IsingDevice* M) {
       // (w + 1/2) 2^-32 < p  <=>  w < p 2^32 - 1/2 (both sides exact in binary64)  <=>  w < ceil(p 2^32 - 1/2)
       double t = ceil(p * 4294967296.0 - 0.5);
       M->thr[c][q] = (t <= 0.0) ? 0ull : (unsigned long long)t;
+      if (q > 0 && (M->probas[c][q] < M->probas[c][q - 1] || M->thr[c][q] < M->thr[c][q - 1])) M->monotone = 0;
     }
   }
 }
+inline void ising_keys_host(uint64_t seed, IsingKeys* K) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) { K->k0[r] = k0; K->k1[r] = k1; k0 += UBM_PHILOX_W0; k1 += UBM_PHILOX_W1; }
+}
 
-// natural statistic of the lattice whose row `lane` is `r`: sum_{i~j} x_i x_j over right and down neighbours
-// (src/ising.cpp:11-35); x y = 1 - 2 (bit_x xor bit_y)
-__device__ __forceinline__ int ising_sum_rows(unsigned r, int lane) {
-  const unsigned right = (r >> 1) | (r << 31);                       // bit j <- bit j+1 (periodic)
-  const unsigned down = __shfl_sync(0xffffffffu, r, (lane + 1) & 31);   // row i+1
-  const int dis = __popc(r ^ right) + __popc(r ^ down);
-  return 2048 - 2 * (int)__reduce_add_sync(0xffffffffu, (unsigned)dis);
+// ubm_philox4x32_10 (include/ubm_numerics.h) with the key schedule precomputed
+__device__ __forceinline__ void ising_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const IsingKeys& K, uint32_t (&w)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)UBM_PHILOX_M0 * c0, p1 = (unsigned long long)UBM_PHILOX_M1 * c2;   // IMAD.WIDE
+    c0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k0[r]; c1 = (uint32_t)p1; c2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k1[r]; c3 = (uint32_t)p0;
+  }
+  w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
 }
 
 template <bool TAPE>
-struct IsingU {   // the replicate's U stream, addressed by absolute index; every warp tracks the same counter
+struct IsingU {   // the replicate's U stream, addressed by absolute index
   const RunParams& P;
   long long rep;
   uint64_t grep;
-  bool bad;
-  __device__ IsingU(const RunParams& p, long long r) : P(p), rep(r), grep((uint64_t)(p.rep_offset + r)), bad(false) {}
-  __device__ __forceinline__ ubm_u32x4 block(unsigned long long b) const { return ubm_stream_block(P.seed, grep, UBM_STREAM_U, b); }
+  bool bad, mute;     // mute: this lane is only shadowing the warp's control flow (tape reads are skipped)
+  __device__ IsingU(const RunParams& p, long long r) : P(p), rep(r), grep((uint64_t)(p.rep_offset + r)), bad(false), mute(false) {}
   __device__ __forceinline__ double u(unsigned long long i) {
     if (TAPE) {
+      if (mute) return 0.5;
       if (!P.tape_u || (long long)i >= P.len_u) { bad = true; return 0.5; }
       return P.tape_u[rep * P.len_u + (long long)i];
     }
@@ -74,194 +95,321 @@ struct IsingU {   // the replicate's U stream, addressed by absolute index; ever
   }
 };
 
-__device__ __forceinline__ unsigned pick_word(const ubm_u32x4& b, unsigned s) {
-  return (s == 0) ? b.w[0] : (s == 1) ? b.w[1] : (s == 2) ? b.w[2] : b.w[3];
+struct IsingLane {          // per-lane constants of a replicate group
+  unsigned T[5], full[5];   // Philox path: word < T[q] (32-bit), or always (+1 with probability one after rounding)
+  double prob[5];           // tape path
+};
+
+// G |= (w < t) ? bit : 0 as a compare and one predicated OR
+__device__ __forceinline__ void ising_or_if_less(unsigned& G, uint32_t w, unsigned t, unsigned bit) {
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(G) : "r"(w), "r"(t), "r"(bit));
+}
+__device__ __forceinline__ unsigned ising_mux(unsigned s, unsigned a, unsigned b) { return (s & a) | (~s & b); }   // s ? a : b, bitwise
+
+// The five threshold planes of one row: bit j of G[q] = [U_j < p_q].  `idx0` = index of the row's first uniform in the
+// replicate's U stream (a multiple of 4 on the Philox path: sweeps start on a block boundary).
+template <bool TAPE>
+__device__ __forceinline__ void ising_row_planes(unsigned (&G)[5], const IsingLane& LN, const IsingKeys& K, IsingU<TAPE>& U,
+                                                 unsigned long long idx0) {
+#pragma unroll
+  for (int q = 0; q < 5; ++q) G[q] = 0u;
+  if (TAPE) {
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+      const double ud = U.u(idx0 + (unsigned)j);
+#pragma unroll
+      for (int q = 0; q < 5; ++q) G[q] |= (ud < LN.prob[q]) ? (1u << j) : 0u;
+    }
+  } else {
+    const unsigned long long b0 = idx0 >> 2;
+    const uint32_t r0 = (uint32_t)U.grep, r1 = (uint32_t)(U.grep >> 32);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const unsigned long long blk = b0 + (unsigned)b;
+      uint32_t w[4];
+      ising_philox((uint32_t)blk, (UBM_STREAM_U << 28) | ((uint32_t)(blk >> 32) & 0x0FFFFFFFu), r0, r1, K, w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int q = 0; q < 5; ++q) ising_or_if_less(G[q], w[k], LN.T[q], 1u << (4 * b + k));
+    }
+#pragma unroll
+    for (int q = 0; q < 5; ++q) G[q] |= LN.full[q];
+  }
 }
 
-// One systematic-scan sweep of this warp's lattice (pair): wavefront over anti-diagonals.  `base` = index of the
-// sweep's first uniform in the replicate's U stream.  COUPLED: both rows, same uniform (src/ising.cpp:67-92).
-template <bool TAPE, bool COUPLED>
-__device__ __forceinline__ void ising_sweep(unsigned& r1, unsigned& r2, int lane, unsigned long long base,
-                                            const unsigned long long (&thr)[5], const double (&prob)[5], IsingU<TAPE>& U) {
-  const unsigned long long B = base + 32ull * lane;     // index of site (lane, 0)
-  ubm_u32x4 cur, nxt;
-  if (!TAPE) { cur = U.block(B >> 2); nxt = cur; }
+// The in-place sequential scan of one row (src/ising.cpp:47-60): `cur` old row, `up` the row above (already new, or
+// the old last row for row 0), `dn` the row below (old, or the new row 0 for the last row).  Returns the new row.
+template <bool MONO>
+__device__ __forceinline__ unsigned ising_row_scan(unsigned cur, unsigned up, unsigned dn, const unsigned (&G)[5]) {
+  const unsigned H0 = ising_mux(dn, G[1], G[0]), H1 = ising_mux(dn, G[2], G[1]);
+  const unsigned H2 = ising_mux(dn, G[3], G[2]), H3 = ising_mux(dn, G[4], G[3]);
+  const unsigned P0 = ising_mux(up, H1, H0), P1 = ising_mux(up, H2, H1), P2 = ising_mux(up, H3, H2);   // by left + right
+  const unsigned cin = cur >> 31;                        // left neighbour of column 0: the old column 31
+  unsigned R = __funnelshift_r(cur, cur, 1);             // bit j = old column j + 1 (bit 31 fixed below)
+  unsigned M0 = ising_mux(R, P1, P0), M1 = ising_mux(R, P2, P1);
+  const unsigned new0 = (cin ? M1 : M0) & 1u;            // column 0 first: it is the right neighbour of column 31
+  R = (R & 0x7fffffffu) | (new0 << 31);
+  M0 = ising_mux(R, P1, P0); M1 = ising_mux(R, P2, P1);
+  if (MONO) {
+    // new_j = M0_j | (M1_j & new_{j-1}): generate M0, propagate M1 & ~M0  ->  the carries of M1 + M0 + cin
+    const unsigned S = M1 + M0 + cin;
+    const unsigned Cin = S ^ M1 ^ M0;                    // carry INTO each bit = new_{j-1}
+    return (M1 & M0) | (Cin & (M1 ^ M0));                // carry OUT of each bit = new_j
+  } else {
+    unsigned nw = 0u, prev = cin;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      prev = ((prev ? M1 : M0) >> j) & 1u;
+      nw |= prev << j;
+    }
+    return nw;
+  }
+}
+
+// One systematic-scan sweep of this lane's lattice (pair).  `base` = index of the lattice's first uniform.  Rows are
+// written back only where `st1` / `st2` (lanes of other replicates of the warp may be doing something else).
+// Returns through dis1 / dis2 the number of disagreeing neighbour pairs, through diff the OR of chain1 ^ chain2.
+template <bool TAPE, bool COUPLED, bool MONO>
+__device__ __forceinline__ void ising_sweep_lane(unsigned* __restrict__ L1, unsigned* __restrict__ L2, const IsingLane& LN,
+                                                 const IsingKeys& K, IsingU<TAPE>& U, unsigned long long base, bool st1, bool st2,
+                                                 int& dis1, int& dis2, unsigned& diff) {
+  unsigned up1 = L1[31 * 32], up2 = COUPLED ? L2[31 * 32] : 0u;
+  unsigned first1 = 0u, first2 = 0u;
+  int d1 = 0, d2 = 0;
+  unsigned df = 0u;
 #pragma unroll 1
-  for (int d = 0; d < 63; ++d) {
-    const int j = d - lane;
-    const unsigned up1 = __shfl_sync(0xffffffffu, r1, (lane + 1) & 31);
-    const unsigned dn1 = __shfl_sync(0xffffffffu, r1, (lane + 31) & 31);
-    unsigned up2 = 0, dn2 = 0;
+  for (int i = 0; i < 32; ++i) {
+    unsigned G[5];
+    ising_row_planes<TAPE>(G, LN, K, U, base + 32ull * (unsigned)i);
+    const int in = ((i + 1) & 31) * 32;
+    const unsigned n1 = ising_row_scan<MONO>(L1[i * 32], up1, L1[in], G);
+    if (st1) L1[i * 32] = n1;
+    d1 += __popc(n1 ^ __funnelshift_r(n1, n1, 1));
+    if (i == 0) first1 = n1; else d1 += __popc(n1 ^ up1);
+    up1 = n1;
     if (COUPLED) {
-      up2 = __shfl_sync(0xffffffffu, r2, (lane + 1) & 31);
-      dn2 = __shfl_sync(0xffffffffu, r2, (lane + 31) & 31);
+      const unsigned n2 = ising_row_scan<MONO>(L2[i * 32], up2, L2[in], G);
+      if (st2) L2[i * 32] = n2;
+      d2 += __popc(n2 ^ __funnelshift_r(n2, n2, 1));
+      if (i == 0) first2 = n2; else d2 += __popc(n2 ^ up2);
+      up2 = n2;
+      df |= n1 ^ n2;
     }
-    const int jc = j < 0 ? 0 : (j > 31 ? 31 : j);
-    const unsigned long long idx = B + (unsigned)jc;
-    unsigned w = 0;
-    double ud = 0.0;
+  }
+  dis1 = d1 + __popc(up1 ^ first1);
+  if (COUPLED) { dis2 = d2 + __popc(up2 ^ first2); diff = df; }
+}
+
+// natural statistic sum_{i~j} x_i x_j over right and down neighbours (src/ising.cpp:11-35); x y = 1 - 2 (bit_x xor bit_y)
+__device__ __forceinline__ int ising_stat_lane(const unsigned* __restrict__ L) {
+  int dis = 0;
+  unsigned prev = L[31 * 32];
+#pragma unroll 4
+  for (int i = 0; i < 32; ++i) {
+    const unsigned r = L[i * 32];
+    dis += __popc(r ^ __funnelshift_r(r, r, 1)) + __popc(r ^ prev);
+    prev = r;
+  }
+  return 2048 - 2 * dis;
+}
+
+// rinit (R/ising.R:4-8,30-36): the lattice from uniforms [first, first + 1024), filled column-major (draw idx -> row
+// idx % 32, column idx / 32), spin +1 iff U >= 0.5 (the top bit of the Philox word)
+template <bool TAPE>
+__device__ __forceinline__ void ising_rinit_lane(unsigned* __restrict__ L, const IsingKeys& K, IsingU<TAPE>& U, unsigned long long first) {
+  unsigned rows[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) rows[i] = 0u;
+#pragma unroll 1
+  for (int j = 0; j < 32; ++j) {
     if (TAPE) {
-      if (j >= 0 && j < 32) ud = U.u(idx);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) rows[i] |= (U.u(first + 32ull * (unsigned)j + (unsigned)i) >= 0.5 ? 1u : 0u) << j;
     } else {
-      // block bookkeeping, executed by all lanes together: a lane's next block is fetched at d % 4 == 0
-      if (j > 0 && j < 32 && (idx & 3ull) == 0) cur = nxt;
-      if ((d & 3) == 0) nxt = U.block((idx >> 2) + 1);
-      w = pick_word(cur, (unsigned)(idx & 3ull));
-    }
-    if (j >= 0 && j < 32) {
-      const int jr = (j + 1) & 31, jl = (j + 31) & 31;
-      const int c1 = (int)((up1 >> j) & 1u) + (int)((dn1 >> j) & 1u) + (int)((r1 >> jr) & 1u) + (int)((r1 >> jl) & 1u);
-      // neighbour sum s = 2 c - 4, table index (s + 4) / 2 = c   (src/ising.cpp:57)
-      bool b1;
-      if (TAPE) b1 = ud < ((c1 == 0) ? prob[0] : (c1 == 1) ? prob[1] : (c1 == 2) ? prob[2] : (c1 == 3) ? prob[3] : prob[4]);
-      else b1 = (unsigned long long)w < ((c1 == 0) ? thr[0] : (c1 == 1) ? thr[1] : (c1 == 2) ? thr[2] : (c1 == 3) ? thr[3] : thr[4]);
-      r1 = (r1 & ~(1u << j)) | ((b1 ? 1u : 0u) << j);
-      if (COUPLED) {
-        const int c2 = (int)((up2 >> j) & 1u) + (int)((dn2 >> j) & 1u) + (int)((r2 >> jr) & 1u) + (int)((r2 >> jl) & 1u);
-        bool b2;
-        if (TAPE) b2 = ud < ((c2 == 0) ? prob[0] : (c2 == 1) ? prob[1] : (c2 == 2) ? prob[2] : (c2 == 3) ? prob[3] : prob[4]);
-        else b2 = (unsigned long long)w < ((c2 == 0) ? thr[0] : (c2 == 1) ? thr[1] : (c2 == 2) ? thr[2] : (c2 == 3) ? thr[3] : thr[4]);
-        r2 = (r2 & ~(1u << j)) | ((b2 ? 1u : 0u) << j);
+      const unsigned long long b0 = (first >> 2) + 8ull * (unsigned)j;
+      const uint32_t r0 = (uint32_t)U.grep, r1 = (uint32_t)(U.grep >> 32);
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const unsigned long long blk = b0 + (unsigned)b;
+        uint32_t w[4];
+        ising_philox((uint32_t)blk, (UBM_STREAM_U << 28) | ((uint32_t)(blk >> 32) & 0x0FFFFFFFu), r0, r1, K, w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rows[4 * b + k] |= (w[k] >> 31) << j;
       }
     }
   }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) L[i * 32] = rows[i];
 }
 
 struct IsingShared {
-  int sums1[ISING_MAXN], sums2[ISING_MAXN];
-  int perm1[ISING_MAXN], perm2[ISING_MAXN];
-  unsigned lat[2][ISING_MAXN][32];
-  long long rep;
+  unsigned lat[ISING_WPB][2][32 * 32];     // [warp][chain][row * 32 + lane]
+  int sums[ISING_WPB][2][32];
+  int perm[ISING_WPB][2][32];
+  unsigned long long thr[ISING_MAXN * 5];
+  double prob[ISING_MAXN * 5];
+  double betas[ISING_MAXN];
 };
 
-// swap move (R/ising.R:48-68 / :97-126): sequential over adjacent pairs, one shared uniform per pair
-template <bool TAPE>
-__device__ __forceinline__ void ising_swap_move(const IsingDevice& M, IsingShared& sh, unsigned& r1, unsigned& r2,
-                                                int lane, int warp, unsigned long long base, bool do2, IsingU<TAPE>& U) {
-  const int N = M.N;
-  sh.lat[0][warp][lane] = r1;
-  sh.lat[1][warp][lane] = r2;
-  __syncthreads();
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int c = 0; c < N; ++c) { sh.perm1[c] = c; sh.perm2[c] = c; }
-      for (int c = 0; c + 1 < N; ++c) {
-        const double deltabeta = M.betas[c] - M.betas[c + 1];
-        const double logu = ubm_log(U.u(base + c));
-        const double lp1 = deltabeta * ((double)sh.sums1[c + 1] - (double)sh.sums1[c]);
-        if (logu < lp1) {
-          int t = sh.sums1[c]; sh.sums1[c] = sh.sums1[c + 1]; sh.sums1[c + 1] = t;
-          t = sh.perm1[c]; sh.perm1[c] = sh.perm1[c + 1]; sh.perm1[c + 1] = t;
-        }
-        if (do2) {
-          const double lp2 = deltabeta * ((double)sh.sums2[c + 1] - (double)sh.sums2[c]);
-          if (logu < lp2) {
-            int t = sh.sums2[c]; sh.sums2[c] = sh.sums2[c + 1]; sh.sums2[c + 1] = t;
-            t = sh.perm2[c]; sh.perm2[c] = sh.perm2[c + 1]; sh.perm2[c + 1] = t;
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-  r1 = sh.lat[0][sh.perm1[warp]][lane];
-  if (do2) r2 = sh.lat[1][sh.perm2[warp]][lane];
-  __syncthreads();
-}
-
-// One CTA per replicate, warp c = temperature c.
-template <bool TAPE>
-#ifndef ISING_MAXT
-#define ISING_MAXT 1024      // threads per CTA the kernel is compiled for (32 temperatures)
-#endif
-#ifndef ISING_MINB
-#define ISING_MINB 1
-#endif
-__global__ void __launch_bounds__(ISING_MAXT, ISING_MINB) ising_driver_kernel(const IsingDevice M, const RunParams P) {
+template <bool TAPE, bool MONO>
+__global__ void __launch_bounds__(32 * ISING_WPB, ISING_MINB) ising_driver_kernel(const IsingDevice M, const RunParams P, const IsingKeys K) {
   __shared__ IsingShared sh;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int N = M.N;
-  unsigned long long thr[5];
-  double prob[5];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int N = M.N, R = 32 / N;
+  const int slot = lane / N, c = lane - slot * N;
+  const bool lane_ok = slot < R;
+  const unsigned slotmask = lane_ok ? ((N == 32) ? FULL : (((1u << N) - 1u) << (slot * N))) : (1u << lane);
+  for (int t = threadIdx.x; t < N * 5; t += blockDim.x) { sh.thr[t] = M.thr[t / 5][t % 5]; sh.prob[t] = M.probas[t / 5][t % 5]; }
+  for (int t = threadIdx.x; t < N; t += blockDim.x) sh.betas[t] = M.betas[t];
+  __syncthreads();
+  IsingLane LN;
 #pragma unroll
-  for (int q = 0; q < 5; ++q) { thr[q] = M.thr[warp][q]; prob[q] = M.probas[warp][q]; }
+  for (int q = 0; q < 5; ++q) {
+    const unsigned long long t = sh.thr[c * 5 + q];
+    LN.full[q] = (t >> 32) ? FULL : 0u;
+    LN.T[q] = (t >> 32) ? FULL : (unsigned)t;
+    LN.prob[q] = sh.prob[c * 5 + q];
+  }
+  unsigned* L1 = &sh.lat[wib][0][lane];
+  unsigned* L2 = &sh.lat[wib][1][lane];
+  int* sums1 = sh.sums[wib][0]; int* sums2 = sh.sums[wib][1];
+  int* perm1 = sh.perm[wib][0]; int* perm2 = sh.perm[wib][1];
   const double denom = (double)(P.m - P.k + 1);
+  const int nbins = (P.mode == MODE_ESTIMATOR && P.nbreaks >= 2) ? P.nbreaks - 1 : 0;
+  double bin_b0 = 0.0, bin_iw = 0.0;
+  if (nbins) { bin_b0 = P.breaks[0]; bin_iw = (double)nbins / (P.breaks[nbins] - P.breaks[0]); }
 
   for (;;) {
-    if (tid == 0) {
-      const unsigned long long got = atomicAdd(P.work_counter, 1ull);
-      sh.rep = (got < (unsigned long long)P.nrep) ? (long long)got : -1;
-    }
-    __syncthreads();
-    const long long rep = sh.rep;
-    __syncthreads();
-    if (rep < 0) break;
+    unsigned long long got = 0;
+    if (lane == 0) got = atomicAdd(P.work_counter, (unsigned long long)R);
+    got = __shfl_sync(FULL, got, 0);
+    if (got >= (unsigned long long)P.nrep) break;
+    const bool valid = lane_ok && (long long)got + slot < P.nrep;
+    const long long rep = valid ? (long long)got + slot : (long long)got;   // idle lanes shadow replicate `got`, without writing
     IsingU<TAPE> U(P, rep);
-    // ---- rinit (R/ising.R:4-8,30-36): lattice c of chain 1 from uniforms [1024 c, 1024 c + 1024), then chain 2;
-    // filled column-major: draw idx -> row idx % 32, column idx / 32; spin +1 iff U >= 0.5
-    unsigned r1 = 0, r2 = 0;
-    for (int j = 0; j < 32; ++j) {
-      const unsigned long long i1 = 1024ull * warp + 32ull * j + lane;
-      const unsigned long long i2 = 1024ull * (N + warp) + 32ull * j + lane;
-      r1 |= (U.u(i1) >= 0.5 ? 1u : 0u) << j;
-      r2 |= (U.u(i2) >= 0.5 ? 1u : 0u) << j;
-    }
+    ising_rinit_lane<TAPE>(L1, K, U, 1024ull * (unsigned)c);
+    ising_rinit_lane<TAPE>(L2, K, U, 1024ull * (unsigned)(N + c));
     unsigned long long iu = 2048ull * N;
-    int s1 = ising_sum_rows(r1, lane), s2 = ising_sum_rows(r2, lane);
+    int s1 = ising_stat_lane(L1), s2 = ising_stat_lane(L2);
     long long mc = 0, co = 0;           // exact integer estimator sums of this temperature
     long long time = 0, tau = 0;
-    bool met = false;
-    if (P.mode == MODE_ESTIMATOR && P.k == 0) mc = s1;
-    if (P.mode == MODE_CHAINS && lane == 0) {
-      P.samples1[(rep * P.stride) * N + warp] = (double)s1;
-      P.samples2[(rep * P.stride) * N + warp] = (double)s2;
+    bool met = false, done = !valid;
+    long long* bn = (nbins && valid && c == P.component) ? P.bin_num + rep * nbins : nullptr;
+    if (P.mode == MODE_ESTIMATOR && P.k == 0) {
+      mc = s1;
+      if (bn) { const int b = bin_of((double)s1, P.breaks, P.nbreaks, bin_b0, bin_iw); if (b >= 0) bn[b] += 1; }
     }
-    // ---- time loop (generic drivers); every warp executes the same control flow
+    if (P.mode == MODE_CHAINS && valid) {
+      P.samples1[(rep * P.stride) * N + c] = (double)s1;
+      P.samples2[(rep * P.stride) * N + c] = (double)s2;
+    }
+    // ---- time loop (generic drivers); the replicates of a warp advance together, each with its own stopping rule
     for (;;) {
-      bool go;
-      if (time < P.lag) go = true;
-      else {
-        const bool capped = (P.max_it > 0 && time >= P.max_it) || U.bad;
-        if (P.mode == MODE_MEETING) go = !met && !capped;
-        else go = (!met || time < (tau > P.m ? tau : P.m)) && !capped;
+      if (TAPE) { if (__ballot_sync(FULL, U.bad) & slotmask) U.bad = true; }
+      bool go = false;
+      if (!done) {
+        if (time < P.lag) go = true;
+        else {
+          const bool capped = (P.max_it > 0 && time >= P.max_it) || U.bad;
+          if (P.mode == MODE_MEETING) go = !met && !capped;
+          else go = (!met || time < (tau > P.m ? tau : P.m)) && !capped;
+        }
+        if (!go) done = true;
       }
-      // U.bad is per-thread: make the decision CTA-uniform
-      if (TAPE) go = !__syncthreads_or(go ? 0 : 1);
-      if (!go) break;
-      time += 1;
-      const bool coupled_step = (time > P.lag) && !met;
-      const bool do2 = coupled_step;
-      const double u_iter = U.u(iu);                               // R/ising.R:46,92
-      iu += 1;
-      if (u_iter < M.pswap) {
-        if (lane == 0) { sh.sums1[warp] = s1; sh.sums2[warp] = s2; }
-        ising_swap_move<TAPE>(M, sh, r1, r2, lane, warp, iu, do2, U);
-        iu += (unsigned long long)(N - 1);
-      } else {
-        const unsigned long long base = iu + 1024ull * warp;
-        if (do2) ising_sweep<TAPE, true>(r1, r2, lane, base, thr, prob, U);
-        else ising_sweep<TAPE, false>(r1, r2, lane, base, thr, prob, U);
-        iu += 1024ull * N;
+      if (!__any_sync(FULL, go)) break;
+      if (go) time += 1;
+      const bool coupled_step = go && (time > P.lag) && !met;
+      double u_iter = 1.0;
+      if (go) { u_iter = U.u(iu); iu += 1; }                        // R/ising.R:46,92
+      const bool do_swap = go && (u_iter < M.pswap);
+      const bool do_sweep = go && !do_swap;
+      unsigned diff = 0u;
+      if (__any_sync(FULL, do_swap)) {
+        // ---- swap move (R/ising.R:48-68 / :97-126): sequential over adjacent pairs, one shared uniform per pair
+        sums1[lane] = s1; sums2[lane] = s2; perm1[lane] = lane; perm2[lane] = lane;
+        __syncwarp();
+        if (do_swap && c == 0) {
+          const int o = slot * N;
+          for (int cc = 0; cc + 1 < N; ++cc) {
+            const double deltabeta = sh.betas[cc] - sh.betas[cc + 1];
+            const double logu = ubm_log(U.u(iu + (unsigned)cc));
+            const double lp1 = deltabeta * ((double)sums1[o + cc + 1] - (double)sums1[o + cc]);
+            if (logu < lp1) {
+              int t = sums1[o + cc]; sums1[o + cc] = sums1[o + cc + 1]; sums1[o + cc + 1] = t;
+              t = perm1[o + cc]; perm1[o + cc] = perm1[o + cc + 1]; perm1[o + cc + 1] = t;
+            }
+            if (coupled_step) {
+              const double lp2 = deltabeta * ((double)sums2[o + cc + 1] - (double)sums2[o + cc]);
+              if (logu < lp2) {
+                int t = sums2[o + cc]; sums2[o + cc] = sums2[o + cc + 1]; sums2[o + cc + 1] = t;
+                t = perm2[o + cc]; perm2[o + cc] = perm2[o + cc + 1]; perm2[o + cc + 1] = t;
+              }
+            }
+          }
+        }
+        __syncwarp();
+        const int src1 = perm1[lane], src2 = perm2[lane];          // identity for lanes that do not swap
+        const unsigned* B1 = &sh.lat[wib][0][0];
+        const unsigned* B2 = &sh.lat[wib][1][0];
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          const unsigned v1 = B1[i * 32 + src1], v2 = B2[i * 32 + src2];
+          __syncwarp();
+          L1[i * 32] = v1; L2[i * 32] = v2;
+          if (do_swap) diff |= v1 ^ v2;
+          __syncwarp();
+        }
+        if (do_swap) { s1 = sums1[lane]; s2 = sums2[lane]; iu += (unsigned long long)(N - 1); }
+        __syncwarp();
       }
-      s1 = ising_sum_rows(r1, lane);                               // R/ising.R:75,135-136
-      if (do2) {
-        s2 = ising_sum_rows(r2, lane);
-        const int eq = __all_sync(0xffffffffu, r1 == r2) ? 1 : 0;
-        if (__syncthreads_and(eq)) { met = true; tau = time; }     // R/ising.R:215
+      if (__any_sync(FULL, do_sweep)) {
+        // Philox path: a sweep starts on a block boundary of the U stream (the numerics contract; tapes are dense)
+        const unsigned long long sweep0 = TAPE ? iu : ((iu + 3ull) & ~3ull);
+        const unsigned long long base = sweep0 + 1024ull * (unsigned)c;
+        int dis1 = 0, dis2 = 0;
+        unsigned df = 0u;
+        U.mute = !do_sweep;
+        if (__any_sync(FULL, do_sweep && coupled_step)) {
+          ising_sweep_lane<TAPE, true, MONO>(L1, L2, LN, K, U, base, do_sweep, do_sweep && coupled_step, dis1, dis2, df);
+          if (do_sweep && coupled_step) { s2 = 2048 - 2 * dis2; diff = df; }
+        } else {
+          ising_sweep_lane<TAPE, false, MONO>(L1, L2, LN, K, U, base, do_sweep, false, dis1, dis2, df);
+        }
+        U.mute = false;
+        if (do_sweep) { s1 = 2048 - 2 * dis1; iu = sweep0 + 1024ull * (unsigned)N; }
       }
-      const int y = (time > P.lag && !coupled_step) ? s1 : s2;     // after meeting chain 2 copies chain 1
-      if (P.mode == MODE_ESTIMATOR) {
-        const bool in_window = (time <= P.lag) ? (time >= P.k) : (P.k <= time && time <= P.m);
-        if (in_window) mc += s1;
-        if ((time >= P.k + P.lag) && (coupled_step || time == P.lag)) co += corr_weight(time, P.k, P.m, P.lag) * (long long)(s1 - y);
-      } else if (P.mode == MODE_CHAINS && lane == 0) {
-        P.samples1[(rep * P.stride + time) * N + warp] = (double)s1;
-        if (time > P.lag) P.samples2[(rep * P.stride + (time - P.lag)) * N + warp] = (double)y;
+      if (__any_sync(FULL, coupled_step)) {
+        const unsigned eq = __ballot_sync(FULL, diff == 0u);
+        if (coupled_step && (eq & slotmask) == slotmask) { met = true; tau = time; }     // R/ising.R:215
+      }
+      if (go) {
+        const int y = (time > P.lag && !coupled_step) ? s1 : s2;     // after meeting chain 2 copies chain 1
+        if (P.mode == MODE_ESTIMATOR) {
+          const bool in_window = (time <= P.lag) ? (time >= P.k) : (P.k <= time && time <= P.m);
+          const bool add_corr = (time >= P.k + P.lag) && (coupled_step || time == P.lag);
+          if (in_window) mc += s1;
+          long long w = 0;
+          if (add_corr) { w = corr_weight(time, P.k, P.m, P.lag); co += w * (long long)(s1 - y); }
+          if (bn) {                                                   // estimator_bin_ numerators (src/estimator_bin.cpp:15-38)
+            const int b1 = bin_of((double)s1, P.breaks, P.nbreaks, bin_b0, bin_iw);
+            if (in_window && b1 >= 0) bn[b1] += 1;
+            if (add_corr) {
+              const int b2 = bin_of((double)y, P.breaks, P.nbreaks, bin_b0, bin_iw);
+              if (b1 >= 0) bn[b1] += w;
+              if (b2 >= 0) bn[b2] -= w;
+            }
+          }
+        } else if (P.mode == MODE_CHAINS) {
+          P.samples1[(rep * P.stride + time) * N + c] = (double)s1;
+          if (time > P.lag) P.samples2[(rep * P.stride + (time - P.lag)) * N + c] = (double)y;
+        }
       }
     }
     // ---- results
-    if (lane == 0) {
-      if (warp == 0) {
+    if (valid) {
+      if (c == 0) {
         double cost = dinf();
         if (met) {
           if (P.mode == MODE_MEETING) cost = (double)(P.lag + 2 * (tau - P.lag));
@@ -275,25 +423,30 @@ __global__ void __launch_bounds__(ISING_MAXT, ISING_MINB) ising_driver_kernel(co
       if (P.mode == MODE_ESTIMATOR) {
         const double dmc = (double)mc, dco = (double)co;
         const double ue = dmc + dco;
-        P.uest[rep * N + warp] = ue / denom;
-        if (P.mcmc) P.mcmc[rep * N + warp] = dmc / denom;
-        if (P.corr) P.corr[rep * N + warp] = dco / denom;
+        P.uest[rep * N + c] = ue / denom;
+        if (P.mcmc) P.mcmc[rep * N + c] = dmc / denom;
+        if (P.corr) P.corr[rep * N + c] = dco / denom;
       }
     }
+    __syncwarp();
   }
 }
 
 inline int ising_launch(const IsingDevice& M, const RunParams& P, bool tape, int nsm, cudaStream_t st,
                         int64_t* launches, std::string* err) {
-  if (P.nbreaks >= 2) { *err = "ising: histogram bins are not available for this model"; return UBM_ERR_UNSUPPORTED; }
   if (P.mode == MODE_ESTIMATOR && P.h_kind != UBM_H_IDENTITY) { *err = "ising: h must be the identity on the natural statistics"; return UBM_ERR_UNSUPPORTED; }
-  const int threads = 32 * M.N;
-  auto kern = tape ? ising_driver_kernel<true> : ising_driver_kernel<false>;
+  IsingKeys K;
+  ising_keys_host(P.seed, &K);
+  void (*kern)(const IsingDevice, const RunParams, const IsingKeys);
+  if (tape) kern = M.monotone ? ising_driver_kernel<true, true> : ising_driver_kernel<true, false>;
+  else kern = M.monotone ? ising_driver_kernel<false, true> : ising_driver_kernel<false, false>;
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * ISING_WPB, 0);
   if (e != cudaSuccess || per_sm < 1) { *err = "ising: occupancy query failed"; return UBM_ERR_CUDA; }
-  int grid = (int)std::min<int64_t>((int64_t)nsm * per_sm, P.nrep);
-  kern<<<grid, threads, 0, st>>>(M, P);
+  const int per_group = 32 / M.N;                                   // replicates of one warp
+  const int64_t groups = (P.nrep + per_group - 1) / per_group;
+  const int grid = (int)std::min<int64_t>((int64_t)nsm * per_sm, (groups + ISING_WPB - 1) / ISING_WPB);
+  kern<<<grid, 32 * ISING_WPB, 0, st>>>(M, P, K);
   *launches += 1;
   return UBM_OK;
 }
