@@ -11,7 +11,7 @@
 // [row][lane] so that every access is conflict free and no lane ever touches another lane's words.  The reference
 // sweep is an in-place sequential scan, and it is reproduced EXACTLY, but a whole row at a time:
 //   * the 32 uniforms of a row are 8 Philox blocks; comparing each word with the 5 acceptance thresholds of the
-//     lane's temperature gives five bit planes G_q (bit j: "site j becomes +1 if q of its neighbours are +1") that
+//     lane's temperature (as the carry out of word + (2^32 - threshold)) gives five bit planes G_q (bit j: "site j becomes +1 if q of its neighbours are +1") that
 //     both chains share;
 //   * the vertical neighbours (new row above, old row below) are fixed during the row, so P_m = G_{up + down + m}
 //     (m = left + right) are three more planes by bitwise multiplexing; the right neighbour is old (except for
@@ -96,13 +96,16 @@ struct IsingU {   // the replicate's U stream, addressed by absolute index
 };
 
 struct IsingLane {          // per-lane constants of a replicate group
-  unsigned T[5], full[5];   // Philox path: word < T[q] (32-bit), or always (+1 with probability one after rounding)
+  unsigned C[5], never[5];  // Philox path: the carry out of word + C, C = 2^32 - thr (mod 2^32), is [word >= thr]; thr = 0: never +1
   double prob[5];           // tape path
 };
 
-// G |= (w < t) ? bit : 0 as a compare and one predicated OR
-__device__ __forceinline__ void ising_or_if_less(unsigned& G, uint32_t w, unsigned t, unsigned bit) {
-  asm("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(G) : "r"(w), "r"(t), "r"(bit));
+// acc = 2 acc + [w + c carries]: one alu-pipe add for the carry, one fma-pipe multiply-add (IMAD.X) to shift it in.  The two
+// pipes issue one warp instruction every other cycle each, and the alu pipe is this kernel's bound (ncu: alu 64%, fma 26% with a
+// compare + predicated OR), so the plane building is split across them (measured +15%).  A compare done entirely on the fma
+// pipe (the high word of IMAD.WIDE w * 1 + c) is undone by ptxas, which turns it back into the add.
+__device__ __forceinline__ void ising_shift_in_carry(unsigned& acc, uint32_t w, unsigned c) {
+  asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\tmadc.lo.u32 %0, %0, 2, 0;\n\t}" : "+r"(acc) : "r"(w), "r"(c));
 }
 __device__ __forceinline__ unsigned ising_mux(unsigned s, unsigned a, unsigned b) { return (s & a) | (~s & b); }   // s ? a : b, bitwise
 
@@ -123,18 +126,20 @@ __device__ __forceinline__ void ising_row_planes(unsigned (&G)[5], const IsingLa
   } else {
     const unsigned long long b0 = idx0 >> 2;
     const uint32_t r0 = (uint32_t)U.grep, r1 = (uint32_t)(U.grep >> 32);
+    // columns 31 .. 0, so that the planes built by shifting (2 acc + bit) end with column j in bit j
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
+    for (int b = 7; b >= 0; --b) {
       const unsigned long long blk = b0 + (unsigned)b;
       uint32_t w[4];
       ising_philox((uint32_t)blk, (UBM_STREAM_U << 28) | ((uint32_t)(blk >> 32) & 0x0FFFFFFFu), r0, r1, K, w);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 3; k >= 0; --k) {
 #pragma unroll
-        for (int q = 0; q < 5; ++q) ising_or_if_less(G[q], w[k], LN.T[q], 1u << (4 * b + k));
+        for (int q = 0; q < 5; ++q) ising_shift_in_carry(G[q], w[k], LN.C[q]);
+      }
     }
 #pragma unroll
-    for (int q = 0; q < 5; ++q) G[q] |= LN.full[q];
+    for (int q = 0; q < 5; ++q) G[q] = ~(G[q] | LN.never[q]);     // [w >= thr] -> [w < thr]
   }
 }
 
@@ -268,8 +273,8 @@ __global__ void __launch_bounds__(32 * ISING_WPB, ISING_MINB) ising_driver_kerne
 #pragma unroll
   for (int q = 0; q < 5; ++q) {
     const unsigned long long t = sh.thr[c * 5 + q];
-    LN.full[q] = (t >> 32) ? FULL : 0u;
-    LN.T[q] = (t >> 32) ? FULL : (unsigned)t;
+    LN.C[q] = (unsigned)(4294967296ull - t);      // thr = 2^32: C = 0, never a carry, always +1
+    LN.never[q] = (t == 0ull) ? FULL : 0u;
     LN.prob[q] = sh.prob[c * 5 + q];
   }
   unsigned* L1 = &sh.lat[wib][0][lane];
