@@ -226,7 +226,10 @@ struct PgLogisticModel {
   const double* chain_state(const State& s) const { return s.beta.data(); }
   void copy(State& dst, const State& src) const { dst = src; }
 
-  // inverse of a lower-triangular matrix (column-major), forward substitution column by column
+  // inverse of a lower-triangular matrix (column-major), forward substitution column by column.  Canonical arithmetic
+  // of all the triangular solves of this model: the diagonal enters through its reciprocal (1 / L_ii once, then one
+  // multiplication per unknown) — on the device a solve is a chain of dependent steps, and a division per step would
+  // triple its length.
   static std::vector<double> tri_inverse(const std::vector<double>& L, int p) {
     std::vector<double> Li((size_t)p * p, 0.0);
     for (int j = 0; j < p; ++j) {
@@ -234,7 +237,7 @@ struct PgLogisticModel {
       for (int i = j + 1; i < p; ++i) {
         double s = 0.0;
         for (int k = j; k < i; ++k) s = ubm_fma(L[(size_t)k * p + i], Li[(size_t)j * p + k], s);
-        Li[(size_t)j * p + i] = -s / L[(size_t)i * p + i];
+        Li[(size_t)j * p + i] = -s * (1.0 / L[(size_t)i * p + i]);
       }
     }
     return Li;
@@ -268,9 +271,14 @@ struct PgLogisticModel {
     int e = 0;
     for (int j1 = 0; j1 < p; ++j1)
       for (int j2 = j1; j2 < p; ++j2, ++e) {
-        // :42-45.  Canonical order: four interleaved chains over the observations (i mod 4), added to invB in turn
+        // :42-45.  Canonical order: four chains over the groups of four observations (class (i / 4) mod 4), each sequential
+        // in i, every term one fma of the rounded X(i,j1) omega(i) with X(i,j2); added to invB in turn.  (What a chain
+        // of FP64 tensor-core m8n8k4 operations computes; the reference sums (X X) omega sequentially.)
         double part[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int i = 0; i < n; ++i) part[i & 3] = ubm_fma(Zprod[(size_t)i * ne + e], omega[i], part[i & 3]);
+        for (int i = 0; i < n; ++i) {
+          const int c = (i >> 2) & 3;
+          part[c] = ubm_fma(X[(size_t)j1 * n + i] * omega[i], X[(size_t)j2 * n + i], part[c]);
+        }
         double a = invB[(size_t)j2 * p + j1];
         for (int c = 0; c < 4; ++c) a = a + part[c];
         r.L[(size_t)j1 * p + j2] = a;                                             // lower triangle (column j1, row j2)
@@ -278,20 +286,21 @@ struct PgLogisticModel {
       }
     bool ok = true;
     chol_lower(r.L, p, &ok);                                                      // :49-50
-    // x = A^{-1} b : L y = b, L^T x = y                                          // :51
+    r.Linv = tri_inverse(r.L, p);                                                 // :55  lower.inverse()
+    // x = A^{-1} b (:51) through the inverse factor that :55 needs anyway: y = Linv b, x = Linv' y — two sets of independent
+    // dot products (terms in increasing index order) instead of two substitutions of p dependent steps each
     std::vector<double> y(p);
     for (int i = 0; i < p; ++i) {
-      double s = ktk[i];
-      for (int k = 0; k < i; ++k) s = ubm_fma(-r.L[(size_t)k * p + i], y[k], s);
-      y[i] = s / r.L[(size_t)i * p + i];
+      double s = 0.0;
+      for (int k = 0; k <= i; ++k) s = ubm_fma(r.Linv[(size_t)k * p + i], ktk[k], s);
+      y[i] = s;
     }
     r.m.assign(p, 0.0);
-    for (int i = p - 1; i >= 0; --i) {                 // back substitution, terms taken from the last row upwards
-      double s = y[i];
-      for (int k = p - 1; k > i; --k) s = ubm_fma(-r.L[(size_t)i * p + k], r.m[k], s);
-      r.m[i] = s / r.L[(size_t)i * p + i];
+    for (int j = 0; j < p; ++j) {
+      double s = 0.0;
+      for (int i = j; i < p; ++i) s = ubm_fma(r.Linv[(size_t)j * p + i], y[i], s);
+      r.m[j] = s;
     }
-    r.Linv = tri_inverse(r.L, p);                                                 // :55  lower.inverse()
     return r;
   }
   // fast_rmvnorm_ with a precomputed upper factor U (src/mvnorm.cpp:9-26): one normal per column, y = z U + mean
@@ -313,7 +322,7 @@ struct PgLogisticModel {
     for (int i = 0; i < p; ++i) {                                                             // :62 lower.solve(xc^T)
       double sacc = x[i] - mean[i];
       for (int k = 0; k < i; ++k) sacc = ubm_fma(-Ls[(size_t)k * p + i], y[k], sacc);
-      y[i] = sacc / Ls[(size_t)i * p + i];
+      y[i] = sacc * (1.0 / Ls[(size_t)i * p + i]);
     }
     double sq = 0.0;
     for (int i = 0; i < p; ++i) sq = ubm_fma(y[i], y[i], sq);

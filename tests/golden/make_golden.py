@@ -1,9 +1,10 @@
 """Regenerates tests/golden/oracle_r01.json: small outputs of the oracle under the engine's numerics contract, stored as
 hex floats.  They pin OUR canonical arithmetic (Philox streams, summation orders, Cholesky variants) against accidental
 drift between rounds (parity with the reference itself is pinned elsewhere: tests/test_r_stream.py against R's printed
-README output, tests/test_ref_parity.py against the reference's compiled C++).  Regenerated in round 2 for the C2 entry: the
+README output, tests/test_ref_parity.py against the reference's compiled C++).  Regenerated in round 2: C2 (the
 column sums of the triangular products are now one fma chain in k order (what a chain of DMMAs computes), without the
-round-1 cut of the long columns.  Run from the repo root:  python tests/golden/make_golden.py"""
+round-1 cut of the long columns), C3 (Gram in FP64-tensor-core order, reciprocal-diagonal triangular solves, m through the inverse factor)
+and C4 (Philox sweeps start on a block boundary).  Run from the repo root:  python tests/golden/make_golden.py"""
 import json
 import os
 import sys

@@ -110,3 +110,15 @@ def test_c3_credit_like_design_bit_exact(engine, oracle):
     g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=12), **kw)
     c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=12), nthreads=6, **kw)
     assert_same(g, c, KEYS)
+
+
+@pytest.mark.parametrize("comp", [0, 3])
+def test_c3_bins_on_the_fly(engine, oracle, comp):
+    """estimator_bin_ (src/estimator_bin.cpp:15-38) of one regression coefficient, accumulated while the chains run"""
+    mdl = cases.c3_model(120, 5, seed=2)
+    bins = R.Bins(comp, np.linspace(-3.0, 3.0, 41))
+    kw = dict(k=5, m=60, lag=1, nrep=24, max_iterations=2000)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=9), bins=bins, **kw)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=9), bins=bins, nthreads=8, **kw)
+    assert_same(g, c, KEYS + ["bins"])
+    assert abs(g["bins"].sum(1).mean() - 1.0) < 0.2

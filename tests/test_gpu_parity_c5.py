@@ -47,3 +47,23 @@ def test_c5_chains_and_replay(engine, oracle):
     g = engine.sample_unbiasedestimator(mdl, draws, k=5, m=50, lag=1, max_iterations=700, nrep=8)
     c = oracle.sample_unbiasedestimator(mdl, draws, k=5, m=50, lag=1, max_iterations=700, nrep=8)
     assert_same(g, c, KEYS)
+
+
+@pytest.mark.parametrize("comp,lag,maxit", [(0, 1, 2000), (17, 2, 2000), (29, 1, 120)])
+def test_c5_bins_on_the_fly(engine, oracle, comp, lag, maxit):
+    """estimator_bin_ (src/estimator_bin.cpp:15-38) of one inclusion indicator, in closed form from the lazy counters;
+    the last case censors some replicates before they meet"""
+    mdl = cases.c5_model(100, 30, kappa=0.1, s0=10, snr=2.0)
+    bins = R.Bins(comp, np.array([-0.5, 0.5, 1.5]))
+    kw = dict(k=30, m=150, lag=lag, nrep=48, max_iterations=maxit)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=6), bins=bins, **kw)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=6), bins=bins, nthreads=8, **kw)
+    assert_same(g, c, KEYS + ["bins"])
+    ok = np.isfinite(g["meetingtime"])
+    np.testing.assert_allclose(g["bins"][ok].sum(1), 1.0, atol=1e-12)          # the two values carry all the mass
+    np.testing.assert_allclose(g["bins"][ok][:, 1], g["uestimator"][ok][:, comp], atol=1e-12)
+    # a break inside (0, 1) and values outside all bins
+    bins2 = R.Bins(comp, np.array([0.25, 0.75, 2.0]))
+    g2 = engine.sample_unbiasedestimator(mdl, R.Draws(seed=6), bins=bins2, **kw)
+    c2 = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=6), bins=bins2, nthreads=8, **kw)
+    assert_same(g2, c2, KEYS + ["bins"])

@@ -204,11 +204,6 @@ static int plan_build(ubm_handle* h, int mode, int32_t model_kind, const void* m
     delete p;
     return fail(h, UBM_ERR_UNSUPPORTED, "this model's state is integer valued (natural statistics / inclusion indicators): h must be the identity");
   }
-  if (mode == MODE_ESTIMATOR && bins && bins->nbreaks >= 2 && model_kind != UBM_MODEL_NORMAL_MIXTURE &&
-      model_kind != UBM_MODEL_MVN && model_kind != UBM_MODEL_ISING_PT) {
-    delete p;
-    return fail(h, UBM_ERR_UNSUPPORTED, "on-the-fly histogram bins are not available for this model (use ubm_sample_coupled_chains + ubm_estimator_bins)");
-  }
   if (mode == MODE_ESTIMATOR && bins && bins->nbreaks >= 2) {
     if (bins->nbreaks > 257) { delete p; return fail(h, UBM_ERR_INVALID, "at most 256 bins"); }
     if (bins->component < 0 || bins->component >= p->dim) { delete p; return fail(h, UBM_ERR_INVALID, "bins: component out of range"); }

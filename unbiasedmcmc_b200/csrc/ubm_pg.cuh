@@ -74,7 +74,7 @@ inline void pg_pack_host(const ubm_model_pg_logistic* s, PgDevice* M, std::vecto
     for (int i = j + 1; i < p; ++i) {
       double acc = 0.0;
       for (int k = j; k < i; ++k) acc = ubm_fma(LB[(size_t)k * p + i], Li[(size_t)j * p + k], acc);
-      Li[(size_t)j * p + i] = -acc / LB[(size_t)i * p + i];
+      Li[(size_t)j * p + i] = -acc * (1.0 / LB[(size_t)i * p + i]);
     }
   }
   for (int a = 0; a < p; ++a)
@@ -271,16 +271,16 @@ __device__ inline void pg_cta_chol(double* A1, double* A2, double* dg, int p, in
   for (int k = t; k < p; k += nthr) A[k * p + k] = d[k];
   __syncthreads();
 }
-// solve L y = rhs (forward), y overwrites `v` (shared); terms taken in increasing column order.  The diagonal sits in
-// registers (lane k mod 32) and the column of the next step is requested one step ahead, so a step is one shuffle
-// pair, one division and one fma deep.
+// solve L y = rhs (forward), y overwrites `v` (shared); terms taken in increasing column order.  The reciprocal diagonal
+// sits in registers (lane k mod 32) and the column of the next step is requested one step ahead, so a step is one
+// shuffle pair, one multiplication and one fma deep (oracle: y_i = s_i * (1 / L_ii)).
 __device__ __noinline__ void pg_warp_forward(const double* L, int p, int lane, double* v) {
   double s[2], dg[2];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     const int i = lane + 32 * q;
     s[q] = (i < p) ? v[i] : 0.0;
-    dg[q] = (i < p) ? L[i * p + i] : 1.0;
+    dg[q] = (i < p) ? 1.0 / L[i * p + i] : 1.0;
   }
   double c0 = (lane < p) ? L[lane] : 0.0, c1 = (lane + 32 < p) ? L[lane + 32] : 0.0;          // column 0
   for (int k = 0; k < p; ++k) {
@@ -288,7 +288,7 @@ __device__ __noinline__ void pg_warp_forward(const double* L, int p, int lane, d
     const double dk = __shfl_sync(0xffffffffu, (k >= 32) ? dg[1] : dg[0], k & 31);
     double n0 = 0.0, n1 = 0.0;
     if (k + 1 < p) { if (lane < p) n0 = L[(k + 1) * p + lane]; if (lane + 32 < p) n1 = L[(k + 1) * p + lane + 32]; }
-    const double yk = sk / dk;
+    const double yk = sk * dk;
     if (lane == k) s[0] = yk; else if (lane > k && lane < p) s[0] = ubm_fma(-c0, yk, s[0]);
     if (lane + 32 == k) s[1] = yk; else if (lane + 32 > k && lane + 32 < p) s[1] = ubm_fma(-c1, yk, s[1]);
     c0 = n0; c1 = n1;
@@ -304,7 +304,7 @@ __device__ __noinline__ void pg_warp_backward(const double* L, int p, int lane, 
   for (int q = 0; q < 2; ++q) {
     const int i = lane + 32 * q;
     s[q] = (i < p) ? v[i] : 0.0;
-    dg[q] = (i < p) ? L[i * p + i] : 1.0;
+    dg[q] = (i < p) ? 1.0 / L[i * p + i] : 1.0;
   }
   // row k of L, element i: L(k, i) = L[i * p + k]
   double c0 = (lane < p) ? L[lane * p + p - 1] : 0.0, c1 = (lane + 32 < p) ? L[(lane + 32) * p + p - 1] : 0.0;
@@ -313,7 +313,7 @@ __device__ __noinline__ void pg_warp_backward(const double* L, int p, int lane, 
     const double dk = __shfl_sync(0xffffffffu, (k >= 32) ? dg[1] : dg[0], k & 31);
     double n0 = 0.0, n1 = 0.0;
     if (k > 0) { if (lane < p) n0 = L[lane * p + k - 1]; if (lane + 32 < p) n1 = L[(lane + 32) * p + k - 1]; }
-    const double xk = sk / dk;
+    const double xk = sk * dk;
     if (lane == k) s[0] = xk; else if (lane < k) s[0] = ubm_fma(-c0, xk, s[0]);
     if (lane + 32 == k) s[1] = xk; else if (lane + 32 < k) s[1] = ubm_fma(-c1, xk, s[1]);
     c0 = n0; c1 = n1;
@@ -322,26 +322,38 @@ __device__ __noinline__ void pg_warp_backward(const double* L, int p, int lane, 
   for (int q = 0; q < 2; ++q) { const int i = lane + 32 * q; if (i < p) v[i] = s[q]; }
   __syncwarp();
 }
-// Li = L^-1 (lower): lane owns columns j = lane, lane + 32 and runs the oracle's forward substitution for each
-__device__ __noinline__ void pg_warp_tri_inverse(const double* L, double* Li, int p, int lane) {
-  for (int q = 0; q < 2; ++q) {
-    const int j = lane + 32 * q;
-    if (j >= p) continue;
-    for (int i = 0; i < j; ++i) Li[j * p + i] = 0.0;
-    Li[j * p + j] = 1.0 / L[j * p + j];
-    for (int i = j + 1; i < p; ++i) {
-      double s = 0.0;
-      int k = j;
-      for (; k + 3 < i; k += 4) {        // operands first, then the four dependent fma (same order as the plain loop)
-        const double l0 = L[k * p + i], l1 = L[(k + 1) * p + i], l2 = L[(k + 2) * p + i], l3 = L[(k + 3) * p + i];
-        const double y0 = Li[j * p + k], y1 = Li[j * p + k + 1], y2 = Li[j * p + k + 2], y3 = Li[j * p + k + 3];
-        s = ubm_fma(l0, y0, s); s = ubm_fma(l1, y1, s); s = ubm_fma(l2, y2, s); s = ubm_fma(l3, y3, s);
-      }
-      for (; k < i; ++k) s = ubm_fma(L[k * p + i], Li[j * p + k], s);
-      Li[j * p + i] = -s / L[i * p + i];
+// Li = L^-1 (lower) of one or two factors, by the warps `w0 .. w0 + nw - 1`: a warp takes whole columns j (the columns are
+// independent forward substitutions L x = e_j) and runs them right-looking with its lanes on the rows: once x_k is known
+// every row i > k takes its term fma(L(i,k), x_k, s_i) — each row still sees k = j, j + 1, ... in order, the oracle's
+// chain — and x_{k+1} = -s_{k+1} (1 / L_{k+1,k+1}) follows by one multiplication and a shuffle.  (One lane per column
+// walking the left-looking loops was a single dependent chain of 1176 fma: 60 K cycles.)
+__device__ inline void pg_tri_inverse_cols(const double* LA, double* LiA, const double* LB, double* LiB, int p, int warp, int lane,
+                                           int w0, int nw) {
+  const int ncol = LB ? 2 * p : p;
+  for (int cj = warp - w0; cj < ncol; cj += nw) {
+    const bool second = cj >= p;
+    const double* L = second ? LB : LA;
+    double* Li = second ? LiB : LiA;
+    const int j = second ? cj - p : cj;
+    double s[2] = {0.0, 0.0}, rd[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) { const int i = lane + 32 * q; rd[q] = (i < p) ? 1.0 / L[i * p + i] : 0.0; }
+    for (int i = lane; i < j; i += 32) Li[j * p + i] = 0.0;
+    double yk = __shfl_sync(0xffffffffu, (j >= 32) ? rd[1] : rd[0], j & 31);     // Li(j,j) = 1 / L(j,j)
+    double c0 = (lane > j && lane < p) ? L[j * p + lane] : 0.0, c1 = (lane + 32 > j && lane + 32 < p) ? L[j * p + lane + 32] : 0.0;
+    for (int k = j; k < p; ++k) {
+      if (lane == (k & 31)) Li[j * p + k] = yk;
+      if (k + 1 == p) break;
+      double n0 = 0.0, n1 = 0.0;                                                  // column k + 1 of L, one step ahead
+      if (lane > k + 1 && lane < p) n0 = L[(k + 1) * p + lane];
+      if (lane + 32 > k + 1 && lane + 32 < p) n1 = L[(k + 1) * p + lane + 32];
+      s[0] = ubm_fma(c0, yk, s[0]);                                                // rows <= k hold c = 0: s stays untouched where it matters
+      s[1] = ubm_fma(c1, yk, s[1]);
+      const double cand0 = -s[0] * rd[0], cand1 = -s[1] * rd[1];
+      yk = __shfl_sync(0xffffffffu, (k + 1 >= 32) ? cand1 : cand0, (k + 1) & 31);
+      c0 = n0; c1 = n1;
     }
   }
-  __syncwarp();
 }
 // S = Li' Li (both triangles), S[a,c] = sum_{i >= c} Li(i,a) Li(i,c), c >= a; entries strided over `nthr` threads
 __device__ inline void pg_ltl(const double* Li, double* S, int p, int t, int nthr) {
@@ -389,29 +401,46 @@ struct PgShared {   // scalars
   int eq;                          // replay: all w pairs equal
 };
 
-// Gram build for one or two chains: A_c[j2, j1] (lower) = invB[j1, j2] + sum_i X(i,j1) X(i,j2) w_c[i].
-// Register-tiled: a thread owns a 4 x 4 block of entries (column blocks bj1 <= bj2) for one of four interleaved
-// observation classes (i mod 4) and keeps its 16 (+16) sums in registers; per observation it reads two 32-byte row
-// segments of the staged X tile and the weights.  Canonical order (oracle: m_sigma): four chains over i mod 4, each
-// sequential in i, then ((((invB + P0) + P1) + P2) + P3).
-#define PG_PLIM 60               // 4 classes x nb (nb + 1) / 2 blocks must fit the 512 threads: ceil(p / 4) <= 15
-template <bool TWO>
+// Gram build for one or two chains: A_c[j2, j1] (lower) = invB[j1, j2] + sum_i (X(i,j1) w_c[i]) X(i,j2), j1 <= j2, on the
+// FP64 tensor pipe: 8 x 8 output tiles (tile row <= tile column), mma.m8n8k4 over groups of four observations.  A DMMA
+// accumulates its four products as an fma chain in observation order (tools/dmma_probe.cu), so an entry's sum is exactly
+// the oracle's (m_sigma): four chains over the observation groups g = i / 4 taken by class g mod 4, each sequential in
+// i, every term one fma of the rounded product X(i,j1) w[i] with X(i,j2); then ((((invB + P0) + P1) + P2) + P3).
+// Warp w holds class w mod 4 of the tiles of subset w / 4 (row-major runs of the tile list) in registers: at most
+// PG_MAXTL accumulators of two doubles per chain.  Operands come from the staged 32-observation tile of the padded
+// row-major copy of X (row stride 68 doubles: the fragment loads of a half-warp hit 16 distinct bank pairs).
+#define PG_PLIM 60               // ceil(p / 8) <= 8 tile rows: 36 tiles, 9 per subset (PG_MAXTL = 9; 7 up to p = 56, the German-credit size)
+__device__ __forceinline__ void pg_dmma(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+#ifdef UBM_PG_TIMING
+static __device__ long long g_pg_gt[4];
+#endif
+template <bool TWO, int PG_MAXTL>
 __device__ inline void pg_gram(const PgDevice& M, const double* w1, const double* w2, double* A1, double* A2,
                                double* xs /* [2][PG_TILE][PG_GS] */, int tid) {
   const int n = M.n, p = M.p;
-  const int nb = (p + 3) / 4, nblk = nb * (nb + 1) / 2;
-  const int cls = tid / nblk, blk = tid - cls * nblk;
-  const bool on = cls < 4;
-  int bj1 = 0, rem = on ? blk : 0;
-  while (rem >= nb - bj1) { rem -= nb - bj1; ++bj1; }
-  const int bj2 = bj1 + rem;
-  double a1[4][4], a2[4][4];
+  const int lane = tid & 31, warp = tid >> 5;
+  const int cls = warp & 3, sub = warp >> 2;
+  const int nt = (p + 7) / 8, ntile = nt * (nt + 1) / 2, per = (ntile + 3) / 4;
+  const int t0 = sub * per, cnt = (ntile - t0 < per) ? ((ntile - t0 > 0) ? ntile - t0 : 0) : per;
+  // this warp's tiles: (ta, tb) of tile t0 + t in row-major order of the upper triangle of tiles
+  int ta[PG_MAXTL], tb[PG_MAXTL];
+  {
+    int a = 0, rem = t0;
+    while (a < nt && rem >= nt - a) { rem -= nt - a; ++a; }
+    int b = a + rem;
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+    for (int t = 0; t < PG_MAXTL; ++t) {
+      ta[t] = (a < nt) ? a : 0; tb[t] = (a < nt) ? b : 0;
+      if (++b >= nt) { ++a; b = a; }
+    }
+  }
+  double a1[PG_MAXTL][2], a2[PG_MAXTL][2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { a1[r][c] = 0.0; a2[r][c] = 0.0; }
-  // tiles of 32 observations, double-buffered: the next tile is fetched into registers (three 16-byte loads per thread
-  // from the row-major padded copy of X) before the current one is consumed, and stored afterwards
+  for (int t = 0; t < PG_MAXTL; ++t) { a1[t][0] = a1[t][1] = 0.0; a2[t][0] = a2[t][1] = 0.0; }
+  const int kk = lane & 3, rr = lane >> 2;                // fragment coordinates: observation kk of the group, column rr of the tile
+  // tiles of 32 observations of the row-major padded copy of X, double-buffered in shared memory
   constexpr int NV = PG_TILE * PG_GS / 2;                 // double2 per tile
   constexpr int PER = (NV + PG_T - 1) / PG_T;
   __syncthreads();
@@ -426,57 +455,73 @@ __device__ inline void pg_gram(const PgDevice& M, const double* w1, const double
     const int rows = (n - i0 < PG_TILE) ? (n - i0) : PG_TILE;
     const double* xt = xs + buf * (PG_TILE * PG_GS);
     const bool more = i0 + PG_TILE < n;
-    double2 nxt[PER];
-    if (more) {
+#ifdef UBM_PG_TIMING
+    long long tg0 = clock64();
+#endif
+    if (more) {     // the next tile goes straight from L2 to the other buffer (cp.async: no registers, no wait here)
       const double2* src = reinterpret_cast<const double2*>(M.Xt + (size_t)(i0 + PG_TILE) * PG_GS);
-#pragma unroll
-      for (int u = 0; u < PER; ++u) { const int q = tid + u * PG_T; nxt[u] = (q < NV) ? src[q] : make_double2(0.0, 0.0); }
-    }
-    if (on) {
-      for (int ii = cls; ii < rows; ii += 4) {
-        const double wa = w1[i0 + ii];
-        const double wb = TWO ? w2[i0 + ii] : 0.0;
-        const double2 xa0 = *reinterpret_cast<const double2*>(xt + ii * PG_GS + 4 * bj1);
-        const double2 xa1 = *reinterpret_cast<const double2*>(xt + ii * PG_GS + 4 * bj1 + 2);
-        const double2 xb0 = *reinterpret_cast<const double2*>(xt + ii * PG_GS + 4 * bj2);
-        const double2 xb1 = *reinterpret_cast<const double2*>(xt + ii * PG_GS + 4 * bj2 + 2);
-        const double xa[4] = {xa0.x, xa0.y, xa1.x, xa1.y}, xb[4] = {xb0.x, xb0.y, xb1.x, xb1.y};
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const double z = xa[r] * xb[c];
-            a1[r][c] = ubm_fma(z, wa, a1[r][c]);
-            if (TWO) a2[r][c] = ubm_fma(z, wb, a2[r][c]);
-          }
-      }
-    }
-    if (more) {
       double2* dst = reinterpret_cast<double2*>(xs + (buf ^ 1) * (PG_TILE * PG_GS));
 #pragma unroll
-      for (int u = 0; u < PER; ++u) { const int q = tid + u * PG_T; if (q < NV) dst[q] = nxt[u]; }
+      for (int u = 0; u < PER; ++u) {
+        const int q = tid + u * PG_T;
+        if (q < NV) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"((unsigned)__cvta_generic_to_shared(dst + q)), "l"(src + q));
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
     }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int g = cls + 4 * h;                          // this warp's groups of the tile: local groups cls and cls + 4
+      if (4 * g < rows) {
+        const int ii = 4 * g + kk;                        // rows past n are zero in the padded copy
+        const double* xr = xt + ii * PG_GS + rr;
+        const double wa = (i0 + ii < n) ? w1[i0 + ii] : 0.0;
+        const double wb = (TWO && i0 + ii < n) ? w2[i0 + ii] : 0.0;
+        double xa = 0.0, ya = 0.0, yb = 0.0;
+        int last = -1;
+#pragma unroll
+        for (int t = 0; t < PG_MAXTL; ++t) {
+          if (t < cnt) {
+            if (ta[t] != last) { last = ta[t]; xa = xr[8 * last]; ya = xa * wa; if (TWO) yb = xa * wb; }
+            const double xb = xr[8 * tb[t]];
+            pg_dmma(a1[t][0], a1[t][1], ya, xb);
+            if (TWO) pg_dmma(a2[t][0], a2[t][1], yb, xb);
+          }
+        }
+      }
+    }
+#ifdef UBM_PG_TIMING
+    long long tg1 = clock64();
+#endif
+    if (more) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#ifdef UBM_PG_TIMING
+    long long tg2 = clock64();
+#endif
     __syncthreads();
+#ifdef UBM_PG_TIMING
+    if (tid == 0 && blockIdx.x == 0) { long long tg3 = clock64(); g_pg_gt[0] += tg1 - tg0; g_pg_gt[1] += tg2 - tg1; g_pg_gt[2] += tg3 - tg2; g_pg_gt[3] += 1; }
+#endif
   }
-  // ((((invB + P0) + P1) + P2) + P3): the four classes add their sums in turn
+  // ((((invB + P0) + P1) + P2) + P3): the four classes add their sums in turn.  Accumulator fragment: rows rr, columns 2 kk + {0, 1}
   for (int turn = 0; turn < 4; ++turn) {
     __syncthreads();
-    if (on && cls == turn) {
+    if (cls == turn) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int t = 0; t < PG_MAXTL; ++t)
+        if (t < cnt) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int j1 = 4 * bj1 + r, j2 = 4 * bj2 + c;
-          if (j1 <= j2 && j2 < p) {
-            const double base = (turn == 0) ? M.invB[(size_t)j2 * p + j1] : A1[j1 * p + j2];
-            const double v1 = base + a1[r][c];
-            A1[j1 * p + j2] = v1;
-            if (turn == 3) A1[j2 * p + j1] = v1;
-            if (TWO) {
-              const double base2 = (turn == 0) ? M.invB[(size_t)j2 * p + j1] : A2[j1 * p + j2];
-              const double v2 = base2 + a2[r][c];
-              A2[j1 * p + j2] = v2;
-              if (turn == 3) A2[j2 * p + j1] = v2;
+          for (int c = 0; c < 2; ++c) {
+            const int j1 = 8 * ta[t] + rr, j2 = 8 * tb[t] + 2 * kk + c;
+            if (j1 <= j2 && j2 < p) {
+              const double base = (turn == 0) ? M.invB[(size_t)j2 * p + j1] : A1[j1 * p + j2];
+              const double v1 = base + a1[t][c];
+              A1[j1 * p + j2] = v1;
+              if (turn == 3) A1[j2 * p + j1] = v1;
+              if (TWO) {
+                const double base2 = (turn == 0) ? M.invB[(size_t)j2 * p + j1] : A2[j1 * p + j2];
+                const double v2 = base2 + a2[t][c];
+                A2[j1 * p + j2] = v2;
+                if (turn == 3) A2[j2 * p + j1] = v2;
+              }
             }
           }
         }
@@ -545,6 +590,11 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
       if (P.h_kind == UBM_H_IDENTITY) acc[tid] = x;
       else if (P.h_kind == UBM_H_SQUARE) acc[tid] = x * x;
       else { acc[tid] = x; acc[p + tid] = x * x; }
+      if (P.nbreaks >= 2 && tid == P.component) {       // estimator_bin_ numerators (src/estimator_bin.cpp:15-38)
+        const int nb = P.nbreaks - 1;
+        const int b = bin_of(x, P.breaks, P.nbreaks, P.breaks[0], (double)nb / (P.breaks[nb] - P.breaks[0]));
+        if (b >= 0) P.bin_num[rep * nb + b] += 1;
+      }
     }
     if (P.mode == MODE_CHAINS && tid < p) {
       P.samples1[(rep * P.stride) * p + tid] = beta1[tid];
@@ -702,25 +752,41 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
       all_equal = __syncthreads_and(all_equal);
       PGMARK(0);
       // ---- 2. Gram build(s)
-      if (coupled_step) pg_gram<true>(M, w1, w2, MA1, MA2, xs, tid);
-      else pg_gram<false>(M, w1, w2, MA1, MA2, xs, tid);
+      if (p <= 56) {
+        if (coupled_step) pg_gram<true, 7>(M, w1, w2, MA1, MA2, xs, tid);
+        else pg_gram<false, 7>(M, w1, w2, MA1, MA2, xs, tid);
+      } else {
+        if (coupled_step) pg_gram<true, 9>(M, w1, w2, MA1, MA2, xs, tid);
+        else pg_gram<false, 9>(M, w1, w2, MA1, MA2, xs, tid);
+      }
       PGMARK(1);
       // ---- 3. m, L, Linv per chain (warp 0: chain 1, warp 1: chain 2)
       pg_cta_chol(MA1, coupled_step ? MA2 : nullptr, tmp, p, tid);   // src/logisticregression.cpp:49-50 (tmp, zz: scratch)
       PGMARK(3);
-      if (warp < 2 && (warp == 0 || coupled_step)) {             // warp 0: chain 1, warp 1: chain 2
-        double* A = warp ? MA2 : MA1;
-        double* Linv = warp ? MB2 : MB1;
-        double* m = warp ? m2 : m1;
-        for (int i = lane; i < p; i += 32) m[i] = M.ktk[i];
-        __syncwarp();
-        pg_warp_forward(A, p, lane, m);                          // :51  L y = b
-        pg_warp_backward(A, p, lane, m);                         //      L' x = y
-        PGMARK(4);
-        pg_warp_tri_inverse(A, Linv, p, lane);                   // :55
-        PGMARK(5);
+      // :55 lower.inverse(): the columns of both factors over all warps
+      pg_tri_inverse_cols(MA1, MB1, coupled_step ? MA2 : nullptr, MB2, p, warp, lane, 0, PG_T / 32);
+      __syncthreads();
+      PGMARK(5);
+      // :51 m = A^-1 b through the inverse factor: y = Linv b, m = Linv' y (independent dot products; oracle: m_sigma)
+      {
+        const int ch = tid >> 6, i = tid & 63;                     // threads 0..63: chain 1, 64..127: chain 2
+        const bool on = ch < (coupled_step ? 2 : 1) && i < p;
+        const double* Li = ch ? MB2 : MB1;
+        double* yv = tmp + ch * PG_MAXP;
+        if (on) {
+          double a = 0.0;
+          for (int k = 0; k <= i; ++k) a = ubm_fma(Li[k * p + i], M.ktk[k], a);
+          yv[i] = a;
+        }
+        __syncthreads();
+        if (on) {
+          double a = 0.0;
+          for (int r = i; r < p; ++r) a = ubm_fma(Li[i * p + r], yv[r], a);
+          (ch ? m2 : m1)[i] = a;
+        }
       }
       __syncthreads();
+      PGMARK(4);
       if (!coupled_step) {
         // single kernel: beta = fast_rmvnorm_chol(1, m, Linv) (germancredit.run.R:27-28): y_j = sum_{i >= j} z_i Linv(i, j)
         if (warp == 0) {
@@ -808,6 +874,19 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
             if (in_window) acc[e] = acc[e] + h1;
             if (corr_now) { const double h2 = sq ? xb * xb : xb; acc[2 * PG_MAXP + e] = acc[2 * PG_MAXP + e] + wgt * (h1 - h2); }
           }
+          if (P.nbreaks >= 2 && tid == P.component) {   // the component's histogram: this thread is the only writer of the row
+            const int nb = P.nbreaks - 1;
+            const double b0 = P.breaks[0], iw = (double)nb / (P.breaks[nb] - P.breaks[0]);
+            long long* bn = P.bin_num + rep * nb;
+            const int b1 = bin_of(xa, P.breaks, P.nbreaks, b0, iw);
+            if (in_window && b1 >= 0) bn[b1] += 1;
+            if (corr_now) {
+              const long long w = corr_weight(time, P.k, P.m, P.lag);
+              const int b2 = bin_of(xb, P.breaks, P.nbreaks, b0, iw);
+              if (b1 >= 0) bn[b1] += w;
+              if (b2 >= 0) bn[b2] -= w;
+            }
+          }
         } else if (P.mode == MODE_CHAINS) {
           P.samples1[(rep * P.stride + time) * p + tid] = xa;
           if (time > P.lag) P.samples2[(rep * P.stride + (time - P.lag)) * p + tid] = xb;
@@ -816,6 +895,9 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
     }
     __syncthreads();
 #ifdef UBM_PG_TIMING
+    if (tid == 0 && blockIdx.x == 0)
+      printf("gram tile iterations %lld: dmma section %.0f store %.0f barrier %.0f cycles each\n", g_pg_gt[3], (double)g_pg_gt[0] / g_pg_gt[3],
+             (double)g_pg_gt[1] / g_pg_gt[3], (double)g_pg_gt[2] / g_pg_gt[3]);
     if (tid == 0 && blockIdx.x == 0)
       printf("pg timing (cycles/step, block 0): steps %lld coupled %lld pg-sweep %.0f gram %.0f | chol %.0f solves %.0f tri-inverse %.0f rest(sample, coupled linalg) %.0f\n", tsteps,
              tcoupled, (double)tacc[0] / tsteps, (double)tacc[1] / tsteps, (double)tacc[3] / tsteps, (double)tacc[4] / tsteps,
@@ -850,7 +932,6 @@ inline size_t pg_smem_bytes(int n, int p) {
 
 inline int pg_launch(const PgDevice& M, const RunParams& P, bool tape, int nsm, cudaStream_t st, int64_t* launches,
                      std::string* err) {
-  if (P.nbreaks >= 2) { *err = "pg logistic: histogram bins are not available for this model yet"; return UBM_ERR_UNSUPPORTED; }
   const size_t smem = pg_smem_bytes(M.n, M.p);
   if (smem > 227 * 1024) { *err = "pg logistic: n / p too large for shared memory"; return UBM_ERR_UNSUPPORTED; }
   auto kern = tape ? pg_driver_kernel<true> : pg_driver_kernel<false>;

@@ -505,6 +505,16 @@ __global__ void __launch_bounds__(32 * VS_WPB, VS_MINB) varsel_driver_kernel(con
           P.uest[rep * p + j] = ue / denom;
           if (P.mcmc) P.mcmc[rep * p + j] = mc / denom;
           if (P.corr) P.corr[rep * p + j] = co / denom;
+          if (P.nbreaks >= 2 && j == P.component) {
+            // estimator_bin_ numerators (src/estimator_bin.cpp:15-38) of a 0/1 coordinate, in closed form: it was 1 at c of the
+            // window's `terms` times and 0 at the others; every correction term moves its weight between the two values
+            const int nb = P.nbreaks - 1;
+            const double b0 = P.breaks[0], iw = (double)nb / (P.breaks[nb] - P.breaks[0]);
+            const long long terms = E.window(0, time);
+            const int bin1 = bin_of(1.0, P.breaks, P.nbreaks, b0, iw), bin0 = bin_of(0.0, P.breaks, P.nbreaks, b0, iw);
+            if (bin1 >= 0) P.bin_num[rep * nb + bin1] += c + E.corr[j];
+            if (bin0 >= 0) P.bin_num[rep * nb + bin0] += (terms - c) - E.corr[j];
+          }
         }
       }
     }
@@ -529,7 +539,6 @@ inline size_t varsel_smem_bytes(int s0) {      // per CTA
 template <class Buf>
 inline int varsel_launch(const VarselDevice& M, const RunParams& P, bool tape, int nsm, cudaStream_t st, Buf& scratch,
                          int64_t* launches, std::string* err) {
-  if (P.nbreaks >= 2) { *err = "variable selection: histogram bins are not available for this model"; return UBM_ERR_UNSUPPORTED; }
   if (P.mode == MODE_ESTIMATOR && P.h_kind != UBM_H_IDENTITY) { *err = "variable selection: h must be the identity (inclusion indicators)"; return UBM_ERR_UNSUPPORTED; }
   const size_t smem = varsel_smem_bytes(M.s0);
   auto kern = tape ? varsel_driver_kernel<true> : varsel_driver_kernel<false>;
