@@ -358,6 +358,7 @@ def main():
                                "dram traffic of the driver kernel is a few KB per launch, see profiles/)")
     roofline["fp64_tflops_measured"] = peaks["fp64_tflops"]
     roofline["int32_tops_measured"] = peaks["int32_tops"]
+    roofline["fp64_tensor_tflops_measured"] = peaks["fp64_tensor_tflops"]   # mma.m8n8k4.f64 chains: the same pipe, the same peak
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(mp):
         roofline["hbm_gbs_measured_peak"] = json.load(open(mp)).get("hbm_gbs")

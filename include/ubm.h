@@ -49,6 +49,12 @@ int64_t ubm_launch_count(const ubm_handle* h);
 /* live roofline denominators that MEASURED_PEAKS.json lacks: FP64 FMA TFLOP/s (2 flop per fma) and INT32
  * multiply-add Top/s, from saturating micro-kernels on this device */
 int ubm_measure_peaks(ubm_handle* h, double* fp64_tflops, double* int32_tops);
+/* Ising parallel tempering: the swap-move counters the reference's kernels return (R/ising.R:48-49,52,60,76 and :89-91,95,
+ * 108,118,137-140), summed over every replicate and iteration of the LAST run of that model on this handle:
+ * swap-move iterations, accepted swaps of chain 1 and of chain 2 per adjacent pair [nchains - 1] (any pointer may be NULL) */
+int ubm_ising_swap_counts(ubm_handle* h, int64_t* nswap_attempts, int64_t* nswap_accepts1, int64_t* nswap_accepts2);
+/* the same for the FP64 tensor pipe (mma.m8n8k4.f64, 2 flop per fma): the pipe of C2's triangular products and C3's Gram */
+int ubm_measure_fp64_tensor_peak(ubm_handle* h, double* fp64_tensor_tflops);
 
 /* ---------------------------------------------------------------------------------------------
  * draw sources.  Replaces R's global RNG stream (GetRNGstate/PutRNGstate brackets, e.g.
@@ -287,6 +293,20 @@ int ubm_rnorm_max_coupling(ubm_handle* h, const ubm_draws* draws, int64_t n, int
                            double sigma1, double sigma2, double* xy, int32_t* identical);
 int ubm_rnorm_reflectionmax(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, double mu1, double mu2,
                             double sigma, double* xy, int32_t* identical);
+/* the other scalar maximal couplings, all through R/get_max_coupling.R:24-39; xy [n][2], identical [n]:
+ *   ubm_rgamma_coupled           R/gamma_couplings.R:14-21     Gamma(alpha, rate beta)
+ *   ubm_rinversegamma_coupled    R/invgamma_couplings.R:29-36  (dinversegamma :7-9, rinversegamma :17-19)
+ *   ubm_rinvgaussian_coupled     src/inversegaussian.cpp:33-63 (rinvgaussian_c :6-25, dinvgaussian_c :27-29)
+ *   ubm_rpositive                n plain draws: kind 0 rgamma(shape a, rate b), 1 rinversegamma, 2 rinvgaussian(mu a, lambda b)
+ * The inverse-Gaussian sampler is the reference's, draw for draw.  R's rgamma belongs to the R runtime: Gamma draws are
+ * Marsaglia-Tsang on the typed streams (a replay tape reproduces this engine's draws, not R's). */
+int ubm_rgamma_coupled(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, double alpha1, double alpha2,
+                       double beta1, double beta2, double* xy, int32_t* identical);
+int ubm_rinversegamma_coupled(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, double alpha1, double alpha2,
+                              double beta1, double beta2, double* xy, int32_t* identical);
+int ubm_rinvgaussian_coupled(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, double mu1, double mu2,
+                             double lambda1, double lambda2, double* xy, int32_t* identical);
+int ubm_rpositive(ubm_handle* h, const ubm_draws* draws, int32_t kind, int64_t n, int64_t rep_offset, double a, double b, double* out);
 int ubm_rmvnorm_reflectionmax(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d,
                               const double* mu1, const double* mu2, const double* chol, const double* chol_inv,
                               double* xy, int32_t* identical);
@@ -301,6 +321,12 @@ int ubm_fast_rmvnorm_chol(ubm_handle* h, const ubm_draws* draws, int64_t n, int6
                           const double* mean, const double* chol, double* out);
 int ubm_fast_dmvnorm_chol_inverse(ubm_handle* h, int64_t n, int32_t d, const double* x, const double* mean,
                                   const double* chol_inv, double* out);
+/* covariance forms: fast_rmvnorm_ (src/mvnorm.cpp:9-26; R/mvnorm.R:12) and fast_dmvnorm_ (:49-67; R/mvnorm.R:48).  The LLT of
+ * the covariance (column-major, d x d) is taken on the host, then the factor forms above run; not positive definite: UBM_ERR_INVALID */
+int ubm_fast_rmvnorm(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d, const double* mean,
+                     const double* covariance, double* out);
+int ubm_fast_dmvnorm(ubm_handle* h, int64_t n, int32_t d, const double* x, const double* mean, const double* covariance,
+                     double* out);
 
 /* ---------------------------------------------------------------------------------------------
  * device-resident variant used for kernel-only timing (bench.py `value`): the model is uploaded once,

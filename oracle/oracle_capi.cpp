@@ -8,6 +8,7 @@
 #include <thread>
 #include "oracle_models.hpp"
 #include "oracle_more.hpp"
+#include "oracle_scalar.hpp"
 
 using namespace orc;
 
@@ -263,6 +264,39 @@ int orc_rnorm_coupling(int32_t mode, const ubm_draws* draws, int64_t n, int64_t 
     if (mode == 0) id = M.reflmax(mu1, mu2, s1, D, &xy[2 * i], &xy[2 * i + 1]);
     else id = M.maxcoupling(mu1, mu2, s1, ubm_log(s1), s2, ubm_log(s2), D, &xy[2 * i], &xy[2 * i + 1]);
     identical[i] = id ? 1 : 0;
+    if (D.exhausted) bad = 1;
+  }
+  return bad ? UBM_ERR_TAPE : UBM_OK;
+}
+
+// covariance forms (src/mvnorm.cpp:9-26, :49-67): LLT by PgLogisticModel::chol_lower, then the factor forms.  `which` 0: the
+// upper factor U (column-major) of the covariance, 1: its inverse
+int orc_cov_factor(int32_t which, int32_t d, const double* covariance, double* out) {
+  std::vector<double> L(covariance, covariance + (size_t)d * d);
+  bool ok = true;
+  PgLogisticModel::chol_lower(L, d, &ok);
+  if (!ok) return UBM_ERR_INVALID;
+  std::vector<double> T = which ? PgLogisticModel::tri_inverse(L, d) : L;
+  for (int j = 0; j < d; ++j) for (int i = 0; i < d; ++i) out[(size_t)j * d + i] = (i <= j) ? T[(size_t)i * d + j] : 0.0;
+  return UBM_OK;
+}
+
+void orc_ising_swap_counts(int32_t reset, int64_t* out63) {
+  for (int i = 0; i < 63; ++i) { if (out63) out63[i] = g_ising_pt[i].load(); if (reset) g_ising_pt[i] = 0; }
+}
+
+// kind 0 Gamma, 1 inverse Gamma, 2 inverse Gaussian; mode 0: n plain draws of the first distribution, 1: coupled pairs
+int orc_positive_coupling(int32_t kind, int32_t mode, const ubm_draws* draws, int64_t n, int64_t rep_offset, double a1,
+                          double a2, double b1, double b2, double* out, int32_t* identical) {
+  const double c1 = (kind == 2) ? 0.0 : a1 * ubm_log(b1) - std::lgamma(a1), c2 = (kind == 2) ? 0.0 : a2 * ubm_log(b2) - std::lgamma(a2);
+  int bad = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    Draws D = make_draws(draws, i, rep_offset);
+    if (mode == 0) {
+      out[i] = (kind == 0) ? rgamma_mt(a1, b1, D) : (kind == 1) ? 1.0 / rgamma_mt(a1, b1, D) : rinvgaussian1(a1, b1, D);
+    } else {
+      identical[i] = positive_max_coupling(kind, a1, a2, b1, b2, c1, c2, D, &out[2 * i], &out[2 * i + 1]) ? 1 : 0;
+    }
     if (D.exhausted) bad = 1;
   }
   return bad ? UBM_ERR_TAPE : UBM_OK;

@@ -6,10 +6,15 @@
 // the vector of natural statistics (one per temperature), as in ising_unbiased_estimator (R/ising.R:148-240),
 // whose lag-1 weights min(1,(t-k)/(m-k+1)) equal the generic driver's.
 #pragma once
+#include <atomic>
 #include <cstring>
 #include "oracle_core.hpp"
 
 namespace orc {
+
+// swap-move counters of the reference's kernels (R/ising.R:48-49,76 / :89-91,137-140), summed over everything run since the
+// last reset: [0] swap-move iterations, [1 .. 31] accepted swaps of chain 1 per pair, [32 .. 62] of chain 2
+inline std::atomic<long long> g_ising_pt[64];
 
 struct IsingModel {
   static const int SZ = 32;
@@ -95,10 +100,11 @@ struct IsingModel {
   void single(State& s, Draws& D) const {
     double u_iteration = D.u();
     if (u_iteration < pswap) {
+      g_ising_pt[0] += 1;
       for (int c = 0; c + 1 < N; ++c) {
         double logprob = (betas[c] - betas[c + 1]) * (s.sums[c + 1] - s.sums[c]);   // :55-56
         double u = D.u();
-        if (ubm_log(u) < logprob) swap_lattices(s, c);
+        if (ubm_log(u) < logprob) { swap_lattices(s, c); g_ising_pt[1 + c] += 1; }
       }
     } else {
       D.align_u4();
@@ -110,13 +116,14 @@ struct IsingModel {
   bool coupled(State& s1, State& s2, Draws& D) const {
     double u_iteration = D.u();
     if (u_iteration < pswap) {
+      g_ising_pt[0] += 1;
       for (int c = 0; c + 1 < N; ++c) {
         double deltabeta = betas[c] - betas[c + 1];
         double lp1 = deltabeta * (s1.sums[c + 1] - s1.sums[c]);
         double lp2 = deltabeta * (s2.sums[c + 1] - s2.sums[c]);
         double logu = ubm_log(D.u());
-        if (logu < lp1) swap_lattices(s1, c);
-        if (logu < lp2) swap_lattices(s2, c);
+        if (logu < lp1) { swap_lattices(s1, c); g_ising_pt[1 + c] += 1; }
+        if (logu < lp2) { swap_lattices(s2, c); g_ising_pt[32 + c] += 1; }
       }
     } else {
       D.align_u4();

@@ -262,6 +262,51 @@ def rnorm_max_coupling(mu1, mu2, sigma1, sigma2, draws, n=1, rep_offset=0):
     return {"xy": xy, "identical": ident.astype(bool)}
 
 
+def ising_swap_counts(nchains, reset=True):
+    out = np.zeros(63, dtype=np.int64)
+    L = lib()
+    L.orc_ising_swap_counts.argtypes = [C.c_int32, C.POINTER(C.c_int64)]
+    L.orc_ising_swap_counts.restype = None
+    L.orc_ising_swap_counts(1 if reset else 0, out.ctypes.data_as(C.POINTER(C.c_int64)))
+    return {"nswap_attempts": int(out[0]), "nswap_accepts1": out[1:nchains], "nswap_accepts2": out[32:31 + nchains]}
+
+
+def _positive(kind, mode, a1, a2, b1, b2, draws, n, rep_offset):
+    L = _prim_lib()
+    L.orc_positive_coupling.argtypes = [C.c_int32, C.c_int32, C.POINTER(A.ubm_draws), C.c_int64, C.c_int64,
+                                        C.c_double, C.c_double, C.c_double, C.c_double, A.c_double_p, A.c_int32_p]
+    L.orc_positive_coupling.restype = C.c_int
+    out = np.zeros((n, 2)) if mode == 1 else np.zeros(n)
+    ident = np.zeros(n, dtype=np.int32)
+    ds = draws.struct(n)
+    _check(L.orc_positive_coupling(kind, mode, C.byref(ds), n, rep_offset, a1, a2, b1, b2, A.dptr(out), A.i32ptr(ident)))
+    return {"xy": out, "identical": ident.astype(bool)} if mode == 1 else out
+
+
+def rgamma_coupled(alpha1, alpha2, beta1, beta2, draws, n=1, rep_offset=0):
+    return _positive(0, 1, alpha1, alpha2, beta1, beta2, draws, n, rep_offset)
+
+
+def rinversegamma_coupled(alpha1, alpha2, beta1, beta2, draws, n=1, rep_offset=0):
+    return _positive(1, 1, alpha1, alpha2, beta1, beta2, draws, n, rep_offset)
+
+
+def rinvgaussian_coupled(mu1, mu2, lambda1, lambda2, draws, n=1, rep_offset=0):
+    return _positive(2, 1, mu1, mu2, lambda1, lambda2, draws, n, rep_offset)
+
+
+def rgamma(n, shape, rate, draws, rep_offset=0):
+    return _positive(0, 0, shape, shape, rate, rate, draws, n, rep_offset)
+
+
+def rinversegamma(n, alpha, beta, draws, rep_offset=0):
+    return _positive(1, 0, alpha, alpha, beta, beta, draws, n, rep_offset)
+
+
+def rinvgaussian(n, mu, lam, draws, rep_offset=0):
+    return _positive(2, 0, mu, mu, lam, lam, draws, n, rep_offset)
+
+
 def rnorm_reflectionmax(mu1, mu2, sigma, draws, n=1, rep_offset=0):
     xy, ident = np.zeros((n, 2)), np.zeros(n, dtype=np.int32)
     ds = draws.struct(n)
@@ -311,6 +356,26 @@ def fast_rmvnorm_chol(nparticles, mean, chol, draws, rep_offset=0):
     _check(_prim_lib().orc_mvn_sample(0, C.byref(ds), nparticles, rep_offset, d, A.dptr(mean), A.dptr(None), A.dptr(ch),
                                       A.dptr(None), A.dptr(out), A.i32ptr(None)))
     return out
+
+
+def _cov_factor(which, covariance):
+    cov = np.asarray(covariance, dtype=np.float64)
+    d = cov.shape[0]
+    flat = _cm(cov)
+    out = np.zeros(d * d)
+    L = lib()
+    L.orc_cov_factor.argtypes = [C.c_int32, C.c_int32, A.c_double_p, A.c_double_p]
+    L.orc_cov_factor.restype = C.c_int
+    _check(L.orc_cov_factor(which, d, A.dptr(flat), A.dptr(out)))
+    return out.reshape(d, d).T           # column-major -> the matrix
+
+
+def fast_rmvnorm(nparticles, mean, covariance, draws, rep_offset=0):
+    return fast_rmvnorm_chol(nparticles, mean, _cov_factor(0, covariance), draws, rep_offset)
+
+
+def fast_dmvnorm(x, mean, covariance):
+    return fast_dmvnorm_chol_inverse(x, mean, _cov_factor(1, covariance))
 
 
 def fast_dmvnorm_chol_inverse(x, mean, chol_inverse):

@@ -103,3 +103,18 @@ def test_c4_replay_tape_two_replicates_per_warp(engine, oracle):
     g = engine.sample_unbiasedestimator(mdl, draws, k=2, m=8, lag=1, max_iterations=steps, nrep=nrep)
     c = oracle.sample_unbiasedestimator(mdl, draws, k=2, m=8, lag=1, max_iterations=steps, nrep=nrep)
     assert_same(g, c, KEYS)
+
+
+def test_c4_swap_counters(engine, oracle):
+    """nswap_attempts / nswap_accepts1 / nswap_accepts2 of the PT kernels (R/ising.R:48-49,76,89-91,137-140), summed over a run"""
+    mdl = cases.c4_model(6, 0.3, 0.25, 0.45)
+    kw = dict(k=5, m=40, lag=2, nrep=37, max_iterations=200)
+    oracle.ising_swap_counts(6, reset=True)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=31), nthreads=8, **kw)
+    want = oracle.ising_swap_counts(6, reset=True)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=31), **kw)
+    got = engine.ising_swap_counts(6)
+    assert_same(g, c, KEYS)
+    assert got["nswap_attempts"] == want["nswap_attempts"] > 0
+    assert np.array_equal(got["nswap_accepts1"], want["nswap_accepts1"]) and got["nswap_accepts1"].sum() > 0
+    assert np.array_equal(got["nswap_accepts2"], want["nswap_accepts2"]) and got["nswap_accepts2"].sum() > 0

@@ -103,3 +103,24 @@ def test_tv_upper_bounds_bit_exact(engine, oracle):
     assert np.array_equal(g, c)
     assert np.array_equal(g, np.array([api.tv_upper_bound(mt, 30, tj).mean() for tj in t]))
     assert np.all(np.diff(g) <= 0) and g[0] > 1 and g[-1] < 0.2       # slow mixing between the two modes
+
+
+@pytest.mark.parametrize("d", [1, 3, 40, 128])
+def test_covariance_forms_bit_exact(engine, oracle, d):
+    """fast_rmvnorm_ / fast_dmvnorm_ (src/mvnorm.cpp:9-26, :49-67; R/mvnorm.R:12,48): LLT on the host, factor forms on the device"""
+    rng = np.random.default_rng(d)
+    G = rng.standard_normal((d, d + 2))
+    S = G @ G.T / d + 0.5 * np.eye(d)
+    mean = rng.normal(size=d)
+    g = engine.fast_rmvnorm(300, mean, S, R.Draws(seed=5), rep_offset=3)
+    c = oracle.fast_rmvnorm(300, mean, S, R.Draws(seed=5), rep_offset=3)
+    assert np.array_equal(g, c)
+    x = rng.normal(size=(50, d))
+    assert np.array_equal(engine.fast_dmvnorm(x, mean, S), oracle.fast_dmvnorm(x, mean, S))
+    if d >= 3:
+        from scipy import stats
+        np.testing.assert_allclose(engine.fast_dmvnorm(x, mean, S), stats.multivariate_normal(mean, S).logpdf(x), rtol=1e-5, atol=1e-4)
+        bad = S.copy(); bad[0, 0] = -1.0
+        from unbiasedmcmc_b200.engine import UbmError
+        with pytest.raises(UbmError):
+            engine.fast_rmvnorm(2, mean, bad, R.Draws(seed=1))

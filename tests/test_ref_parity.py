@@ -258,6 +258,9 @@ def test_mvnorm_sampling_and_density(oracle, ref, d):
     ref.ref_fast_dmvnorm(5, d, ref_py._d(ref_py.cm(x)), ref_py._d(mean), ref_py._d(ref_py.cm(S)), ref_py._d(dens2))
     _close(dens, oracle.fast_dmvnorm_chol_inverse(x, mean, Ui))                                       # :71-86
     _close(dens2, dens)                                                                               # :49-67 (check_mvnorm.R:38-46)
+    # the covariance forms of the oracle (its own LLT) against the reference's (Eigen's LLT inside)
+    _close(out, oracle.fast_rmvnorm(1, mean, S, R.Draws(tape_n=tn[None]))[0])
+    _close(dens2, oracle.fast_dmvnorm(x, mean, S))
 
 
 @pytest.mark.parametrize("d", [2, 7, 100])

@@ -117,6 +117,14 @@ def load_lib():
     lib.ubm_launch_count.restype = C.c_int64
     lib.ubm_measure_peaks.argtypes = [vp, c_double_p, c_double_p]
     lib.ubm_measure_peaks.restype = C.c_int
+    lib.ubm_fast_rmvnorm.argtypes = [vp, C.POINTER(ubm_draws), C.c_int64, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p]
+    lib.ubm_fast_rmvnorm.restype = C.c_int
+    lib.ubm_fast_dmvnorm.argtypes = [vp, C.c_int64, C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]
+    lib.ubm_fast_dmvnorm.restype = C.c_int
+    lib.ubm_ising_swap_counts.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.ubm_ising_swap_counts.restype = C.c_int
+    lib.ubm_measure_fp64_tensor_peak.argtypes = [vp, c_double_p]
+    lib.ubm_measure_fp64_tensor_peak.restype = C.c_int
     lib.ubm_summary_len.argtypes = [C.c_int32, C.c_int32]
     lib.ubm_summary_len.restype = C.c_int64
     lib.ubm_model_dim.argtypes = [C.c_int32, vp, c_int32_p]
@@ -145,6 +153,12 @@ def load_lib():
                                             c_double_p, c_int32_p, c_int64_p]
     lib.ubm_c_chains_to_measure.restype = C.c_int
     dp = C.POINTER(ubm_draws)
+    for name in ("ubm_rgamma_coupled", "ubm_rinversegamma_coupled", "ubm_rinvgaussian_coupled"):
+        getattr(lib, name).argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                       c_double_p, C.POINTER(C.c_int32)]
+        getattr(lib, name).restype = C.c_int
+    lib.ubm_rpositive.argtypes = [vp, dp, C.c_int32, C.c_int64, C.c_int64, C.c_double, C.c_double, c_double_p]
+    lib.ubm_rpositive.restype = C.c_int
     lib.ubm_rnorm_max_coupling.argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double,
                                            C.c_double, c_double_p, c_int32_p]
     lib.ubm_rnorm_reflectionmax.argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double,

@@ -339,6 +339,54 @@ def rmvnorm_max_chol(mu1, mu2, Cholesky1, Cholesky2, Cholesky_inverse1, Cholesky
                                             R.Draws(seed=seed), n=n), n)
 
 
+def fast_rmvnorm(nparticles, mean, covariance, seed=1):
+    """R/mvnorm.R:12"""
+    return _eng().fast_rmvnorm(nparticles, mean, covariance, R.Draws(seed=seed))
+
+
+def fast_dmvnorm(x, mean, covariance):
+    """R/mvnorm.R:48"""
+    return _eng().fast_dmvnorm(x, mean, covariance)
+
+
+def rgamma_coupled(alpha1, alpha2, beta1, beta2, n=1, seed=1):
+    """R/gamma_couplings.R:14-21"""
+    return _eng().rgamma_coupled(alpha1, alpha2, beta1, beta2, R.Draws(seed=seed), n=n)
+
+
+def rinversegamma_coupled(alpha1, alpha2, beta1, beta2, n=1, seed=1):
+    """R/invgamma_couplings.R:29-36"""
+    return _eng().rinversegamma_coupled(alpha1, alpha2, beta1, beta2, R.Draws(seed=seed), n=n)
+
+
+def rinversegamma(n, alpha, beta, seed=1):
+    """R/invgamma_couplings.R:17-19"""
+    return _eng().rinversegamma(n, alpha, beta, R.Draws(seed=seed))
+
+
+def dinversegamma(x, alpha, beta):
+    """R/invgamma_couplings.R:7-9 (host arithmetic: a closed form, no device work)"""
+    from math import lgamma
+    x = np.asarray(x, dtype=np.float64)
+    return alpha * np.log(beta) - lgamma(alpha) - (alpha + 1) * np.log(x) - beta / x
+
+
+def rinvgaussian(n, mu, lam, seed=1):
+    """R/invgaussian_couplings.R:27-29 / src/inversegaussian.cpp:6-25"""
+    return _eng().rinvgaussian(n, mu, lam, R.Draws(seed=seed))
+
+
+def dinvgaussian(x, mu, lam):
+    """R/invgaussian_couplings.R:7-9"""
+    x = np.asarray(x, dtype=np.float64)
+    return 0.5 * np.log(lam / (2 * np.pi)) - 1.5 * np.log(x) - lam * (x - mu) ** 2 / (2 * mu ** 2 * x)
+
+
+def rinvgaussian_coupled(mu1, mu2, lambda1, lambda2, n=1, seed=1):
+    """R/invgaussian_couplings.R:36-38 / src/inversegaussian.cpp:33-63"""
+    return _eng().rinvgaussian_coupled(mu1, mu2, lambda1, lambda2, R.Draws(seed=seed), n=n)
+
+
 def fast_rmvnorm_chol(nparticles, mean, chol, seed=1):
     """R/mvnorm.R:32."""
     return _eng().fast_rmvnorm_chol(nparticles, mean, chol, R.Draws(seed=seed))

@@ -28,6 +28,8 @@ struct ubm_handle {
   std::string err;
   int64_t launches = 0;
   cudaDeviceProp prop{};
+  long long* pt_counts = nullptr;     // device [2 * ISING_MAXN]: swap-move counters of the last Ising run (R/ising.R:48-49,89-91)
+  int pt_n = 0;
 };
 
 static int fail(ubm_handle* h, int code, const std::string& msg) {
@@ -285,6 +287,11 @@ static int plan_run(ubm_plan* p, int draws_mode, uint64_t seed, int64_t nrep, in
   P.bin_num = p->bin_num.as<long long>();
   P.samples1 = p->samples1.as<double>(); P.samples2 = p->samples2.as<double>(); P.stride = p->stride;
   P.work_counter = p->counter.as<unsigned long long>(); P.status = p->status.as<int>();
+  if (p->model_kind == UBM_MODEL_ISING_PT) {
+    if (!h->pt_counts) CU(cudaMalloc(&h->pt_counts, 2 * ISING_MAXN * sizeof(long long)));
+    CU(cudaMemsetAsync(h->pt_counts, 0, 2 * ISING_MAXN * sizeof(long long), h->stream));
+    P.pt_counts = h->pt_counts; h->pt_n = p->ising.N;
+  }
   cudaStream_t st = h->stream;
   CU(cudaMemsetAsync(p->counter.p, 0, 8, st));
   CU(cudaMemsetAsync(p->status.p, 0, 4, st));
@@ -397,6 +404,7 @@ int ubm_create(int device, ubm_handle** out) {
 int ubm_destroy(ubm_handle* h) {
   if (!h) return UBM_OK;
   cudaSetDevice(h->device);
+  if (h->pt_counts) cudaFree(h->pt_counts);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return UBM_OK;
@@ -443,6 +451,44 @@ int ubm_measure_peaks(ubm_handle* h, double* fp64_tflops, double* int32_tops) {
   const double ops = (double)grid * threads * iters * 64.0;   // fma / imad per launch
   if (fp64_tflops) *fp64_tflops = 2.0 * ops / (best_d * 1e-3) * 1e-12;
   if (int32_tops) *int32_tops = 2.0 * ops / (best_i * 1e-3) * 1e-12;
+  return UBM_OK;
+}
+
+int ubm_measure_fp64_tensor_peak(ubm_handle* h, double* fp64_tensor_tflops) {
+  if (!h || !fp64_tensor_tflops) return UBM_ERR_INVALID;
+  CU(cudaSetDevice(h->device));
+  DevBuf out;
+  CU(out.alloc(64));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  const int grid = h->prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(e0, h->stream));
+    peak_dmma_kernel<<<grid, threads, 0, h->stream>>>(out.as<double>(), iters, 0.999999, 1e-9);
+    CU(cudaEventRecord(e1, h->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+    h->launches += 1;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  const double fma = (double)grid * (threads / 32) * iters * 8.0 * 256.0;   // 256 fma per m8n8k4
+  *fp64_tensor_tflops = 2.0 * fma / (best * 1e-3) * 1e-12;
+  return UBM_OK;
+}
+
+int ubm_ising_swap_counts(ubm_handle* h, int64_t* nswap_attempts, int64_t* nswap_accepts1, int64_t* nswap_accepts2) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!h->pt_counts || h->pt_n < 1) return fail(h, UBM_ERR_INVALID, "no Ising parallel-tempering run on this handle yet");
+  long long host[2 * ISING_MAXN];
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(host, h->pt_counts, sizeof(host), cudaMemcpyDeviceToHost));
+  if (nswap_attempts) *nswap_attempts = host[0];
+  for (int c = 0; c + 1 < h->pt_n; ++c) {
+    if (nswap_accepts1) nswap_accepts1[c] = host[1 + c];
+    if (nswap_accepts2) nswap_accepts2[c] = host[h->pt_n + c];
+  }
   return UBM_OK;
 }
 
@@ -789,6 +835,46 @@ int ubm_rnorm_reflectionmax(ubm_handle* h, const ubm_draws* draws, int64_t n, in
   return scalar_coupling(h, draws, 0, n, rep_offset, mu1, mu2, sigma, sigma, xy, identical);
 }
 
+static int positive_coupling(ubm_handle* h, const ubm_draws* draws, int kind, int mode, int64_t n, int64_t rep_offset, double a1,
+                             double a2, double b1, double b2, double* out, int32_t* identical) {
+  if (!h) return UBM_ERR_INVALID;
+  if (!out || (mode == 1 && !identical)) return fail(h, UBM_ERR_INVALID, "null output");
+  if (!(a1 > 0) || !(b1 > 0) || (mode == 1 && (!(a2 > 0) || !(b2 > 0)))) return fail(h, UBM_ERR_INVALID, "parameters must be > 0");
+  RunParams P; DevBuf tu, tn, status, dout, did;
+  int st = prim_params(h, draws, n, rep_offset, &P, &tu, &tn, &status);
+  if (st != UBM_OK) return st;
+  const double c1 = (kind == 2) ? 0.0 : a1 * ubm_log(b1) - std::lgamma(a1);
+  const double c2 = (kind == 2 || mode == 0) ? 0.0 : a2 * ubm_log(b2) - std::lgamma(a2);
+  const size_t ob = (size_t)n * 8 * (mode == 1 ? 2 : 1);
+  CU(dout.alloc(ob)); CU(did.alloc((size_t)n * 4));
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  if (draws->mode == UBM_DRAWS_TAPE)
+    prim_positive_coupling_kernel<true><<<grid, 128, 0, h->stream>>>(P, kind, mode, a1, a2, b1, b2, c1, c2, dout.as<double>(), did.as<int>());
+  else
+    prim_positive_coupling_kernel<false><<<grid, 128, 0, h->stream>>>(P, kind, mode, a1, a2, b1, b2, c1, c2, dout.as<double>(), did.as<int>());
+  h->launches += 1;
+  st = prim_finish(h, &status);
+  CU(cudaMemcpy(out, dout.p, ob, cudaMemcpyDeviceToHost));
+  if (mode == 1) CU(cudaMemcpy(identical, did.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return st;
+}
+int ubm_rgamma_coupled(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, double alpha1, double alpha2,
+                       double beta1, double beta2, double* xy, int32_t* identical) {
+  return positive_coupling(h, draws, 0, 1, n, rep_offset, alpha1, alpha2, beta1, beta2, xy, identical);
+}
+int ubm_rinversegamma_coupled(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, double alpha1, double alpha2,
+                              double beta1, double beta2, double* xy, int32_t* identical) {
+  return positive_coupling(h, draws, 1, 1, n, rep_offset, alpha1, alpha2, beta1, beta2, xy, identical);
+}
+int ubm_rinvgaussian_coupled(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, double mu1, double mu2,
+                             double lambda1, double lambda2, double* xy, int32_t* identical) {
+  return positive_coupling(h, draws, 2, 1, n, rep_offset, mu1, mu2, lambda1, lambda2, xy, identical);
+}
+int ubm_rpositive(ubm_handle* h, const ubm_draws* draws, int32_t kind, int64_t n, int64_t rep_offset, double a, double b, double* out) {
+  if (kind < 0 || kind > 2) return h ? fail(h, UBM_ERR_INVALID, "kind: 0 Gamma, 1 inverse Gamma, 2 inverse Gaussian") : UBM_ERR_INVALID;
+  return positive_coupling(h, draws, kind, 0, n, rep_offset, a, a, b, b, out, nullptr);
+}
+
 static int mvn_sample(ubm_handle* h, const ubm_draws* draws, int mode, int64_t n, int64_t rep_offset, int32_t d,
                       const double* mu1, const double* mu2, const double* chol, const double* chol_inv, double* out,
                       int32_t* identical) {
@@ -879,6 +965,46 @@ int ubm_rmvnorm_max_chol(ubm_handle* h, const ubm_draws* draws, int64_t n, int64
 int ubm_fast_rmvnorm_chol(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d,
                           const double* mean, const double* chol, double* out) {
   return mvn_sample(h, draws, 0, n, rep_offset, d, mean, nullptr, chol, nullptr, out, nullptr);
+}
+extern "C" int ubm_fast_dmvnorm_chol_inverse(ubm_handle* h, int64_t n, int32_t d, const double* x, const double* mean,
+                                             const double* chol_inv, double* out);
+// covariance forms (src/mvnorm.cpp:9-26 fast_rmvnorm_, :49-67 fast_dmvnorm_): the LLT of the covariance is taken on the host
+// (the canonical left-looking factorisation of this engine), then the factor forms run
+static int host_factor(ubm_handle* h, int32_t d, const double* covariance, std::vector<double>* L) {
+  if (!covariance) return fail(h, UBM_ERR_INVALID, "null covariance");
+  if (d < 1 || d > PRIM_MAXD) return fail(h, UBM_ERR_INVALID, "1 <= d <= 128");
+  L->assign(covariance, covariance + (size_t)d * d);
+  pg_chol_lower_host(*L, d);
+  for (int j = 0; j < d; ++j) if (!((*L)[(size_t)j * d + j] > 0.0)) return fail(h, UBM_ERR_INVALID, "covariance is not positive definite");
+  return UBM_OK;
+}
+int ubm_fast_rmvnorm(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d, const double* mean,
+                     const double* covariance, double* out) {
+  if (!h) return UBM_ERR_INVALID;
+  std::vector<double> L;
+  int st = host_factor(h, d, covariance, &L);
+  if (st != UBM_OK) return st;
+  std::vector<double> U((size_t)d * d, 0.0);                    // upper factor, column-major: U(i, j) = L(j, i)
+  for (int j = 0; j < d; ++j) for (int i = 0; i <= j; ++i) U[(size_t)j * d + i] = L[(size_t)i * d + j];
+  return mvn_sample(h, draws, 0, n, rep_offset, d, mean, nullptr, U.data(), nullptr, out, nullptr);
+}
+int ubm_fast_dmvnorm(ubm_handle* h, int64_t n, int32_t d, const double* x, const double* mean, const double* covariance,
+                     double* out) {
+  if (!h) return UBM_ERR_INVALID;
+  std::vector<double> L;
+  int st = host_factor(h, d, covariance, &L);
+  if (st != UBM_OK) return st;
+  std::vector<double> Li((size_t)d * d, 0.0), Ui((size_t)d * d, 0.0);
+  for (int j = 0; j < d; ++j) {                                 // inverse of the lower factor, reciprocal diagonal (as pg_pack_host)
+    Li[(size_t)j * d + j] = 1.0 / L[(size_t)j * d + j];
+    for (int i = j + 1; i < d; ++i) {
+      double acc = 0.0;
+      for (int k = j; k < i; ++k) acc = ubm_fma(L[(size_t)k * d + i], Li[(size_t)j * d + k], acc);
+      Li[(size_t)j * d + i] = -acc * (1.0 / L[(size_t)i * d + i]);
+    }
+  }
+  for (int j = 0; j < d; ++j) for (int i = 0; i <= j; ++i) Ui[(size_t)j * d + i] = Li[(size_t)i * d + j];   // inverse of the upper factor
+  return ubm_fast_dmvnorm_chol_inverse(h, n, d, x, mean, Ui.data(), out);
 }
 int ubm_rmvnorm_reflectionmax(ubm_handle* h, const ubm_draws* draws, int64_t n, int64_t rep_offset, int32_t d,
                               const double* mu1, const double* mu2, const double* chol, const double* chol_inv,

@@ -37,6 +37,7 @@ struct RunParams {
   // control
   unsigned long long* work_counter;   // replicate hand-out
   int* status;                        // sticky: UBM_ERR_TAPE
+  long long* pt_counts;               // Ising PT: [0] swap-move iterations, [1 .. N-1] accepted swaps of chain 1, [N .. 2N-2] of chain 2
 };
 
 // weight of Delta_t in H_{k:m}: floor((t-k)/lag) - ceiling(max(lag, t-m)/lag) + 1

@@ -337,6 +337,8 @@ __global__ void __launch_bounds__(32 * ISING_WPB, ISING_MINB) ising_driver_kerne
         __syncwarp();
         if (do_swap && c == 0) {
           const int o = slot * N;
+          unsigned long long* cnt = reinterpret_cast<unsigned long long*>(P.pt_counts);   // R/ising.R:48-49,52,60 / :89-91,95,108,118
+          if (cnt) atomicAdd(cnt, 1ull);
           for (int cc = 0; cc + 1 < N; ++cc) {
             const double deltabeta = sh.betas[cc] - sh.betas[cc + 1];
             const double logu = ubm_log(U.u(iu + (unsigned)cc));
@@ -344,12 +346,14 @@ __global__ void __launch_bounds__(32 * ISING_WPB, ISING_MINB) ising_driver_kerne
             if (logu < lp1) {
               int t = sums1[o + cc]; sums1[o + cc] = sums1[o + cc + 1]; sums1[o + cc + 1] = t;
               t = perm1[o + cc]; perm1[o + cc] = perm1[o + cc + 1]; perm1[o + cc + 1] = t;
+              if (cnt) atomicAdd(cnt + 1 + cc, 1ull);
             }
             if (coupled_step) {
               const double lp2 = deltabeta * ((double)sums2[o + cc + 1] - (double)sums2[o + cc]);
               if (logu < lp2) {
                 int t = sums2[o + cc]; sums2[o + cc] = sums2[o + cc + 1]; sums2[o + cc + 1] = t;
                 t = perm2[o + cc]; perm2[o + cc] = perm2[o + cc + 1]; perm2[o + cc + 1] = t;
+                if (cnt) atomicAdd(cnt + N + cc, 1ull);
               }
             }
           }

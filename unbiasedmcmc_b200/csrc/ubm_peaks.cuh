@@ -33,4 +33,21 @@ __global__ void __launch_bounds__(256) peak_imad_kernel(unsigned* out, int iters
   if (s == 0x12345678u) out[0] = s;
 }
 
+// FP64 tensor pipe: eight independent m8n8k4 accumulator chains per warp (256 fma per instruction)
+__global__ void __launch_bounds__(256) peak_dmma_kernel(double* out, int iters, double a, double b) {
+  double d[8][2];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { d[u][0] = threadIdx.x + u; d[u][1] = 0.5 * u; }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(d[u][0]), "+d"(d[u][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) s += d[u][0] + d[u][1];
+  if (s == 12345.678) out[0] = s;
+}
+
 }  // namespace ubm

@@ -49,6 +49,76 @@ __global__ void prim_scalar_coupling_kernel(const RunParams P, int mode, double 
   if (D.bad) atomicExch(P.status, UBM_ERR_TAPE);
 }
 
+// ---- the other scalar maximal couplings: R/gamma_couplings.R:14-21, R/invgamma_couplings.R:7-36,
+// src/inversegaussian.cpp:6-63, through R/get_max_coupling.R:24-39.  kind 0: Gamma(a, b) (rate b), 1: inverse Gamma,
+// 2: inverse Gaussian (a = mu, b = lambda).  R's rgamma is part of the R runtime, not of the reference: Gamma draws are
+// Marsaglia & Tsang (2000) on the typed streams (two draws per attempt; shape < 1 by the U^(1/shape) boost); lgamma
+// enters through the host-computed constants c = a log(b) - lgamma(a).
+template <bool TAPE>
+__device__ inline double prim_rgamma(double shape, double rate, ScalarDraws<TAPE>& D) {
+  const double a = shape < 1.0 ? shape + 1.0 : shape;
+  const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  double g = 0.0;
+  for (;;) {
+    const double x = D.n();
+    const double t = 1.0 + c * x;
+    const double u = D.u();
+    if (D.bad) return 1.0;
+    if (t <= 0.0) continue;
+    const double v = t * t * t;
+    if (ubm_log(u) < 0.5 * x * x + d - d * v + d * ubm_log(v)) { g = d * v; break; }
+  }
+  if (shape < 1.0) g = g * ubm_exp(ubm_log(D.u()) / shape);
+  return g / rate;
+}
+template <bool TAPE>
+__device__ inline double prim_rinvgaussian(double mu, double lambda, ScalarDraws<TAPE>& D) {   // src/inversegaussian.cpp:6-25
+  const double nu = D.n();
+  const double z = D.u();
+  double x = nu * nu;
+  x = mu + mu * mu * x / (2. * lambda) - mu / (2. * lambda) * sqrt(4. * mu * lambda * x + mu * mu * x * x);
+  return (z <= mu / (mu + x)) ? x : mu * mu / x;
+}
+template <bool TAPE>
+__device__ inline double prim_positive_draw(int kind, double a, double b, ScalarDraws<TAPE>& D, bool clamp) {
+  if (kind == 0) return prim_rgamma(a, b, D);
+  if (kind == 1) return 1.0 / prim_rgamma(a, b, D);
+  const double v = prim_rinvgaussian(a, b, D);
+  return (clamp && v < 1e-20) ? 1e-20 : v;                      // :40-42,52-54
+}
+__device__ inline double prim_positive_logpdf(int kind, double x, double a, double b, double c) {
+  if (kind == 0) return c + (a - 1.0) * ubm_log(x) - b * x;
+  if (kind == 1) return c - (a + 1.0) * ubm_log(x) - b / x;   // R/invgamma_couplings.R:7-9
+  return 0.5 * ubm_log(b / 6.283185) - 1.5 * ubm_log(x) - b * (x - a) * (x - a) / (2 * a * a * x);   // src/inversegaussian.cpp:27-29
+}
+// mode 0: out [n] plain draws of the first distribution; mode 1: out [n][2] maximally coupled pairs, ident [n]
+template <bool TAPE>
+__global__ void prim_positive_coupling_kernel(const RunParams P, int kind, int mode, double a1, double a2, double b1, double b2,
+                                              double c1, double c2, double* __restrict__ out, int* __restrict__ ident) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nrep) return;
+  ScalarDraws<TAPE> D;
+  D.init(P, i);
+  if (mode == 0) {
+    out[i] = prim_positive_draw(kind, a1, b1, D, false);
+  } else {
+    const double x = prim_positive_draw(kind, a1, b1, D, true);
+    double y = x;
+    bool id = true;
+    if (!(prim_positive_logpdf(kind, x, a1, b1, c1) + ubm_log(D.u()) < prim_positive_logpdf(kind, x, a2, b2, c2))) {
+      id = false;
+      bool reject = true;
+      y = 0.0;
+      while (reject && !D.bad) {
+        y = prim_positive_draw(kind, a2, b2, D, true);
+        reject = prim_positive_logpdf(kind, y, a2, b2, c2) + ubm_log(D.u()) < prim_positive_logpdf(kind, y, a1, b1, c1);
+      }
+    }
+    out[2 * i] = x; out[2 * i + 1] = y; ident[i] = id ? 1 : 0;
+  }
+  if (D.bad) atomicExch(P.status, UBM_ERR_TAPE);
+}
+
 // y_j = sum_{i <= j} v_i U[i, j], U column-major upper triangular: one fma chain, sequential in i (the engine's order;
 // see ubm_mvn.cuh / oracle_models.hpp: vec_times_upper)
 __device__ inline void prim_vec_times_upper(const double* v, const double* __restrict__ U, int d, double* out) {

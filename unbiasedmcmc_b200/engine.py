@@ -68,7 +68,16 @@ class Engine:
     def measure_peaks(self):
         a, b = C.c_double(), C.c_double()
         self._check(self.lib.ubm_measure_peaks(self.h, C.byref(a), C.byref(b)))
-        return {"fp64_tflops": a.value, "int32_tops": b.value}
+        t = C.c_double()
+        self._check(self.lib.ubm_measure_fp64_tensor_peak(self.h, C.byref(t)))
+        return {"fp64_tflops": a.value, "int32_tops": b.value, "fp64_tensor_tflops": t.value}
+
+    def ising_swap_counts(self, nchains):
+        """nswap_attempts, nswap_accepts1, nswap_accepts2 (R/ising.R:76,137-140) summed over the last Ising PT run"""
+        att = C.c_int64()
+        a1, a2 = np.zeros(max(nchains - 1, 1), dtype=np.int64), np.zeros(max(nchains - 1, 1), dtype=np.int64)
+        self._check(self.lib.ubm_ising_swap_counts(self.h, C.byref(att), A.i64ptr(a1), A.i64ptr(a2)))
+        return {"nswap_attempts": att.value, "nswap_accepts1": a1[:nchains - 1], "nswap_accepts2": a2[:nchains - 1]}
 
     def launch_count(self):
         return int(self.lib.ubm_launch_count(self.h))
@@ -171,6 +180,37 @@ class Engine:
                                                     A.dptr(xy), A.i32ptr(ident)))
         return {"xy": xy, "identical": ident.astype(bool)}
 
+    # ---- the other scalar maximal couplings (R/gamma_couplings.R, R/invgamma_couplings.R, src/inversegaussian.cpp)
+    def _positive_coupled(self, fn, p1, p2, q1, q2, draws, n, rep_offset):
+        xy, ident = np.zeros((n, 2)), np.zeros(n, dtype=np.int32)
+        ds = draws.struct(n)
+        self._check(fn(self.h, C.byref(ds), n, rep_offset, p1, p2, q1, q2, A.dptr(xy), A.i32ptr(ident)))
+        return {"xy": xy, "identical": ident.astype(bool)}
+
+    def rgamma_coupled(self, alpha1, alpha2, beta1, beta2, draws, n=1, rep_offset=0):
+        return self._positive_coupled(self.lib.ubm_rgamma_coupled, alpha1, alpha2, beta1, beta2, draws, n, rep_offset)
+
+    def rinversegamma_coupled(self, alpha1, alpha2, beta1, beta2, draws, n=1, rep_offset=0):
+        return self._positive_coupled(self.lib.ubm_rinversegamma_coupled, alpha1, alpha2, beta1, beta2, draws, n, rep_offset)
+
+    def rinvgaussian_coupled(self, mu1, mu2, lambda1, lambda2, draws, n=1, rep_offset=0):
+        return self._positive_coupled(self.lib.ubm_rinvgaussian_coupled, mu1, mu2, lambda1, lambda2, draws, n, rep_offset)
+
+    def _rpositive(self, kind, a, b, draws, n, rep_offset):
+        out = np.zeros(n)
+        ds = draws.struct(n)
+        self._check(self.lib.ubm_rpositive(self.h, C.byref(ds), kind, n, rep_offset, a, b, A.dptr(out)))
+        return out
+
+    def rgamma(self, n, shape, rate, draws, rep_offset=0):
+        return self._rpositive(0, shape, rate, draws, n, rep_offset)
+
+    def rinversegamma(self, n, alpha, beta, draws, rep_offset=0):
+        return self._rpositive(1, alpha, beta, draws, n, rep_offset)
+
+    def rinvgaussian(self, n, mu, lam, draws, rep_offset=0):
+        return self._rpositive(2, mu, lam, draws, n, rep_offset)
+
     def rnorm_reflectionmax(self, mu1, mu2, sigma, draws, n=1, rep_offset=0):
         xy, ident = np.zeros((n, 2)), np.zeros(n, dtype=np.int32)
         ds = draws.struct(n)
@@ -223,6 +263,26 @@ class Engine:
         ds = draws.struct(nparticles)
         self._check(self.lib.ubm_fast_rmvnorm_chol(self.h, C.byref(ds), nparticles, rep_offset, d, A.dptr(mean),
                                                    A.dptr(ch), A.dptr(out)))
+        return out
+
+    def fast_rmvnorm(self, nparticles, mean, covariance, draws, rep_offset=0):
+        """R/mvnorm.R:12 / src/mvnorm.cpp:9-26"""
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        d = len(mean)
+        cov = np.ascontiguousarray(np.asarray(covariance, dtype=np.float64).T).reshape(-1)
+        out = np.zeros((nparticles, d))
+        ds = draws.struct(nparticles)
+        self._check(self.lib.ubm_fast_rmvnorm(self.h, C.byref(ds), nparticles, rep_offset, d, A.dptr(mean), A.dptr(cov), A.dptr(out)))
+        return out
+
+    def fast_dmvnorm(self, x, mean, covariance):
+        """R/mvnorm.R:48 / src/mvnorm.cpp:49-67"""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        n, d = x.shape
+        cov = np.ascontiguousarray(np.asarray(covariance, dtype=np.float64).T).reshape(-1)
+        out = np.zeros(n)
+        self._check(self.lib.ubm_fast_dmvnorm(self.h, n, d, A.dptr(x), A.dptr(mean), A.dptr(cov), A.dptr(out)))
         return out
 
     def fast_dmvnorm_chol_inverse(self, x, mean, chol_inverse):
