@@ -1,4 +1,4 @@
-"""Small single-launch cases for ncu (one driver-kernel launch each). Usage: python tools/prof_case.py c2|c1 [nrep]"""
+"""Small single-launch cases for ncu (one driver-kernel launch each). Usage: python tools/prof_case.py c1|c2|c3|c4|c5 [nrep]"""
 import os
 import sys
 
@@ -28,6 +28,9 @@ elif which == "c1":
     nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 18
     res = eng.sample_unbiasedestimator(cases.c1_model(), R.Draws(seed=1), bins=cases.c1_bins(), k=500, m=2000, lag=500,
                                        nrep=nrep, want_bins=False, per_replicate=False)
+elif which == "c3":
+    nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 148
+    res = eng.sample_unbiasedestimator(cases.c3_model(), R.Draws(seed=1), k=10, m=60, lag=1, nrep=nrep, want_bins=False)
 if which != "c5":
     print(which, "ok", res["meetingtime"][:4] if res.get("meetingtime") is not None else res["summary"][:6])
 if which == "c5":
