@@ -154,13 +154,22 @@ struct PgSeq {
   __device__ __forceinline__ bool overflow() const { return bad; }
 };
 
-// PolyaGamma::a — src/PolyaGamma.cpp:65-79
+// PolyaGamma::a — src/PolyaGamma.cpp:65-79.  log(pi / 2) and log((n + 1/2) pi), n < 8, do not depend on the draw: they are
+// evaluated once per kernel (by the same ubm_log, so the values are the oracle's) instead of at every call.
+#define PG_NLOGK 8
+static __device__ double g_pg_logs[1 + PG_NLOGK];
+__global__ void pg_log_table_kernel() {
+  const int t = threadIdx.x;
+  if (t == 0) g_pg_logs[0] = ubm_log(0.5 * PG_PI_D);
+  else if (t <= PG_NLOGK) g_pg_logs[t] = ubm_log(((t - 1) + 0.5) * PG_PI_D);
+}
 __device__ __noinline__ double pg_a(int n, double x) {
   const double K = (n + 0.5) * PG_PI_D;
   double y = 0;
   if (x > PG_TRUNC_D) y = K * pg_exp(-0.5 * K * K * x);
   else if (x > 0) {
-    const double expnt = -1.5 * (pg_log(0.5 * PG_PI_D) + pg_log(x)) + pg_log(K) - 2.0 * (n + 0.5) * (n + 0.5) / x;
+    const double logK = (n < PG_NLOGK) ? g_pg_logs[1 + n] : pg_log(K);
+    const double expnt = -1.5 * (g_pg_logs[0] + pg_log(x)) + logK - 2.0 * (n + 0.5) * (n + 0.5) / x;
     y = pg_exp(expnt);
   }
   return y;
@@ -941,8 +950,9 @@ inline int pg_launch(const PgDevice& M, const RunParams& P, bool tape, int nsm, 
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PG_T, smem);
   if (e != cudaSuccess || per_sm < 1) { *err = "pg logistic: occupancy query failed"; return UBM_ERR_CUDA; }
   const int grid = (int)std::min<int64_t>((int64_t)nsm * per_sm, P.nrep);
+  pg_log_table_kernel<<<1, 32, 0, st>>>();
   kern<<<grid, PG_T, smem, st>>>(M, P);
-  *launches += 1;
+  *launches += 2;
   return UBM_OK;
 }
 
