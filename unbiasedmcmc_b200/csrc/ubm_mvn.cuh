@@ -158,13 +158,18 @@ __device__ __forceinline__ void draw_n4_warp(const RunParams& P, long long rep, 
       pr[2] = ubm_u01_53(A1.w[0], A1.w[1]); pr[3] = ubm_u01_53(A1.w[2], A1.w[3]);
     }
   }
+  // the central branch of all four draws, branch-free: eight independent Horner chains (numerator, denominator) keep the
+  // FP64 pipe busy instead of one dependent chain at a time; the few tail draws are overwritten below
+  double zc[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) zc[c] = ubm_qnorm_central(pr[c] - 0.5);
   unsigned bal[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const double q = pr[c] - 0.5;
     const bool valid = c < nvalid;
     const bool tail = valid && !(fabs(q) <= 0.425);
-    if (nvalid > 0 && !tail) row[4 * lane + c] = valid ? ubm_qnorm_central(q) : 0.0;
+    if (nvalid > 0 && !tail) row[4 * lane + c] = valid ? zc[c] : 0.0;
     bal[c] = __ballot_sync(0xffffffffu, tail);
   }
   const int n0 = __popc(bal[0]), n1 = n0 + __popc(bal[1]), n2 = n1 + __popc(bal[2]), n3 = n2 + __popc(bal[3]);
