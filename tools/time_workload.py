@@ -16,7 +16,8 @@ kw = dict(spec["kw"])
 if len(sys.argv) > 4:
     kw["k"], kw["m"] = int(sys.argv[3]), int(sys.argv[4])
 eng = Engine(0)
-eng.sample_unbiasedestimator(spec["model"], R.Draws(seed=2), nrep=min(nrep, 64), want_bins=False, **{**kw, "k": 2, "m": 8})   # warm-up
+eng.sample_unbiasedestimator(spec["model"], R.Draws(seed=2), nrep=min(nrep, 64), want_bins=False,
+                             **{**kw, "k": kw["lag"] + 1, "m": kw["lag"] + 8})   # warm-up
 t = time.time()
 res = eng.sample_unbiasedestimator(spec["model"], R.Draws(seed=1), nrep=nrep, want_bins=False, **kw)
 dt = time.time() - t

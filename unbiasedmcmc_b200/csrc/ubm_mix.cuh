@@ -35,7 +35,7 @@ struct MixModel {
     return -((UBM_LN_SQRT_2PI + 0.5 * z * z) + log_sigma);
   }
   // README.Rmd:69-72
-  __device__ double target(double x) const {
+  __device__ __noinline__ double target(double x) const {
     double ev[8];
     double mx = -dinf();
 #pragma unroll
@@ -121,7 +121,7 @@ template <bool TAPE>
 #ifndef MIX_MINB
 #define MIX_MINB 5      // CTAs per SM asked of the register allocator (96 registers): 3 -> 5.5e6, 4 -> 6.1e6, 5 -> 6.6e6 est/s on C1
 #endif
-__global__ void __launch_bounds__(128, MIX_MINB) mix_driver_kernel(const MixParams MP, const RunParams P) {
+__global__ void __launch_bounds__(128, MIX_MINB) mix_driver_kernel(const __grid_constant__ MixParams MP, const RunParams P) {
   extern __shared__ unsigned char smem_raw[];
   const int nbins = (P.mode == MODE_ESTIMATOR && P.nbreaks >= 2) ? P.nbreaks - 1 : 0;
   double* s_breaks = reinterpret_cast<double*>(smem_raw);
