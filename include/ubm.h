@@ -141,7 +141,9 @@ typedef struct {
   const double* B;        /* p x p prior covariance (column-major, symmetric positive definite) */
   int32_t w_coupling;     /* sample_w(mode=) of R/logistic_regression.R:166-175: 0 = 'max' (w_max_couplingC, the scripts'
                              choice), 1 = 'rej_samp' (w_rejsamplerC, src/logisticregressioncoupling.cpp:42-75) */
-  int32_t reserved;
+  int32_t beta_coupling;  /* coupled beta-step: 0 = maximal coupling of the two Normals (sample_beta, R/logistic_regression.R:180-209,
+                             germancredit.run.R:36), 1 = common random numbers: one increment for both chains
+                             (pgg_coupled_kernel, vignettes/polyagammagibbs.Rmd:189-214) */
 } ubm_model_pg_logistic;
 
 /* C5: Bayesian variable selection, g-prior spike-and-slab, flip / swap Metropolis-Hastings on gamma in {0,1}^p,

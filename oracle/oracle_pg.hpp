@@ -173,6 +173,7 @@ inline double pg_logcosh(double x) {
 struct PgLogisticModel {
   struct State { std::vector<double> beta; uint64_t sweep = 0; };
   int n = 0, p = 0, w_coupling = 0;   // w_coupling: sample_w(mode=): 0 'max', 1 'rej_samp'
+  int beta_coupling = 0;              // coupled beta-step: 0 maximal coupling (sample_beta), 1 common random numbers (vignette)
   std::vector<double> X;        // n x p column-major
   std::vector<double> invB;     // p x p column-major  (logisticregression_precomputation, R/logistic_regression.R:34-50)
   std::vector<double> ktk;      // KTkappaplusinvBtimesb = X^T (Y - 1/2) + invB b
@@ -196,7 +197,7 @@ struct PgLogisticModel {
   }
 
   explicit PgLogisticModel(const ubm_model_pg_logistic* s) {
-    n = s->n; p = s->p; w_coupling = s->w_coupling;
+    n = s->n; p = s->p; w_coupling = s->w_coupling; beta_coupling = s->beta_coupling;
     X.assign(s->X, s->X + (size_t)n * p);
     b.assign(s->b, s->b + p);
     // invB = solve(B); ktk = t(X) %*% (Y - 0.5) + invB %*% b  (host-side precomputation, as in R)
@@ -416,6 +417,19 @@ struct PgLogisticModel {
     }
     // sample_beta — R/logistic_regression.R:180-209: rmvnorm_max(m1, m2, t(C1) %*% C1, t(C2) %*% C2)
     MS r1 = m_sigma(w1), r2 = m_sigma(w2);
+    if (beta_coupling == 1) {
+      // pgg_coupled_kernel, vignettes/polyagammagibbs.Rmd:203-211: increment <- rnorm(p); beta_c = m_c + increment %*% Cholesky_c
+      std::vector<double> z(p);
+      for (int j = 0; j < p; ++j) z[j] = D.n();
+      for (int j = 0; j < p; ++j) {
+        double a1 = 0.0, a2 = 0.0;
+        for (int i = j; i < p; ++i) { a1 = ubm_fma(z[i], r1.Linv[(size_t)j * p + i], a1); a2 = ubm_fma(z[i], r2.Linv[(size_t)j * p + i], a2); }
+        s1.beta[j] = a1 + r1.m[j];
+        s2.beta[j] = a2 + r2.m[j];
+      }
+      if (all_equal) s2.beta = s1.beta;
+      return all_equal;
+    }
     std::vector<double> S1 = ltl(r1.Linv, p), S2 = ltl(r2.Linv, p);
     bool ok = true;
     chol_lower(S1, p, &ok); chol_lower(S2, p, &ok);                  // LLT of Sigma1, Sigma2 (src/mvnorm.cpp:12,52)

@@ -68,6 +68,7 @@ static void model_from(List spec, Model& M) {
     M.pg.n = X.nrow(); M.pg.p = X.ncol();
     M.pg.X = M.vec(spec["X"]); M.pg.Y = M.vec(spec["Y"]); M.pg.b = M.vec(spec["b"]); M.pg.B = M.vec(spec["B"]);
     M.pg.w_coupling = as<std::string>(spec["mode"]) == "rej_samp" ? 1 : 0;      // sample_w(mode = ), R/logistic_regression.R:166-175
+    M.pg.beta_coupling = spec.containsElementNamed("beta_coupling") && as<std::string>(spec["beta_coupling"]) == "crn" ? 1 : 0;
   } else if (kind == "varsel") {                        // R/variableselection.R:1-148
     M.kind = UBM_MODEL_VARSEL;
     NumericMatrix X = spec["X"];

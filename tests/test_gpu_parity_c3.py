@@ -122,3 +122,22 @@ def test_c3_bins_on_the_fly(engine, oracle, comp):
     c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=9), bins=bins, nthreads=8, **kw)
     assert_same(g, c, KEYS + ["bins"])
     assert abs(g["bins"].sum(1).mean() - 1.0) < 0.2
+
+
+@pytest.mark.parametrize("lag,h", [(1, A.UBM_H_IDENTITY), (3, A.UBM_H_BOTH)])
+def test_c3_common_random_number_beta_step_bit_exact(engine, oracle, lag, h):
+    """beta_coupling='crn': the coupled kernel of the vignette (vignettes/polyagammagibbs.Rmd:189-214): max-coupled PG
+    variables, ONE Normal increment for both chains' regression coefficients"""
+    mdl = cases.c3_model(150, 6, seed=5, beta_coupling="crn")
+    kw = dict(h_kind=h, k=5, m=50, lag=lag, nrep=24, max_iterations=3000)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=12), **kw)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=12), nthreads=8, **kw)
+    assert_same(g, c, KEYS)
+    assert np.isfinite(g["meetingtime"]).all()
+    ch_g = engine.sample_coupled_chains(mdl, R.Draws(seed=3), m=30, lag=lag, stride=3100, nrep=6, max_iterations=3000)
+    ch_c = oracle.sample_coupled_chains(mdl, R.Draws(seed=3), m=30, lag=lag, stride=3100, nrep=6, max_iterations=3000)
+    assert_same(ch_g, ch_c, ["meetingtime", "iteration", "cost"])
+    for r in range(6):
+        n = int(ch_c["iteration"][r]) + 1
+        assert np.array_equal(ch_g["samples1"][r, :n], ch_c["samples1"][r, :n])
+        assert np.array_equal(ch_g["samples2"][r, :n - lag], ch_c["samples2"][r, :n - lag])

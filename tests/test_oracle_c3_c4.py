@@ -80,3 +80,18 @@ def test_c3_rejsampler_coupling_is_a_valid_coupling(oracle):
     diff = est["max"][0] - est["rej_samp"][0]
     se = np.sqrt(est["max"][1] ** 2 + est["rej_samp"][1] ** 2)
     assert np.all(np.abs(diff) < 4.5 * se)
+
+
+def test_c3_crn_beta_step_is_a_valid_coupling(oracle):
+    """pgg_coupled_kernel of the vignette (vignettes/polyagammagibbs.Rmd:189-214): chain 1 follows the same single-chain law
+    as under sample_beta's maximal coupling (same posterior means from the unbiased estimators), and the chains meet."""
+    est = {}
+    for bc in ("max", "crn"):
+        mdl = cases.c3_model(120, 4, seed=3, beta_coupling=bc)
+        r = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=21), k=20, m=120, lag=1, nrep=400, nthreads=8, max_iterations=5000)
+        assert np.isfinite(r["meetingtime"]).all()
+        est[bc] = (r["uestimator"].mean(0), r["uestimator"].std(0, ddof=1) / np.sqrt(400), r["meetingtime"].mean())
+    diff = est["max"][0] - est["crn"][0]
+    se = np.sqrt(est["max"][1] ** 2 + est["crn"][1] ** 2)
+    assert np.all(np.abs(diff) < 5 * se)
+    assert est["crn"][2] < 200

@@ -70,7 +70,7 @@ class ubm_model_ising_pt(C.Structure):
 
 class ubm_model_pg_logistic(C.Structure):
     _fields_ = [("n", C.c_int32), ("p", C.c_int32), ("X", c_double_p), ("Y", c_double_p),
-                ("b", c_double_p), ("B", c_double_p), ("w_coupling", C.c_int32), ("reserved", C.c_int32)]
+                ("b", c_double_p), ("B", c_double_p), ("w_coupling", C.c_int32), ("beta_coupling", C.c_int32)]
 
 
 class ubm_model_varsel(C.Structure):

@@ -100,10 +100,11 @@ def ising_pt_kernels(betas, proba_swapmove):
     return {"single_kernel": m, "coupled_kernel": m, "rinit": m}
 
 
-def logisticregression_kernels(Y, X, b, B, mode="max"):
+def logisticregression_kernels(Y, X, b, B, mode="max", beta_coupling="max"):
     """single_kernel / coupled_kernel / rinit of inst/reproducegermancredit/germancredit.run.R:23-49; `mode` is
-    sample_w's (R/logistic_regression.R:166): 'max' (w_max_couplingC) or 'rej_samp' (w_rejsamplerC)."""
-    m = R.PgLogistic(Y, X, b, B, mode=mode)
+    sample_w's (R/logistic_regression.R:166): 'max' (w_max_couplingC) or 'rej_samp' (w_rejsamplerC); `beta_coupling` 'max'
+    (sample_beta) or 'crn' (the common-random-number step of pgg_coupled_kernel, vignettes/polyagammagibbs.Rmd:189-214)."""
+    m = R.PgLogistic(Y, X, b, B, mode=mode, beta_coupling=beta_coupling)
     return {"single_kernel": m, "coupled_kernel": m, "rinit": m}
 
 

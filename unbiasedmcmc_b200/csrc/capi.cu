@@ -142,6 +142,7 @@ static int register_model(ubm_plan* p, int32_t kind, const void* model) {
     const ubm_model_pg_logistic* s = (const ubm_model_pg_logistic*)model;
     if (s->p < 1 || s->p > PG_PLIM || s->n < 1 || s->n > 4096) return fail(h, UBM_ERR_INVALID, "pg logistic: 1 <= p <= 60, 1 <= n <= 4096");
     if (s->w_coupling != 0 && s->w_coupling != 1) return fail(h, UBM_ERR_INVALID, "pg logistic: w_coupling must be 0 ('max') or 1 ('rej_samp')");
+    if (s->beta_coupling != 0 && s->beta_coupling != 1) return fail(h, UBM_ERR_INVALID, "pg logistic: beta_coupling must be 0 (maximal coupling) or 1 (common random numbers)");
     if (!s->X || !s->Y || !s->b || !s->B) return fail(h, UBM_ERR_INVALID, "pg logistic: null data");
     p->dim = s->p;
     std::vector<double> blob;

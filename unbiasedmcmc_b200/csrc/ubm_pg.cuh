@@ -41,7 +41,7 @@ namespace ubm {
 #define PG_TRUNC_D 0.64
 
 struct PgDevice {
-  int n, p, ne, w_coupling;
+  int n, p, ne, w_coupling, beta_coupling;
   const double *X, *invB, *ktk, *b, *cholB;   // device: X n x p col-major; invB p x p; ktk, b [p]; cholB upper p x p
   const double *Xt;                            // device: X again, row-major [ceil(n/32)*32][PG_GS], zero padded: the Gram tiles
   size_t offs[6];
@@ -64,7 +64,7 @@ inline void pg_chol_lower_host(std::vector<double>& A, int p) {
 }
 inline void pg_pack_host(const ubm_model_pg_logistic* s, PgDevice* M, std::vector<double>* blob) {
   const int n = s->n, p = s->p;
-  M->n = n; M->p = p; M->ne = p * (p + 1) / 2; M->w_coupling = s->w_coupling;
+  M->n = n; M->p = p; M->ne = p * (p + 1) / 2; M->w_coupling = s->w_coupling; M->beta_coupling = s->beta_coupling;
   std::vector<double> LB(s->B, s->B + (size_t)p * p);
   pg_chol_lower_host(LB, p);
   std::vector<double> cholB((size_t)p * p, 0.0), Li((size_t)p * p, 0.0), invB((size_t)p * p, 0.0), ktk(p, 0.0);
@@ -811,6 +811,24 @@ __global__ void __launch_bounds__(PG_T) pg_driver_kernel(const PgDevice M, const
           }
           if (lane == 0) sh.in = in0 + p;
         }
+      } else if (M.beta_coupling == 1) {
+        // common random numbers (pgg_coupled_kernel, vignettes/polyagammagibbs.Rmd:203-206): one increment, beta_c = m_c + z Linv_c
+        if (warp == 0) {
+          const unsigned long long in0 = sh.in;
+          bool badr = false;
+          for (int j = lane; j < p; j += 32) zz[j] = draw_n_at<TAPE>(P, rep, in0 + j, &badr);
+          if (TAPE && __any_sync(0xffffffffu, badr) && lane == 0) sh.bad = 1;
+          __syncwarp();
+          for (int j = lane; j < p; j += 32) {
+            double a = 0.0, b2 = 0.0;
+            for (int i = j; i < p; ++i) { a = ubm_fma(zz[i], MB1[j * p + i], a); b2 = ubm_fma(zz[i], MB2[j * p + i], b2); }
+            const double v1 = a + m1[j];
+            beta1[j] = v1;
+            beta2[j] = all_equal ? v1 : (b2 + m2[j]);                      // :207-211: identical iff every PG pair is
+          }
+          if (lane == 0) sh.in = in0 + p;
+        }
+        if (all_equal) { met = true; tau = time; }
       } else {
         // sample_beta (R/logistic_regression.R:180-209): Sigma_c = Linv_c' Linv_c, then LLT of Sigma_c (src/mvnorm.cpp:12,52)
         pg_ltl(MB1, MA1, p, tid, PG_T);                                  // all warps: the entries are independent

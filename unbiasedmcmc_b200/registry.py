@@ -153,10 +153,13 @@ class PgLogistic(ModelSpec):
     inst/reproducegermancredit/germancredit.run.R:23-49.  Prior beta ~ N(b, B)."""
     kind = A.UBM_MODEL_PG_LOGISTIC
 
-    def __init__(self, Y, X, b, B, mode="max"):
+    def __init__(self, Y, X, b, B, mode="max", beta_coupling="max"):
         if mode not in ("max", "rej_samp"):                       # sample_w(mode=), R/logistic_regression.R:166-175
             raise ValueError("PG logistic: mode must be 'max' or 'rej_samp'")
+        if beta_coupling not in ("max", "crn"):                   # sample_beta vs the vignette's common random numbers
+            raise ValueError("PG logistic: beta_coupling must be 'max' or 'crn'")
         self.w_coupling = 0 if mode == "max" else 1
+        self.beta_coupling = 0 if beta_coupling == "max" else 1
         X = np.asarray(X, dtype=np.float64)
         self.n, self.p = X.shape
         if not (1 <= self.p <= 60 and 1 <= self.n <= 4096):
@@ -169,7 +172,7 @@ class PgLogistic(ModelSpec):
 
     def struct(self):
         return A.ubm_model_pg_logistic(self.n, self.p, A.dptr(self.X), A.dptr(self.Y), A.dptr(self.b), A.dptr(self.B),
-                                       self.w_coupling, 0)
+                                       self.w_coupling, self.beta_coupling)
 
 
 class VariableSelection(ModelSpec):

@@ -56,10 +56,10 @@ def c3_data(n=1000, p=49, seed=SEED):
     return Y, X
 
 
-def c3_model(n=1000, p=49, seed=SEED, mode="max"):
+def c3_model(n=1000, p=49, seed=SEED, mode="max", beta_coupling="max"):
     """germancredit.run.R:18-20: prior b = 0, B = 10 I."""
     Y, X = c3_data(n, p, seed)
-    return R.PgLogistic(Y, X, np.zeros(p), 10.0 * np.eye(p), mode=mode)
+    return R.PgLogistic(Y, X, np.zeros(p), 10.0 * np.eye(p), mode=mode, beta_coupling=beta_coupling)
 
 
 # marginal summaries of the German-credit columns (inst/reproducegermancredit/german_credit.csv): (mean, sd, min, max) of
