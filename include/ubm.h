@@ -162,6 +162,17 @@ typedef struct {
   double proportion_singleflip;
 } ubm_model_varsel;
 
+/* Bayesian lasso: the Gibbs sampler of get_blasso and its coupling, R/bayesianlasso.R:22-98 with
+ * src/blassoutil.cpp:17-88 (beta | tau2, sigma2 through rmvnorm_max_coupling_), rinversegamma_coupled for sigma2 and
+ * rinvgaussian_coupled per component of 1 / tau2.  Chain state = c(beta[p], tau2[p], sigma2): dim = 2 p + 1.
+ * rinit is the reference's deterministic c(0.., 1.., 1). */
+typedef struct {
+  int32_t n, p;           /* n <= 4096 observations, p <= 60 covariates */
+  const double* X;        /* n x p column-major */
+  const double* Y;        /* [n] */
+  double lambda;          /* the lasso penalty (lambda2 = lambda^2, R/bayesianlasso.R:28) */
+} ubm_model_blasso;
+
 /* ---------------------------------------------------------------------------------------------
  * test functions h and histogram bins
  * ------------------------------------------------------------------------------------------- */
@@ -210,6 +221,7 @@ typedef struct {
 #define UBM_MODEL_PG_LOGISTIC 3
 #define UBM_MODEL_ISING_PT 4
 #define UBM_MODEL_VARSEL 5
+#define UBM_MODEL_BLASSO 6
 
 /* dimension of the chain state / of h for a model (so callers can size buffers) */
 int ubm_model_dim(int32_t model_kind, const void* model, int32_t* dim);

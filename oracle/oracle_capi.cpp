@@ -281,6 +281,17 @@ int orc_cov_factor(int32_t which, int32_t d, const double* covariance, double* o
   return UBM_OK;
 }
 
+// Bayesian lasso probe: one blassoconditional step (src/blassoutil.cpp:17-41) from a tape of normals: beta [p], {norm, betaDbeta}
+int orc_blasso_conditional(const ubm_model_blasso* mdl, const ubm_draws* draws, const double* tau2, double sigma2, double* beta,
+                           double* norm_bdb) {
+  BlassoModel M(mdl);
+  Draws D = make_draws(draws, 0, 0);
+  const BlassoModel::Cond c = M.conditional(tau2, sigma2);
+  M.draw_beta(c, D, beta);
+  norm_bdb[0] = M.rss(beta); norm_bdb[1] = M.bdb(beta, tau2);
+  return D.exhausted ? UBM_ERR_TAPE : UBM_OK;
+}
+
 void orc_ising_swap_counts(int32_t reset, int64_t* out63) {
   for (int i = 0; i < 63; ++i) { if (out63) out63[i] = g_ising_pt[i].load(); if (reset) g_ising_pt[i] = 0; }
 }

@@ -262,6 +262,17 @@ def rnorm_max_coupling(mu1, mu2, sigma1, sigma2, draws, n=1, rep_offset=0):
     return {"xy": xy, "identical": ident.astype(bool)}
 
 
+def blasso_conditional(model, draws, tau2, sigma2):
+    L = lib()
+    L.orc_blasso_conditional.argtypes = [C.c_void_p, C.POINTER(A.ubm_draws), A.c_double_p, C.c_double, A.c_double_p, A.c_double_p]
+    L.orc_blasso_conditional.restype = C.c_int
+    beta, nb = np.zeros(model.p), np.zeros(2)
+    ds = draws.struct(1)
+    tau2 = np.ascontiguousarray(tau2, dtype=np.float64)
+    _check(L.orc_blasso_conditional(model.ref(), C.byref(ds), A.dptr(tau2), sigma2, A.dptr(beta), A.dptr(nb)))
+    return beta, nb[0], nb[1]
+
+
 def ising_swap_counts(nchains, reset=True):
     out = np.zeros(63, dtype=np.int64)
     L = lib()

@@ -96,6 +96,8 @@ def lib(flavour="libm"):
                   "ref_rmvnorm_max_coupling", "ref_rmvnorm_max_coupling_cholesky", "ref_rmvnorm_reflection_max_coupling",
                   "ref_sigma", "ref_m_sigma_function"):
             getattr(L, f).restype = None
+        L.ref_blassoconditional.argtypes = [C.c_int32, C.c_int32, dp, dp, dp, dp, dp, C.c_double, dp, dp]
+        L.ref_blassoconditional.restype = None
         L.ref_marginal_likelihood_c_2.argtypes = [C.c_int32, C.c_int32, dp, dp, dp, C.c_double, C.c_double]
         L.ref_marginal_likelihood_c_2.restype = C.c_double
         _libs[flavour] = L

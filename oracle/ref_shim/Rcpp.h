@@ -37,11 +37,13 @@ struct Range {
 };
 
 // ---- vectors: a handle to shared storage, as an R vector seen through Rcpp -------------------------------------
+template <class T> class Matrix;
 template <class T>
 class Vector {
  public:
   std::shared_ptr<std::vector<T>> p;
   Vector() : p(std::make_shared<std::vector<T>>()) {}
+  Vector(const Matrix<T>& m);                    // an R matrix is a vector with a dim attribute (NumericVector(wrap(matrix)))
   Vector(int n) : p(std::make_shared<std::vector<T>>((size_t)n, T())) {}
   Vector(int n, T v) : p(std::make_shared<std::vector<T>>((size_t)n, v)) {}
   Vector(const T* src, int n) : p(std::make_shared<std::vector<T>>(src, src + n)) {}
@@ -102,6 +104,7 @@ class Matrix {
   }
 };
 typedef Matrix<double> NumericMatrix;
+template <class T> Vector<T>::Vector(const Matrix<T>& m) : p(std::make_shared<std::vector<T>>(*m.p)) {}
 typedef Matrix<int> IntegerMatrix;
 
 // ---- List: named heterogeneous values --------------------------------------------------------------------------

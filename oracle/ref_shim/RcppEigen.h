@@ -225,10 +225,12 @@ template <> struct AsImpl<Eigen::ArrayXd> {
 };
 template <> struct AsImpl<Eigen::VectorXd> {
   static Eigen::VectorXd get(const NumericVector& v) { Eigen::VectorXd o(v.size()); o.a = *v.p; return o; }
+  static Eigen::VectorXd get(const NumericMatrix& m) { Eigen::VectorXd o(m.size()); o.a = *m.p; return o; }
 };
 template <class T, class S> T as(const S& s) { return AsImpl<T>::get(s); }
 inline NumericMatrix wrap(const Eigen::MatT<double>& m) { return NumericMatrix(m.a.data(), m.r, m.c); }
 inline NumericVector wrap(const Eigen::VecT<double>& v) { return NumericVector(v.a.data(), v.r); }
+inline NumericMatrix wrap(const Eigen::ArrT<double>& m) { return NumericMatrix(m.a.data(), m.r, m.c); }
 }  // namespace Rcpp
 
 #endif

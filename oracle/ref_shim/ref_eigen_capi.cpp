@@ -12,6 +12,9 @@ List m_sigma_function_(const Eigen::Map<Eigen::MatrixXd>& omega, const Eigen::Ma
                        const Eigen::Map<Eigen::MatrixXd>& invB, const Eigen::Map<Eigen::VectorXd>& KTkappaplusinvBtimesb);   // :32
 double marginal_likelihood_c_2(Eigen::VectorXf selection, const Eigen::MatrixXf& X, const Eigen::VectorXf& Y, double Y2, double g);   // src/vs_mlikelihood.cpp:5
 
+List blassoconditional(const Eigen::VectorXd& Y, const Eigen::MatrixXd& X, const Eigen::VectorXd& XtY, const Eigen::MatrixXd& XtX,
+                       const NumericVector tau2, const double sigma2);                                           // src/blassoutil.cpp:17
+
 namespace {
 Eigen::MatrixXd emat(const double* a, int r, int c) { Eigen::MatrixXd m(r, c); m.a.assign(a, a + (size_t)r * c); return m; }
 Eigen::VectorXd evec(const double* a, int n) { Eigen::VectorXd v(n); v.a.assign(a, a + n); return v; }
@@ -19,6 +22,15 @@ void put(const NumericMatrix& m, double* out) { std::copy(m.begin(), m.end(), ou
 }  // namespace
 
 extern "C" {
+
+// blassoconditional (src/blassoutil.cpp:17-41): beta [p], norm, betaDbeta
+void ref_blassoconditional(int32_t n, int32_t p, const double* Y, const double* X, const double* XtY, const double* XtX,
+                           const double* tau2, double sigma2, double* beta, double* norm_bdb) {
+  List r = blassoconditional(evec(Y, n), emat(X, n, p), evec(XtY, p), emat(XtX, p, p), NumericVector(tau2, p), sigma2);
+  NumericVector b = r["beta"];
+  for (int j = 0; j < p; ++j) beta[j] = b(j);
+  norm_bdb[0] = (double)r["norm"]; norm_bdb[1] = (double)r["betaDbeta"];
+}
 
 // out: nsamples x d column-major
 void ref_fast_rmvnorm(int32_t nsamples, int32_t d, const double* mean, const double* covariance, double* out) {

@@ -49,6 +49,10 @@ ising_pt_kernels <- function(betas, proba_swapmove)       # R/ising.R:45-141
   registry_kernels(list(kind = "ising_pt", betas = betas, proba_swapmove = proba_swapmove))
 logisticregression_kernels <- function(Y, X, b, B, mode = "max")   # germancredit.run.R:23-49
   registry_kernels(list(kind = "pg_logistic", X = X, Y = as.numeric(Y), b = b, B = B, mode = mode))
+get_blasso <- function(Y, X, lambda) {                      # R/bayesianlasso.R:22
+  k <- registry_kernels(list(kind = "blasso", X = X, Y = as.numeric(Y), lambda = lambda))
+  list(rinit = k$rinit, gibbs_kernel = k$single_kernel, coupled_gibbs_kernel = k$coupled_kernel)
+}
 get_variableselection <- function(Y, X, g, kappa, s0, proportion_singleflip)   # R/variableselection.R:1
   registry_kernels(list(kind = "varsel", X = X, Y = as.numeric(Y), g = g, kappa = kappa, s0 = s0,
                         proportion_singleflip = proportion_singleflip))

@@ -28,6 +28,7 @@ static ubm_draws philox() { ubm_draws d = {UBM_DRAWS_PHILOX, 0, r_seed(), nullpt
 struct Model {
   int32_t kind = 0;
   ubm_model_normal_mixture mix{}; ubm_model_mvn mvn{}; ubm_model_ising_pt ising{}; ubm_model_pg_logistic pg{}; ubm_model_varsel vs{};
+  ubm_model_blasso bl{};
   std::vector<NumericVector> keep;
   const void* ptr() const {
     switch (kind) {
@@ -35,6 +36,7 @@ struct Model {
       case UBM_MODEL_MVN: return &mvn;
       case UBM_MODEL_ISING_PT: return &ising;
       case UBM_MODEL_PG_LOGISTIC: return &pg;
+      case UBM_MODEL_BLASSO: return &bl;
       default: return &vs;
     }
   }
@@ -76,6 +78,11 @@ static void model_from(List spec, Model& M) {
     M.vs.X = M.vec(spec["X"]); M.vs.Y = M.vec(spec["Y"]);
     M.vs.g = as<double>(spec["g"]); M.vs.kappa = as<double>(spec["kappa"]); M.vs.s0 = as<int>(spec["s0"]);
     M.vs.proportion_singleflip = as<double>(spec["proportion_singleflip"]);
+  } else if (kind == "blasso") {                        // R/bayesianlasso.R:22-98
+    M.kind = UBM_MODEL_BLASSO;
+    NumericMatrix X = spec["X"];
+    M.bl.n = X.nrow(); M.bl.p = X.ncol();
+    M.bl.X = M.vec(spec["X"]); M.bl.Y = M.vec(spec["Y"]); M.bl.lambda = as<double>(spec["lambda"]);
   } else {
     stop("ubm: unknown model kind '" + kind + "'");
   }

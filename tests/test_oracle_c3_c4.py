@@ -95,3 +95,18 @@ def test_c3_crn_beta_step_is_a_valid_coupling(oracle):
     se = np.sqrt(est["max"][1] ** 2 + est["crn"][1] ** 2)
     assert np.all(np.abs(diff) < 5 * se)
     assert est["crn"][2] < 200
+
+
+def test_blasso_unbiased_estimators_match_a_long_chain(oracle):
+    """get_blasso (R/bayesianlasso.R:22-98): the coupled Gibbs sampler meets, and the unbiased estimators of the posterior
+    means of (beta, tau2, sigma2) agree with a long single chain"""
+    mdl = cases.blasso_model(120, 8, 1.0)
+    r = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=3), k=30, m=200, lag=1, nrep=300, nthreads=8, max_iterations=20000)
+    assert np.isfinite(r["meetingtime"]).all() and r["meetingtime"].mean() < 50
+    u = r["uestimator"]
+    ch = oracle.sample_coupled_chains(mdl, R.Draws(seed=5), m=30000, lag=1, stride=30100, nrep=1, max_iterations=30050)
+    s = ch["samples1"][0, 2000:30001]
+    bm = s[: (len(s) // 40) * 40].reshape(40, -1, s.shape[1]).mean(1)
+    se = np.sqrt(bm.var(0, ddof=1) / 40 + u.var(0, ddof=1) / len(u))
+    assert np.all(np.abs(u.mean(0) - s.mean(0)) < 5 * se)
+    assert np.all(s[:, 8:] > 0)                                   # tau2 and sigma2 are positive

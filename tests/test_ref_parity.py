@@ -365,3 +365,22 @@ def test_marginal_likelihood_float32_reference_bound(oracle, ref):
             assert abs(o - exact) <= 1e-9 * abs(exact)            # the FP64 path is the accurate one
             worst = max(worst, abs(r - o) / abs(o))
     assert worst < 2e-4, worst                                    # float32 evaluation: ~1e-5 relative on log-ml
+
+
+def test_blasso_conditional_against_the_compiled_reference(oracle, refu):
+    """blassoconditional (src/blassoutil.cpp:17-41, Eigen .inverse() + fast_rmvnorm_'s LLT) against the oracle's Cholesky route,
+    same normal tape: the regression draw, the residual sum of squares and beta' D^-1 beta agree to rounding"""
+    from unbiasedmcmc_b200 import workloads as W
+    for n, p in ((60, 5), (150, 12)):
+        mdl = W.blasso_model(n, p, 1.3)
+        Y, X = W.blasso_data(n, p)
+        rng = np.random.default_rng(p)
+        tau2, sigma2, tn = rng.uniform(0.5, 2.0, p), 1.7, rng.standard_normal(p)
+        beta, nb = np.zeros(p), np.zeros(2)
+        t = ref_py.Tape(refu, n=tn)
+        refu.ref_blassoconditional(n, p, ref_py._d(ref_py.f64(Y)), ref_py._d(ref_py.cm(X)), ref_py._d(ref_py.f64(X.T @ Y)),
+                                   ref_py._d(ref_py.cm(X.T @ X)), ref_py._d(ref_py.f64(tau2)), sigma2, ref_py._d(beta), ref_py._d(nb))
+        assert t.used() == ((0, p, 0), False)
+        b, norm, bdb = oracle.blasso_conditional(mdl, R.Draws(tape_n=tn[None]), tau2, sigma2)
+        _close(beta, b, 1e-9)
+        _close(np.array([norm, bdb]), nb, 1e-9)

@@ -16,6 +16,7 @@ UBM_DRAWS_PHILOX, UBM_DRAWS_TAPE = 0, 1
 UBM_COUPLING_REFLECTION_MAX, UBM_COUPLING_MAX = 0, 1
 UBM_H_IDENTITY, UBM_H_SQUARE, UBM_H_BOTH = 0, 1, 2
 UBM_MODEL_NORMAL_MIXTURE, UBM_MODEL_MVN, UBM_MODEL_PG_LOGISTIC, UBM_MODEL_ISING_PT, UBM_MODEL_VARSEL = 1, 2, 3, 4, 5
+UBM_MODEL_BLASSO = 6
 UBM_SUMMARY_HEAD = 6
 
 c_double_p = C.POINTER(C.c_double)
@@ -71,6 +72,10 @@ class ubm_model_ising_pt(C.Structure):
 class ubm_model_pg_logistic(C.Structure):
     _fields_ = [("n", C.c_int32), ("p", C.c_int32), ("X", c_double_p), ("Y", c_double_p),
                 ("b", c_double_p), ("B", c_double_p), ("w_coupling", C.c_int32), ("beta_coupling", C.c_int32)]
+
+
+class ubm_model_blasso(C.Structure):
+    _fields_ = [("n", C.c_int32), ("p", C.c_int32), ("X", c_double_p), ("Y", c_double_p), ("lambda_", C.c_double)]
 
 
 class ubm_model_varsel(C.Structure):

@@ -108,6 +108,12 @@ def logisticregression_kernels(Y, X, b, B, mode="max", beta_coupling="max"):
     return {"single_kernel": m, "coupled_kernel": m, "rinit": m}
 
 
+def get_blasso(Y, X, lam):
+    """get_blasso(Y, X, lambda) (R/bayesianlasso.R:22): list(rinit, gibbs_kernel, coupled_gibbs_kernel)"""
+    m = R.BayesianLasso(Y, X, lam)
+    return {"rinit": m, "gibbs_kernel": m, "coupled_gibbs_kernel": m}
+
+
 def get_variableselection(Y, X, g, kappa, s0, proportion_singleflip):
     """R/variableselection.R:3 — returns the kernels and rinit (marginal likelihood / prior run on the device)."""
     m = R.VariableSelection(Y, X, g, kappa, s0, proportion_singleflip)

@@ -19,6 +19,7 @@
 #include "ubm_post.cuh"
 #include "ubm_peaks.cuh"
 #include "ubm_prims.cuh"
+#include "ubm_blasso.cuh"
 
 using namespace ubm;
 
@@ -67,6 +68,7 @@ struct ubm_plan {
   IsingDevice ising{};
   PgDevice pg{};
   VarselDevice varsel{};
+  BlassoDevice blasso{};
   DevBuf model_blob;
   // results
   DevBuf uest, mcmc, corr, tau, cost, iter, bins_out, bin_acc, bin_num, breaks, summary, counter, status, scratch;
@@ -93,6 +95,7 @@ static int model_dims(int32_t kind, const void* model, int* dim) {
     case UBM_MODEL_ISING_PT: *dim = ((const ubm_model_ising_pt*)model)->nchains; return UBM_OK;
     case UBM_MODEL_PG_LOGISTIC: *dim = ((const ubm_model_pg_logistic*)model)->p; return UBM_OK;
     case UBM_MODEL_VARSEL: *dim = ((const ubm_model_varsel*)model)->p; return UBM_OK;
+    case UBM_MODEL_BLASSO: *dim = 2 * ((const ubm_model_blasso*)model)->p + 1; return UBM_OK;
     default: return UBM_ERR_UNSUPPORTED;
   }
 }
@@ -151,6 +154,20 @@ static int register_model(ubm_plan* p, int32_t kind, const void* model) {
     CU(cudaMemcpyAsync(p->model_blob.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     pg_bind_device(&p->pg, p->model_blob.as<double>());
+    return UBM_OK;
+  }
+  if (kind == UBM_MODEL_BLASSO) {
+    const ubm_model_blasso* s = (const ubm_model_blasso*)model;
+    if (s->p < 1 || s->p > PG_PLIM || s->n < 3 || s->n > 4096) return fail(h, UBM_ERR_INVALID, "bayesian lasso: 1 <= p <= 60, 3 <= n <= 4096");
+    if (!s->X || !s->Y) return fail(h, UBM_ERR_INVALID, "bayesian lasso: null data");
+    if (!(s->lambda > 0.0)) return fail(h, UBM_ERR_INVALID, "bayesian lasso: lambda > 0");
+    p->dim = 2 * s->p + 1;
+    std::vector<double> blob;
+    blasso_pack_host(s, &p->blasso, &blob);
+    CU(p->model_blob.alloc(blob.size() * sizeof(double)));
+    CU(cudaMemcpyAsync(p->model_blob.p, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    blasso_bind_device(&p->blasso, p->model_blob.as<double>());
     return UBM_OK;
   }
   if (kind == UBM_MODEL_VARSEL) {
@@ -321,6 +338,9 @@ static int plan_run(ubm_plan* p, int draws_mode, uint64_t seed, int64_t nrep, in
     if (stl != UBM_OK) return stl;
   } else if (p->model_kind == UBM_MODEL_PG_LOGISTIC) {
     int stl = pg_launch(p->pg, P, tape, nsm, st, &h->launches, &h->err);
+    if (stl != UBM_OK) return stl;
+  } else if (p->model_kind == UBM_MODEL_BLASSO) {
+    int stl = blasso_launch(p->blasso, P, tape, nsm, st, &h->launches, &h->err);
     if (stl != UBM_OK) return stl;
   } else if (p->model_kind == UBM_MODEL_ISING_PT) {
     int stl = ising_launch(p->ising, P, tape, nsm, st, &h->launches, &h->err);

@@ -54,8 +54,8 @@ __global__ void prim_scalar_coupling_kernel(const RunParams P, int mode, double 
 // 2: inverse Gaussian (a = mu, b = lambda).  R's rgamma is part of the R runtime, not of the reference: Gamma draws are
 // Marsaglia & Tsang (2000) on the typed streams (two draws per attempt; shape < 1 by the U^(1/shape) boost); lgamma
 // enters through the host-computed constants c = a log(b) - lgamma(a).
-template <bool TAPE>
-__device__ inline double prim_rgamma(double shape, double rate, ScalarDraws<TAPE>& D) {
+template <class DS>
+__device__ inline double prim_rgamma(double shape, double rate, DS& D) {
   const double a = shape < 1.0 ? shape + 1.0 : shape;
   const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
   double g = 0.0;
@@ -71,16 +71,16 @@ __device__ inline double prim_rgamma(double shape, double rate, ScalarDraws<TAPE
   if (shape < 1.0) g = g * ubm_exp(ubm_log(D.u()) / shape);
   return g / rate;
 }
-template <bool TAPE>
-__device__ inline double prim_rinvgaussian(double mu, double lambda, ScalarDraws<TAPE>& D) {   // src/inversegaussian.cpp:6-25
+template <class DS>
+__device__ inline double prim_rinvgaussian(double mu, double lambda, DS& D) {   // src/inversegaussian.cpp:6-25
   const double nu = D.n();
   const double z = D.u();
   double x = nu * nu;
   x = mu + mu * mu * x / (2. * lambda) - mu / (2. * lambda) * sqrt(4. * mu * lambda * x + mu * mu * x * x);
   return (z <= mu / (mu + x)) ? x : mu * mu / x;
 }
-template <bool TAPE>
-__device__ inline double prim_positive_draw(int kind, double a, double b, ScalarDraws<TAPE>& D, bool clamp) {
+template <class DS>
+__device__ inline double prim_positive_draw(int kind, double a, double b, DS& D, bool clamp) {
   if (kind == 0) return prim_rgamma(a, b, D);
   if (kind == 1) return 1.0 / prim_rgamma(a, b, D);
   const double v = prim_rinvgaussian(a, b, D);
@@ -90,6 +90,22 @@ __device__ inline double prim_positive_logpdf(int kind, double x, double a, doub
   if (kind == 0) return c + (a - 1.0) * ubm_log(x) - b * x;
   if (kind == 1) return c - (a + 1.0) * ubm_log(x) - b / x;   // R/invgamma_couplings.R:7-9
   return 0.5 * ubm_log(b / 6.283185) - 1.5 * ubm_log(x) - b * (x - a) * (x - a) / (2 * a * a * x);   // src/inversegaussian.cpp:27-29
+}
+// R/get_max_coupling.R:24-39 for the three families; returns `identical`
+template <class DS>
+__device__ inline bool prim_positive_max_coupling(int kind, double a1, double a2, double b1, double b2, double c1, double c2, DS& D,
+                                                  double* xo, double* yo) {
+  const double x = prim_positive_draw(kind, a1, b1, D, true);
+  *xo = x;
+  if (prim_positive_logpdf(kind, x, a1, b1, c1) + ubm_log(D.u()) < prim_positive_logpdf(kind, x, a2, b2, c2)) { *yo = x; return true; }
+  bool reject = true;
+  double y = 0.0;
+  while (reject && !D.bad) {
+    y = prim_positive_draw(kind, a2, b2, D, true);
+    reject = prim_positive_logpdf(kind, y, a2, b2, c2) + ubm_log(D.u()) < prim_positive_logpdf(kind, y, a1, b1, c1);
+  }
+  *yo = y;
+  return false;
 }
 // mode 0: out [n] plain draws of the first distribution; mode 1: out [n][2] maximally coupled pairs, ident [n]
 template <bool TAPE>
@@ -102,18 +118,8 @@ __global__ void prim_positive_coupling_kernel(const RunParams P, int kind, int m
   if (mode == 0) {
     out[i] = prim_positive_draw(kind, a1, b1, D, false);
   } else {
-    const double x = prim_positive_draw(kind, a1, b1, D, true);
-    double y = x;
-    bool id = true;
-    if (!(prim_positive_logpdf(kind, x, a1, b1, c1) + ubm_log(D.u()) < prim_positive_logpdf(kind, x, a2, b2, c2))) {
-      id = false;
-      bool reject = true;
-      y = 0.0;
-      while (reject && !D.bad) {
-        y = prim_positive_draw(kind, a2, b2, D, true);
-        reject = prim_positive_logpdf(kind, y, a2, b2, c2) + ubm_log(D.u()) < prim_positive_logpdf(kind, y, a1, b1, c1);
-      }
-    }
+    double x, y;
+    const bool id = prim_positive_max_coupling(kind, a1, a2, b1, b2, c1, c2, D, &x, &y);
     out[2 * i] = x; out[2 * i + 1] = y; ident[i] = id ? 1 : 0;
   }
   if (D.bad) atomicExch(P.status, UBM_ERR_TAPE);

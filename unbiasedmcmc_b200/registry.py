@@ -193,3 +193,24 @@ class VariableSelection(ModelSpec):
     def struct(self):
         return A.ubm_model_varsel(self.n, self.p, A.dptr(self.X), A.dptr(self.Y), self.g, self.kappa, self.s0, 0,
                                   self.proportion_singleflip)
+
+
+class BayesianLasso(ModelSpec):
+    """get_blasso(Y, X, lambda) (R/bayesianlasso.R:22): Gibbs sampler on (beta, tau2, sigma2) and its coupling
+    (src/blassoutil.cpp:17-88, rinversegamma_coupled, rinvgaussian_coupled).  Chain state c(beta, tau2, sigma2)."""
+    kind = A.UBM_MODEL_BLASSO
+
+    def __init__(self, Y, X, lam):
+        X = np.asarray(X, dtype=np.float64)
+        self.n, self.p = X.shape
+        if not (1 <= self.p <= 60 and 3 <= self.n <= 4096):
+            raise ValueError("Bayesian lasso: 3 <= n <= 4096, p <= 60")
+        self.dim = 2 * self.p + 1
+        self.X = _colmajor(X)
+        self.Y = _f64(Y).reshape(-1)
+        self.lam = float(lam)
+        if not self.lam > 0:
+            raise ValueError("Bayesian lasso: lambda > 0")
+
+    def struct(self):
+        return A.ubm_model_blasso(self.n, self.p, A.dptr(self.X), A.dptr(self.Y), self.lam)

@@ -122,6 +122,25 @@ def c5_model(n=500, p=1000, kappa=2.0, s0=100, snr=1.0, seed=SEED):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def blasso_data(n=120, p=8, seed=SEED):
+    """a diabetes-like standardised design (inst/reproducebayesianlasso uses lars::diabetes: n = 442, p = 10 / 64): columns
+    centred and scaled to unit norm, a sparse signal, Y centred"""
+    rng = np.random.default_rng(seed + 17)
+    X = rng.standard_normal((n, p))
+    X[:, 1::3] += 0.5 * X[:, [0]]
+    X = X - X.mean(0)
+    X = X / np.sqrt((X ** 2).sum(0))
+    beta = np.zeros(p)
+    beta[: max(p // 3, 1)] = 40.0 * rng.standard_normal(max(p // 3, 1))
+    Y = X @ beta + rng.standard_normal(n)
+    return Y - Y.mean(), X
+
+
+def blasso_model(n=120, p=8, lam=1.0, seed=SEED):
+    Y, X = blasso_data(n, p, seed)
+    return R.BayesianLasso(Y, X, lam)
+
+
 # bench workloads: the five BASELINE.json configs at the horizons the reference's scripts use (SURVEY.md §8d)
 # ---------------------------------------------------------------------------------------------------------------------
 KERNEL_OF = {"c1": "mix_driver_kernel", "c2": "mvn_driver_kernel", "c3": "pg_driver_kernel", "c4": "ising_driver_kernel",
