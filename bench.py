@@ -236,8 +236,8 @@ class Bench:
         res = None
         # one untimed call of a small batch first: the first host-buffer call of a process pays one-off costs (context-level
         # allocator growth, first touch of the pinned staging the driver keeps for pageable copies) that are not per step
-        self.eng.sample_unbiasedestimator(mdl, R.Draws(seed=W.SEED + 1), nrep=nrep, want_bins=False,
-                                          **{**kw, "k": kw["lag"] + 1, "m": kw["lag"] + 8})     # same buffers, a short horizon
+        self.eng.sample_unbiasedestimator(mdl, R.Draws(seed=W.SEED + 1), nrep=nrep, want_bins=False, max_iterations=kw["lag"] + 16,
+                                          **{**kw, "k": kw["lag"] + 1, "m": kw["lag"] + 8})     # same buffers, 16 capped iterations
         self.barrier()
         t0 = time.perf_counter()
         for s in range(steps):

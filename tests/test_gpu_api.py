@@ -81,3 +81,27 @@ def test_registry_models_through_the_api():
     assert r["uestimator"].shape == (64, 30) and incl[:10].mean() > 0.8 and abs(incl[10:].mean()) < 0.2
     c = api.rnorm_max_coupling(0.0, 1.0, 1.0, 1.0, n=1000, seed=2)
     assert c["xy"].shape == (1000, 2) and c["identical"].dtype == bool
+
+
+def test_round2_additions_through_the_api():
+    """get_blasso, the CRN beta-step, the positive-variable couplings and the covariance-form MVN helpers by their R names"""
+    from tests import cases
+    from unbiasedmcmc_b200 import api
+    Y, X = cases.blasso_data(120, 8)
+    ks = api.get_blasso(Y, X, 1.0)
+    r = api.sample_unbiasedestimator(ks["gibbs_kernel"], ks["coupled_gibbs_kernel"], ks["rinit"], k=20, m=100, nrep=64, seed=2)
+    assert r["uestimator"].shape == (64, 17) and np.isfinite(r["meetingtime"]).all()
+    ols = np.linalg.lstsq(X, Y, rcond=None)[0]
+    assert np.all(np.abs(r["uestimator"].mean(0)[:2] - ols[:2]) < 0.2 * np.abs(ols[:2]))      # strong signals: little shrinkage
+    Yc, Xc = cases.c3_data(150, 6, seed=2)
+    ks = api.logisticregression_kernels(Yc, Xc, np.zeros(6), 10 * np.eye(6), beta_coupling="crn")
+    assert np.isfinite(api.sample_meetingtime(ks["single_kernel"], ks["coupled_kernel"], ks["rinit"], nrep=16, seed=2)["meetingtime"]).all()
+    g = api.rgamma_coupled(2.0, 2.5, 1.0, 1.2, n=2000, seed=1)
+    assert g["xy"].shape == (2000, 2) and 0.5 < g["identical"].mean() < 1.0
+    ig = api.rinvgaussian_coupled(1.0, 1.1, 2.0, 2.0, n=500, seed=1)
+    assert np.all(ig["xy"] > 0)
+    S = np.array([[2.0, 0.3], [0.3, 1.0]])
+    x = api.fast_rmvnorm(4000, np.array([1.0, -1.0]), S, seed=3)
+    assert np.allclose(np.cov(x.T), S, atol=0.15) and np.allclose(x.mean(0), [1.0, -1.0], atol=0.1)
+    from scipy import stats
+    np.testing.assert_allclose(api.fast_dmvnorm(x[:5], np.array([1.0, -1.0]), S), stats.multivariate_normal([1.0, -1.0], S).logpdf(x[:5]), atol=1e-6)
