@@ -290,3 +290,14 @@ def test_c2_on_the_fly_bins_bit_exact(engine, oracle, d, comp):
     ch = engine.sample_coupled_chains(mdl, R.Draws(seed=21), m=60, lag=3, stride=stride, nrep=nrep, rep_offset=3)
     stored = engine.estimator_bins(ch, bins, k=10, m=60)
     assert np.array_equal(stored, g["bins"])
+
+
+@pytest.mark.parametrize("d", [3, 9, 31, 128])
+def test_c2_edge_dimensions_bit_exact(engine, oracle, d):
+    """dimensions that are not multiples of the 4-wide k steps / 8-wide output tiles of the tensor-core phases, and the
+    largest supported one"""
+    mdl = cases.c2_model(d, "dense", "offset")
+    kw = dict(h_kind=A.UBM_H_IDENTITY, k=3, m=25, lag=2, nrep=40 if d < 128 else 24, max_iterations=4000)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=8), **kw)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=8), nthreads=8, **kw)
+    assert_same(g, c, ["meetingtime", "iteration", "cost", "uestimator", "mcmcestimator", "correction", "summary"])

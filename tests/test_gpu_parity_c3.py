@@ -141,3 +141,14 @@ def test_c3_common_random_number_beta_step_bit_exact(engine, oracle, lag, h):
         n = int(ch_c["iteration"][r]) + 1
         assert np.array_equal(ch_g["samples1"][r, :n], ch_c["samples1"][r, :n])
         assert np.array_equal(ch_g["samples2"][r, :n - lag], ch_c["samples2"][r, :n - lag])
+
+
+@pytest.mark.parametrize("n,p", [(90, 57), (130, 60), (64, 1), (33, 9)])
+def test_c3_edge_sizes_bit_exact(engine, oracle, n, p):
+    """p above 56 takes the 8 x 8 tile lists of nine tiles per warp in the Gram build, p = 60 is the largest supported;
+    p = 1 and a number of observations that is not a multiple of the 4-observation groups or of the 32-row tiles"""
+    mdl = cases.c3_model(n, p, seed=4)
+    kw = dict(k=2, m=12, lag=1, nrep=6, max_iterations=400)
+    g = engine.sample_unbiasedestimator(mdl, R.Draws(seed=6), **kw)
+    c = oracle.sample_unbiasedestimator(mdl, R.Draws(seed=6), nthreads=8, **kw)
+    assert_same(g, c, KEYS)
