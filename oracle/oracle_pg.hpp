@@ -178,7 +178,6 @@ struct PgLogisticModel {
   std::vector<double> invB;     // p x p column-major  (logisticregression_precomputation, R/logistic_regression.R:34-50)
   std::vector<double> ktk;      // KTkappaplusinvBtimesb = X^T (Y - 1/2) + invB b
   std::vector<double> b, cholB; // prior mean, upper Cholesky factor of B (rinit: fast_rmvnorm(1, b, B))
-  std::vector<double> Zprod;    // Zprod[i][e] = X(i,j1) X(i,j2), e = index of (j1 <= j2) in column-of-j1-major order
 
   static void chol_lower(std::vector<double>& A, int p, bool* ok) {   // in place: lower triangle becomes L, A = L L^T
     for (int j = 0; j < p; ++j) {
@@ -214,13 +213,6 @@ struct PgLogisticModel {
       for (int i = 0; i < n; ++i) acc = ubm_fma(X[(size_t)j * n + i], s->Y[i] - 0.5, acc);
       for (int k = 0; k < p; ++k) acc = ubm_fma(invB[(size_t)k * p + j], b[k], acc);
       ktk[j] = acc;
-    }
-    const int ne = p * (p + 1) / 2;
-    Zprod.assign((size_t)n * ne, 0.0);
-    for (int i = 0; i < n; ++i) {
-      int e = 0;
-      for (int j1 = 0; j1 < p; ++j1)
-        for (int j2 = j1; j2 < p; ++j2) Zprod[(size_t)i * ne + e++] = X[(size_t)j1 * n + i] * X[(size_t)j2 * n + i];
     }
   }
   int dim() const { return p; }
@@ -266,12 +258,10 @@ struct PgLogisticModel {
   struct MS { std::vector<double> m, L, Linv; };
   // m_sigma_function_ — src/logisticregression.cpp:32-56
   MS m_sigma(const std::vector<double>& omega) const {
-    const int ne = p * (p + 1) / 2;
     MS r;
     r.L.assign((size_t)p * p, 0.0);
-    int e = 0;
     for (int j1 = 0; j1 < p; ++j1)
-      for (int j2 = j1; j2 < p; ++j2, ++e) {
+      for (int j2 = j1; j2 < p; ++j2) {
         // :42-45.  Canonical order: four chains over the groups of four observations (class (i / 4) mod 4), each sequential
         // in i, every term one fma of the rounded X(i,j1) omega(i) with X(i,j2); added to invB in turn.  (What a chain
         // of FP64 tensor-core m8n8k4 operations computes; the reference sums (X X) omega sequentially.)

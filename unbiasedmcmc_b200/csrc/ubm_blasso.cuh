@@ -76,8 +76,8 @@ struct BlDraws {
 struct BlShared {
   long long rep;
   unsigned long long in, iu;
-  double rate[2], rssw[2][16];
-  int bad, same, ident_prop;
+  double rssw[2][16];
+  int bad;
 };
 
 // A^-1 XtY and the lower factor of sigma2 A^-1 for one or two chains (src/blassoutil.cpp:21-30): A_c in MA_c, work MB_c
