@@ -186,7 +186,7 @@ def bench_spec(name):
             sum_tau, sum_iter = S[2], S[5]
             site_updates = 0.99 * 16 * 1024 * (sum_iter + (sum_tau - S[0]))
             return 25.0 * site_updates
-        return dict(model=mdl, kw=kw, nrep=2368, desc=desc, flops=flops, bound="int32", cpu_one_wave=True)
+        return dict(model=mdl, kw=kw, nrep=4736, desc=desc, flops=flops, bound="int32", cpu_one_wave=True)
     if name == "c3":
         mdl = c3_credit_like_model()
         n, p_ = 1000, 49
