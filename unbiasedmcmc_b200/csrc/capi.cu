@@ -12,6 +12,7 @@
 #include "ubm_common.cuh"
 #include "ubm_mix.cuh"
 #include "ubm_mvn.cuh"
+#include "ubm_mvn_single.cuh"
 #include "ubm_ising.cuh"
 #include "ubm_pg.cuh"
 #include "ubm_varsel.cuh"
@@ -331,7 +332,10 @@ static int plan_run(ubm_plan* p, int draws_mode, uint64_t seed, int64_t nrep, in
     kern<<<grid, threads, smem, st>>>(p->mix, P);
     h->launches += 1;
   } else if (p->model_kind == UBM_MODEL_MVN) {
-    int stl = mvn_launch(p->mvn, P, tape, nsm, st, p->scratch, &h->launches, &h->err);
+    // estimator runs on Philox streams take two passes: coupled phase, then the single-chain continuation with twice the slots
+    const bool two_pass = p->mode == MODE_ESTIMATOR && !tape && mvn_two_pass_fits(p->mvn, P) && !getenv("UBM_MVN_ONE_PASS");
+    int stl = two_pass ? mvn_launch_two_pass(p->mvn, P, nsm, st, p->scratch, &h->launches, &h->err)
+                       : mvn_launch(p->mvn, P, tape, nsm, st, p->scratch, &h->launches, &h->err);
     if (stl != UBM_OK) return stl;
   } else if (p->model_kind == UBM_MODEL_VARSEL) {
     int stl = varsel_launch(p->varsel, P, tape, nsm, st, p->scratch, &h->launches, &h->err);

@@ -38,6 +38,13 @@ struct RunParams {
   unsigned long long* work_counter;   // replicate hand-out
   int* status;                        // sticky: UBM_ERR_TAPE
   long long* pt_counts;               // Ising PT: [0] swap-move iterations, [1 .. N-1] accepted swaps of chain 1, [N .. 2N-2] of chain 2
+  // C2 estimator runs in two passes (ubm_mvn.cuh: coupled phase, ubm_mvn_single.cuh: single-chain continuation).  The hand-off
+  // record of a replicate that has met but not reached its horizon lives in its own, not yet final, output rows: state in
+  // uest[rep], mcmc / correction numerators in mcmc[rep] / corr[rep], log-density in cost[rep], time in iter[rep], tau in
+  // tau[rep]; plus the two draw counters below.  Null pointers = one pass.
+  long long* ho_int;                  // [nrep][2]  next uniform, next normal
+  int* ho_list;                       // [nrep]     replicates to continue, in hand-off order
+  unsigned long long* ho_count;       // number of entries of ho_list
 };
 
 // weight of Delta_t in H_{k:m}: floor((t-k)/lag) - ceiling(max(lag, t-m)/lag) + 1

@@ -460,7 +460,33 @@ __global__ void __launch_bounds__(MVN_T) mvn_driver_kernel(const MvnDevice M, co
         }
         if (ph == SL_INIT) finished = false;
         if (lane == 0) S.in[s] += (ph == SL_INIT) ? 2 * d : d;          // normals consumed by the step just finished
-        if (finished) {
+        if (P.ho_int && P.mode == MODE_ESTIMATOR && met && !finished && ph != SL_INIT) {
+          // two-pass run: the replicate has met and still has single-chain steps to its horizon — it continues in the
+          // single-chain kernel (ubm_mvn_single.cuh) from this record (kept in its own output rows, see RunParams), and the
+          // slot is free for the next coupled pair
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = lane + 32 * i;
+            if (j < d) {
+              P.uest[rep * dimh + j] = sm.X1[s * DPS + j];
+#pragma unroll
+              for (int hh = 0; hh < NH; ++hh) {
+                P.mcmc[rep * dimh + hh * d + j] = am[hh][i];
+                P.corr[rep * dimh + hh * d + j] = ac[hh][i];
+              }
+            }
+          }
+          if (lane == 0) {
+            P.cost[rep] = S.pdf1[s];
+            P.iter[rep] = time; P.tau[rep] = (double)S.tau[s];
+            P.ho_int[rep * 2 + 0] = (long long)S.iu[s]; P.ho_int[rep * 2 + 1] = (long long)S.in[s];
+            __threadfence();
+            const unsigned long long q = atomicAdd(P.ho_count, 1ull);
+            P.ho_list[q] = (int)rep;
+          }
+          ph = SL_IDLE;
+        } else if (finished) {
           if (lane == 0) {
             const long long tt = S.tau[s];
             double cost = dinf();
