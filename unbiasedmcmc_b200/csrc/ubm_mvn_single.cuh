@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(MVN_T) mvn_single_kernel(const MvnDevice M, co
   double bin_b0 = 0.0, bin_iw = 0.0;
   if (nbins) { bin_b0 = P.breaks[0]; bin_iw = (double)nbins / (P.breaks[nbins] - P.breaks[0]); }
   const unsigned long long ntodo = *P.ho_count;
-  int cur = 0;
+  int cur = 0, stepno = 0;
   // MCMC numerators of this warp's two slots (slots warp and warp + 16): coordinate j = lane + 32 i, test-function block hh
   double am[2][NH][4];
 #pragma unroll
@@ -74,7 +74,16 @@ __global__ void __launch_bounds__(MVN_T) mvn_single_kernel(const MvnDevice M, co
       for (int i = 0; i < 4; ++i) am[u][hh][i] = 0.0;
   const int kq = lane & 3;
 
+#ifdef UBM_MVN_TIMING
+  long long ta[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tn = 0, tp = clock64();
+#define SMARK(i) do { long long now_ = clock64(); ta[i] += now_ - tp; tp = now_; } while (0)
+#else
+#define SMARK(i) do { } while (0)
+#endif
   for (;;) {
+#ifdef UBM_MVN_TIMING
+    tp = clock64(); tn++;
+#endif
     double* XIc = XI + cur * MVS_R * DPS;          // this step's rows (normals -> proposals)
     double* XIn = XI + (cur ^ 1) * MVS_R * DPS;    // filled by the producers for the next step ...
     const double* XIp = XIn;                       // ... and, until barrier 1, still holding the proposals of the step just computed
@@ -183,8 +192,10 @@ __global__ void __launch_bounds__(MVN_T) mvn_single_kernel(const MvnDevice M, co
       if (ph != MS_IDLE) my_active = 1;
     }
     if (tid == 0) S.draw_next = 0;
+    SMARK(0);
     const int any_active = __syncthreads_or(my_active);      // CTA barrier 1: phases of this step are published
     if (!any_active) break;
+    SMARK(1);
     // the d normals of the NEXT step of every live slot: 32 independent jobs handed out through a shared counter — to the
     // producer warps from the start of the step, to the consumer warps once their GEMM phases are done (with 32 slots the
     // draws, not the GEMMs, are the longer half of a step)
@@ -241,6 +252,7 @@ __global__ void __launch_bounds__(MVN_T) mvn_single_kernel(const MvnDevice M, co
           }
         }
         consumer_bar();
+        SMARK(2);
         // ------------------------------------------------------------ w = Cinv_pi^T (prop - mean), |w|^2 per 4-column group
         for (int jb = 0; jb < MVN_JMAX; ++jb) {
           const int jt = M.jobs[cw][jb];
@@ -257,7 +269,9 @@ __global__ void __launch_bounds__(MVN_T) mvn_single_kernel(const MvnDevice M, co
           }
         }
       }
+      SMARK(3);
       draw_jobs();
+      SMARK(4);
     } else {
       // ================================================================ PRODUCERS (warps 8-15): draws of the NEXT step
       const int pw = warp - MVN_CW;
@@ -266,19 +280,32 @@ __global__ void __launch_bounds__(MVN_T) mvn_single_kernel(const MvnDevice M, co
         const bool on = S.phase[s] != MS_IDLE;
         unsigned long long pu = 0, target = 0;
         bool past_end = false;
+        // a step consumes one log-uniform; the ring is topped up to six ahead every fourth step (or when a slot has fewer
+        // than two left), so that the dependent Philox + log chain is paid once per four steps with four lanes busy
         if (on) {
-          pu = S.pu[s]; target = S.iu[s] + 6;
+          pu = S.pu[s];
+          const unsigned long long iu = S.iu[s];
+          if ((stepno & 3) == 0 || pu < iu + 2) target = iu + 6;
           const unsigned long long idx = pu + l8;
           if (idx < target) LU[s * 8 + (int)(idx & 7ull)] = ubm_log(draw_u_at<false>(P, S.rep[s], idx, &past_end));
         }
         __syncwarp();
         if (on && l8 == 0 && target > pu) S.pu[s] = target;
       }
+      SMARK(3);
       draw_jobs();
+      SMARK(4);
     }
     __syncthreads();      // CTA barrier 2: step computed, draws of the next step in place
-    cur ^= 1;
+    SMARK(5);
+    cur ^= 1; ++stepno;
   }
+#ifdef UBM_MVN_TIMING
+  if (blockIdx.x == 0 && (tid == 0 || tid == 256))
+    printf("mvn single timing (cycles/step, block 0, warp %d): steps %lld | slots %.0f barrier1 %.0f | %s %.0f, %s %.0f | draw queue %.0f | barrier2 %.0f\n",
+           warp, tn, (double)ta[0] / tn, (double)ta[1] / tn, warp ? "-" : "phase B", (double)ta[2] / tn, warp ? "log-uniform ring" : "phase C",
+           (double)ta[3] / tn, (double)ta[4] / tn, (double)ta[5] / tn);
+#endif
 }
 
 // the two-pass launch of an estimator run: coupled pass (hand-off at the meeting), then the single-chain continuation
