@@ -128,6 +128,22 @@ __device__ __forceinline__ double warp_butterfly(double v) {
   return v;
 }
 
+// position of the (r + 1)-th set bit of m (r < popc(m)): a five-level popcount descent (__fns is a software loop, 5 % of the
+// stall samples of the single-chain kernel)
+__device__ __forceinline__ int mvn_nth_set_bit(unsigned m, int r) {
+  int pos = 0;
+  int c = __popc(m & 0xffffu);
+  if (r >= c) { r -= c; pos = 16; m >>= 16; }
+  c = __popc(m & 0xffu);
+  if (r >= c) { r -= c; pos += 8; m >>= 8; }
+  c = __popc(m & 0xfu);
+  if (r >= c) { r -= c; pos += 4; m >>= 4; }
+  c = __popc(m & 0x3u);
+  if (r >= c) { r -= c; pos += 2; m >>= 2; }
+  if (r >= (int)(m & 1u)) pos += 1;
+  return pos;
+}
+
 // Standard normals i0 + 4 lane .. + 3 of a replicate's N stream, written to row[4 lane .. 4 lane + 3] (shared memory;
 // entries past nvalid are zeroed, lanes with nvalid <= 0 write nothing), executed by a whole warp.  AS241's central
 // branch is evaluated in place; the ~15 % of draws that fall in the tails are COMPACTED over the warp (ballot + rank),
@@ -178,7 +194,7 @@ __device__ __forceinline__ void draw_n4_warp(const RunParams& P, long long rep, 
     const int c = (i < n0) ? 0 : (i < n1) ? 1 : (i < n2) ? 2 : 3;
     const int rank = i - ((c == 0) ? 0 : (c == 1) ? n0 : (c == 2) ? n1 : n2);
     const unsigned m = (c == 0) ? bal[0] : (c == 1) ? bal[1] : (c == 2) ? bal[2] : bal[3];
-    const int src = (i < n3) ? (int)__fns(m, 0, rank + 1) : 0;
+    const int src = (i < n3) ? mvn_nth_set_bit(m, rank) : 0;
     const double p0 = __shfl_sync(0xffffffffu, pr[0], src), p1 = __shfl_sync(0xffffffffu, pr[1], src);
     const double p2 = __shfl_sync(0xffffffffu, pr[2], src), p3 = __shfl_sync(0xffffffffu, pr[3], src);
     if (i < n3) {
