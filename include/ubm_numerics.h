@@ -70,9 +70,8 @@ typedef struct { uint32_t w[4]; } ubm_u32x4;
 
 UBM_HD void ubm_mulhilo32(uint32_t a, uint32_t b, uint32_t* hi, uint32_t* lo) {
 #if defined(__CUDA_ARCH__)
-  const unsigned long long p = (unsigned long long)a * (unsigned long long)b;   /* one IMAD.WIDE instead of IMAD.HI + IMAD */
-  *hi = (uint32_t)(p >> 32);
-  *lo = (uint32_t)p;
+  *hi = __umulhi(a, b);
+  *lo = a * b;
 #else
   uint64_t p = (uint64_t)a * (uint64_t)b;
   *hi = (uint32_t)(p >> 32);
@@ -119,15 +118,8 @@ UBM_HD ubm_u32x4 ubm_stream_block(uint64_t seed, uint64_t rep, uint32_t type, ui
 UBM_HD double ubm_u01_32(uint32_t w) { return ((double)w + 0.5) * 2.3283064365386962890625e-10; }
 /* 53-bit version from two words, also exact and strictly inside (0,1). */
 UBM_HD double ubm_u01_53(uint32_t hi, uint32_t lo) {
-#if defined(__CUDA_ARCH__)
-  /* integer -> double through the 2^52 magic number: exact for these 27- and 26-bit integers, one add on the FP64 pipe
-   * instead of a conversion instruction (quarter rate) */
-  double a = __hiloint2double(0x43300000, (int)(hi >> 5)) - 4503599627370496.0;
-  double b = __hiloint2double(0x43300000, (int)(lo >> 6)) - 4503599627370496.0;
-#else
   double a = (double)(hi >> 5);  /* 27 bits */
   double b = (double)(lo >> 6);  /* 26 bits */
-#endif
   return (a * 67108864.0 + b + 0.5) * 1.1102230246251565404236316680908203125e-16; /* 2^-53 */
 }
 
