@@ -144,21 +144,14 @@ __device__ __forceinline__ int mvn_nth_set_bit(unsigned m, int r) {
   return pos;
 }
 
-// Standard normals i0 + 4 lane .. + 3 of a replicate's N stream, written to row[4 lane .. 4 lane + 3] (shared memory;
-// entries past nvalid are zeroed, lanes with nvalid <= 0 write nothing), executed by a whole warp.  AS241's central
-// branch is evaluated in place; the ~15 % of draws that fall in the tails are COMPACTED over the warp (ballot + rank),
-// so that the log/sqrt branch runs once per warp for up to 32 tail draws instead of once per tail draw of the
-// unluckiest lane.
-template <bool TAPE>
-__device__ __forceinline__ void draw_n4_warp(const RunParams& P, long long rep, unsigned long long i0, int nvalid,
-                                             double* __restrict__ row, int lane, bool* bad) {
-  if (TAPE) {
-    if (nvalid > 0) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) row[4 * lane + c] = (c < nvalid) ? draw_n_at<true>(P, rep, i0 + c, bad) : 0.0;
-    }
-    return;
-  }
+// Four standard normals per lane: draws i0 .. i0 + 3 of replicate `rep`'s N stream (both per lane: the lanes of a warp may
+// serve different replicates), written to dst[0..3] (shared memory; entries past nvalid are zeroed, lanes with nvalid <= 0 write
+// nothing), executed by a whole warp.  AS241's central branch is evaluated in place for all four draws, branch-free: eight
+// independent Horner chains (numerator, denominator) keep the FP64 pipe busy instead of one dependent chain at a time; the
+// ~15 % of draws that fall in the tails are COMPACTED over the warp (ballot + rank), so that the log/sqrt branch runs once per
+// warp for up to 32 tail draws instead of once per tail draw of the unluckiest lane.
+__device__ __forceinline__ void draw_n4_lanes(const RunParams& P, long long rep, unsigned long long i0, int nvalid,
+                                              double* dst, int lane) {
   const uint64_t grep = (uint64_t)(P.rep_offset + rep);
   double pr[4] = {0.5, 0.5, 0.5, 0.5};
   if (nvalid > 0) {
@@ -174,8 +167,6 @@ __device__ __forceinline__ void draw_n4_warp(const RunParams& P, long long rep, 
       pr[2] = ubm_u01_53(A1.w[0], A1.w[1]); pr[3] = ubm_u01_53(A1.w[2], A1.w[3]);
     }
   }
-  // the central branch of all four draws, branch-free: eight independent Horner chains (numerator, denominator) keep the
-  // FP64 pipe busy instead of one dependent chain at a time; the few tail draws are overwritten below
   double zc[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) zc[c] = ubm_qnorm_central(pr[c] - 0.5);
@@ -185,10 +176,11 @@ __device__ __forceinline__ void draw_n4_warp(const RunParams& P, long long rep, 
     const double q = pr[c] - 0.5;
     const bool valid = c < nvalid;
     const bool tail = valid && !(fabs(q) <= 0.425);
-    if (nvalid > 0 && !tail) row[4 * lane + c] = valid ? zc[c] : 0.0;
+    if (nvalid > 0 && !tail) dst[c] = valid ? zc[c] : 0.0;
     bal[c] = __ballot_sync(0xffffffffu, tail);
   }
   const int n0 = __popc(bal[0]), n1 = n0 + __popc(bal[1]), n2 = n1 + __popc(bal[2]), n3 = n2 + __popc(bal[3]);
+  const unsigned long long dsta = (unsigned long long)dst;
   for (int first = 0; first < n3; first += 32) {      // one pass unless more than 32 of the 4 x 32 draws are in the tails
     const int i = first + lane;
     const int c = (i < n0) ? 0 : (i < n1) ? 1 : (i < n2) ? 2 : 3;
@@ -197,11 +189,25 @@ __device__ __forceinline__ void draw_n4_warp(const RunParams& P, long long rep, 
     const int src = (i < n3) ? mvn_nth_set_bit(m, rank) : 0;
     const double p0 = __shfl_sync(0xffffffffu, pr[0], src), p1 = __shfl_sync(0xffffffffu, pr[1], src);
     const double p2 = __shfl_sync(0xffffffffu, pr[2], src), p3 = __shfl_sync(0xffffffffu, pr[3], src);
+    double* const dsrc = (double*)__shfl_sync(0xffffffffu, dsta, src);
     if (i < n3) {
       const double pc = (c == 0) ? p0 : (c == 1) ? p1 : (c == 2) ? p2 : p3;
-      row[4 * src + c] = ubm_qnorm_tail(pc, pc - 0.5);
+      dsrc[c] = ubm_qnorm_tail(pc, pc - 0.5);
     }
   }
+}
+// the same for one row: draws i0 + 4 lane .. + 3 of one replicate go to row[4 lane .. 4 lane + 3]
+template <bool TAPE>
+__device__ __forceinline__ void draw_n4_warp(const RunParams& P, long long rep, unsigned long long i0, int nvalid,
+                                             double* __restrict__ row, int lane, bool* bad) {
+  if (TAPE) {
+    if (nvalid > 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) row[4 * lane + c] = (c < nvalid) ? draw_n_at<true>(P, rep, i0 + c, bad) : 0.0;
+    }
+    return;
+  }
+  draw_n4_lanes(P, rep, i0, nvalid, row + 4 * lane, lane);
 }
 
 struct MvnSmem {

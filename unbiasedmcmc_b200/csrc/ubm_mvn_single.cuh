@@ -199,18 +199,22 @@ __global__ void __launch_bounds__(MVN_T) mvn_single_kernel(const MvnDevice M, co
     // the d normals of the NEXT step of every live slot: 32 independent jobs handed out through a shared counter — to the
     // producer warps from the start of the step, to the consumer warps once their GEMM phases are done (with 32 slots the
     // draws, not the GEMMs, are the longer half of a step)
+    // A job is 128 consecutive draws of the concatenation of the 32 rows (row length 4 nCG, 100 at d = 100): 25 jobs instead
+    // of 32 row-sized ones with a quarter of the lanes idle; a lane's four draws never straddle two rows.
     auto draw_jobs = [&]() {
+      const int D4 = 4 * nCG, njobs = (MVS_R * D4 + 127) >> 7;
       for (;;) {
-        int s = 0;
-        if (lane == 0) s = atomicAdd(&S.draw_next, 1);
-        s = __shfl_sync(FULL, s, 0);
-        if (s >= MVS_R) break;
-        const int ph = S.phase[s];
-        if (ph == MS_IDLE) continue;
-        const unsigned long long base = (ph == MS_RESUME) ? S.in[s] : S.in[s] + d;
-        bool past_end = false;
-        const int nvalid = (lane < nCG) ? d - 4 * lane : 0;
-        draw_n4_warp<false>(P, S.rep[s], base + 4 * lane, nvalid, XIn + s * DPS, lane, &past_end);
+        int job = 0;
+        if (lane == 0) job = atomicAdd(&S.draw_next, 1);
+        job = __shfl_sync(FULL, job, 0);
+        if (job >= njobs) break;
+        const int g = 128 * job + 4 * lane;
+        const int s = g / D4, o = g - s * D4;
+        const int ph = (s < MVS_R) ? S.phase[s] : MS_IDLE;
+        const bool on = ph != MS_IDLE;
+        const int sc = on ? s : 0;
+        const unsigned long long base = (ph == MS_RESUME) ? S.in[sc] : S.in[sc] + d;
+        draw_n4_lanes(P, S.rep[sc], base + (unsigned)o, on ? d - o : 0, XIn + sc * DPS + o, lane);
       }
     };
 
